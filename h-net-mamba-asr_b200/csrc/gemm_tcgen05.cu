@@ -1,0 +1,329 @@
+// bf16 GEMM on tcgen05 tensor cores: TMA (SWIZZLE_128B) -> 3-stage smem ring -> tcgen05.mma (128x128x16,
+// fp32 accumulator in TMEM) -> tcgen05.ld epilogue with fused bias / residual / dtype cast / split-K atomics.
+// Serves the in/out projections of the mixer (both directions fused into one GEMM each), the router
+// W_q|W_k projection, proj_in/proj_out, and every dgrad / wgrad of those.
+//
+//   C[M,N] = A(M,K) . B(N,K)^T      A: K-major [M,K] or MN-major [K,M];  B: K-major [N,K] or MN-major [K,N]
+//
+// One 128x128 output tile per CTA, 128 threads, 2 CTAs per SM (96 KB smem, 128 TMEM columns each) so that one
+// CTA's epilogue overlaps the other's main loop.  Warp 0 lane 0 drives TMA, warp 1 lane 0 issues MMAs, all four
+// warps drain TMEM (warp w owns TMEM lanes [32w, 32w+32)).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hnb {
+
+PFN_tmapEncodeTiled get_tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return HNB_ERR_CUDA; }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base %p dims %llu,%llu stride %llu box %u,%u", (int)r, base,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0);
+    return HNB_ERR_CUDA;
+  }
+  return HNB_OK;
+}
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int TILE_BYTES = 128 * BK * 2;                    // 16 KB per operand per stage
+constexpr int GEMM_SMEM = STAGES * 2 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  int M, N, K;
+  int kblocks_per_split;
+  const float* bias;
+  const void* R;
+  long long ldr;
+  void* C;
+  long long ldc;
+  int c_is_f32;
+  int atomic;
+};
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(128, 2)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * STAGES * TILE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * p.kblocks_per_split;
+  const int kb1 = min(kb0 + p.kblocks_per_split, total_kb);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmA);
+    umma::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    umma::mbar_init(accum_full, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc(tmem_slot, BN);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0 && lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        umma::mbar_wait(&empty[s], ph ^ 1);
+        umma::mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+        const int k0 = (kb0 + i) * BK;
+        uint8_t* a = sA + s * TILE_BYTES;
+        uint8_t* b = sB + s * TILE_BYTES;
+        if (TA == 0) {
+          umma::tma_load_2d(a, &tmA, &full[s], k0, m0);                    // box {64 k, 128 m}
+        } else {
+          umma::tma_load_2d(a, &tmA, &full[s], m0, k0);                    // box {64 m, 64 k} x 2
+          umma::tma_load_2d(a + TILE_BYTES / 2, &tmA, &full[s], m0 + 64, k0);
+        }
+        if (TB == 0) {
+          umma::tma_load_2d(b, &tmB, &full[s], k0, n0);
+        } else {
+          umma::tma_load_2d(b, &tmB, &full[s], n0, k0);
+          umma::tma_load_2d(b + TILE_BYTES / 2, &tmB, &full[s], n0 + 64, k0);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = umma::make_idesc_bf16(BM, BN, TA, TB);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        umma::mbar_wait(&full[s], ph);
+        umma::tc_fence_after();
+        const uint32_t a = umma::smem_u32(sA + s * TILE_BYTES);
+        const uint32_t b = umma::smem_u32(sB + s * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = (TA == 0) ? umma::make_smem_desc(a + k * 32, 16, 1024)
+                                        : umma::make_smem_desc(a + k * 2048, TILE_BYTES / 2, 1024);
+          const uint64_t db = (TB == 0) ? umma::make_smem_desc(b + k * 32, 16, 1024)
+                                        : umma::make_smem_desc(b + k * 2048, TILE_BYTES / 2, 1024);
+          umma::mma_bf16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma::mma_commit(&empty[s]);                                       // frees the smem slot when the MMAs retire
+      }
+      umma::mma_commit(accum_full);
+    }
+  }
+  __syncwarp();
+
+  // ---------------- epilogue: TMEM -> registers -> global ----------------
+  if (nkb > 0) {
+    umma::mbar_wait(accum_full, 0);
+    umma::tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      umma::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      umma::tmem_ld_wait();
+      const int col0 = n0 + c0;
+      if (row_ok && col0 < p.N) {
+        const int ncols = min(32, p.N - col0);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += p.bias[col0 + j];
+        }
+        if (p.atomic) {
+          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(c + j, v[j]);
+        } else if (p.c_is_f32) {
+          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+          const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
+          const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0) &&
+                           (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (r) { const float4 t = *reinterpret_cast<const float4*>(r + j); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              *reinterpret_cast<float4*>(c + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = v[j] + (r ? r[j] : 0.f);
+          }
+        } else {
+          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+          const __nv_bfloat16* r = p.R ? reinterpret_cast<const __nv_bfloat16*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
+          const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0) &&
+                           (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = v[j + e];
+              if (r) {
+                float t[8];
+                ldv<__nv_bfloat16, 8>(r + j, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += t[e];
+              }
+              stv<__nv_bfloat16, 8>(c + j, o);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = __float2bfloat16_rn(v[j] + (r ? __bfloat162float(r[j]) : 0.f));
+          }
+        }
+      }
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem_d, BN);
+}
+
+// naive reference for the self test
+__global__ void ref_gemm_kernel(const __nv_bfloat16* A, long long lda, int ta, const __nv_bfloat16* B, long long ldb,
+                                int tb, int M, int N, int K, float* C) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float a = __bfloat162float(ta ? A[(long long)k * lda + m] : A[(long long)m * lda + k]);
+    const float b = __bfloat162float(tb ? B[(long long)k * ldb + n] : B[(long long)n * ldb + k]);
+    acc += a * b;
+  }
+  C[(long long)m * N + n] = acc;
+}
+__global__ void fill_kernel(__nv_bfloat16* p, long long n, unsigned seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned x = (unsigned)i * 2654435761u + seed;
+  x ^= x >> 13; x *= 0x5bd1e995u; x ^= x >> 15;
+  p[i] = __float2bfloat16_rn(((int)(x & 0xffff) - 32768) / 32768.f);
+}
+__global__ void maxdiff_kernel(const float* a, const float* b, long long n, float* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = fabsf(a[i] - b[i]);
+  atomicMax(reinterpret_cast<int*>(out), __float_as_int(d));            // d >= 0: int order == float order
+}
+
+}  // namespace
+}  // namespace hnb
+
+using namespace hnb;
+
+extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const void* B, long long ldb, int transB, int M,
+                             int N, int K, const float* bias, const void* R, long long ldr, void* C, long long ldc,
+                             int c_dtype, int splitk, void* stream) {
+  HNB_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_bf16: bad arguments");
+  HNB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
+  HNB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                "gemm_bf16: operands must be 16-byte aligned");
+  HNB_CHECK_ARG(c_dtype == HNB_F32 || c_dtype == HNB_BF16, "gemm_bf16: bad output dtype");
+  if (splitk < 1) splitk = 1;
+  HNB_CHECK_ARG(splitk == 1 || (c_dtype == HNB_F32 && !bias && !R), "gemm_bf16: split-K needs fp32 C and no bias/residual");
+  CUtensorMap tmA, tmB;
+  int rc;
+  {
+    uint64_t dims[2], st[1];
+    uint32_t box[2];
+    if (!transA) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)M; box[0] = BK; box[1] = BM; }
+    else         { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
+    st[0] = (uint64_t)lda * 2;
+    if ((rc = make_tmap_bf16(&tmA, A, 2, dims, st, box))) return rc;
+    if (!transB) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = BN; }
+    else         { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
+    st[0] = (uint64_t)ldb * 2;
+    if ((rc = make_tmap_bf16(&tmB, B, 2, dims, st, box))) return rc;
+  }
+  const int total_kb = cdiv(K, BK);
+  if (splitk > total_kb) splitk = total_kb;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.kblocks_per_split = cdiv(total_kb, splitk);
+  splitk = cdiv(total_kb, p.kblocks_per_split);
+  p.bias = bias; p.R = R; p.ldr = ldr; p.C = C; p.ldc = ldc;
+  p.c_is_f32 = (c_dtype == HNB_F32);
+  p.atomic = splitk > 1;
+  dim3 grid(cdiv(N, BN), cdiv(M, BM), splitk);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(TA, TB)                                                                                              \
+  do {                                                                                                              \
+    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
+    gemm_bf16_kernel<TA, TB><<<grid, 128, GEMM_SMEM, st>>>(tmA, tmB, p);                                            \
+  } while (0)
+  if (!transA && !transB) LAUNCH(0, 0);
+  else if (!transA && transB) LAUNCH(0, 1);
+  else if (transA && !transB) LAUNCH(1, 0);
+  else LAUNCH(1, 1);
+#undef LAUNCH
+  HNB_LAUNCH_CHECK("gemm_bf16");
+  return HNB_OK;
+}
+
+// Runs the four operand-major combinations (with ragged M, N, K tails, a bias/residual epilogue and a split-K
+// case) against a naive kernel.  Allocates scratch with cudaMalloc: diagnostic entry point, not a hot-path call.
+extern "C" int hnb_umma_selftest(float* max_abs_err_host, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = 328, N = 200, K = 424;                         // tails in every dimension
+  const long long lda = 432, ldb = 432;                        // covers both [M,K] (K=424) and [K,M] (M=328) storage
+  __nv_bfloat16 *A, *B;
+  float *C, *Cref, *err;
+  HNB_CUDA_CALL(cudaMalloc(&A, sizeof(__nv_bfloat16) * 432 * 432));
+  HNB_CUDA_CALL(cudaMalloc(&B, sizeof(__nv_bfloat16) * 432 * 432));
+  HNB_CUDA_CALL(cudaMalloc(&C, sizeof(float) * M * N));
+  HNB_CUDA_CALL(cudaMalloc(&Cref, sizeof(float) * M * N));
+  HNB_CUDA_CALL(cudaMalloc(&err, sizeof(float) * 8));
+  HNB_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(float) * 8, st));
+  fill_kernel<<<cdiv(432 * 432, 256), 256, 0, st>>>(A, 432 * 432, 1u);
+  fill_kernel<<<cdiv(432 * 432, 256), 256, 0, st>>>(B, 432 * 432, 7u);
+  int rc = HNB_OK;
+  for (int combo = 0; combo < 5 && rc == HNB_OK; ++combo) {
+    const int ta = combo & 1, tb = (combo >> 1) & 1;
+    const int splitk = combo == 4 ? 3 : 1;
+    HNB_CUDA_CALL(cudaMemsetAsync(C, 0, sizeof(float) * M * N, st));
+    ref_gemm_kernel<<<dim3(cdiv(N, 128), M), 128, 0, st>>>(A, lda, ta, B, ldb, tb, M, N, K, Cref);
+    rc = hnb_gemm_bf16(A, lda, ta, B, ldb, tb, M, N, K, nullptr, nullptr, 0, C, N, HNB_F32, splitk, stream);
+    if (rc == HNB_OK) maxdiff_kernel<<<cdiv((long long)M * N, 256), 256, 0, st>>>(C, Cref, (long long)M * N, err + combo);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == HNB_OK && e != cudaSuccess) { set_error("umma_selftest: %s", cudaGetErrorString(e)); rc = HNB_ERR_CUDA; }
+  if (rc == HNB_OK) cudaMemcpy(max_abs_err_host, err, sizeof(float) * 5, cudaMemcpyDeviceToHost);
+  cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Cref); cudaFree(err);
+  return rc;
+}

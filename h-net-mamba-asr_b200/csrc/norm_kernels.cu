@@ -1,0 +1,343 @@
+// LayerNorm (pre-norm / final norm of MambaBlock / MambaStack) and the mixer's gated RMSNorm.
+// One warp per row; rows are short (d_model 384..768, d_inner 768..1536) so a row lives in L1 and is
+// re-read for the second moment instead of being held in a variable-size register array.
+#include "common.cuh"
+
+namespace hnb {
+
+constexpr int NORM_WARPS = 8;
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward
+// ---------------------------------------------------------------------------------------------
+template <typename TX, typename TY, int VN>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     long long rows, int d, float eps, TY* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TX* xr = x + row * d;
+  float s = 0.f;
+  for (int c = lane * VN; c < d; c += 32 * VN) {
+    float v[VN]; ldv<TX, VN>(xr + c, v);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) s += v[i];
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+  for (int c = lane * VN; c < d; c += 32 * VN) {
+    float v[VN]; ldv<TX, VN>(xr + c, v);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { const float t = v[i] - mean; q += t * t; }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  TY* yr = y + row * d;
+  for (int c = lane * VN; c < d; c += 32 * VN) {
+    float v[VN], g[VN], b[VN];
+    ldv<TX, VN>(xr + c, v); ldv<float, VN>(gamma + c, g); ldv<float, VN>(beta + c, b);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
+    stv<TY, VN>(yr + c, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward (+ residual gradient).  Persistent-style grid: each warp strides over rows and
+// keeps its dgamma/dbeta columns in registers; one shared-memory reduction + atomics per block.
+// ---------------------------------------------------------------------------------------------
+template <typename TDY, typename TX, typename TDX, int VN, int NV>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const TDX* __restrict__ dres,
+                     long long rows, int d, TDX* __restrict__ dx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+  extern __shared__ float sm[];                                     // [2][d]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float ag[NV][VN], ab[NV][VN], gm[NV][VN];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * VN;
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { ag[k][i] = 0.f; ab[k][i] = 0.f; gm[k][i] = 0.f; }
+    if (c < d) ldv<float, VN>(gamma + c, gm[k]);
+  }
+  for (long long row = (long long)blockIdx.x * NORM_WARPS + w; row < rows; row += (long long)gridDim.x * NORM_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][VN], g[NV][VN];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { xh[k][i] = 0.f; g[k][i] = 0.f; }
+      if (c < d) {
+        float xv[VN];
+        ldv<TX, VN>(x + row * d + c, xv);
+        ldv<TDY, VN>(dy + row * d + c, g[k]);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          xh[k][i] = (xv[i] - mu) * rs;
+          ag[k][i] += g[k][i] * xh[k][i];
+          ab[k][i] += g[k][i];
+          const float gg = g[k][i] * gm[k][i];
+          s1 += gg; s2 += gg * xh[k][i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+      if (c < d) {
+        float o[VN], r[VN];
+        if (dres) ldv<TDX, VN>(dres + row * d + c, r);
+#pragma unroll
+        for (int i = 0; i < VN; ++i)
+          o[i] = rs * (g[k][i] * gm[k][i] - s1 - xh[k][i] * s2) + (dres ? r[i] : 0.f);
+        stv<TDX, VN>(dx + row * d + c, o);
+      }
+    }
+  }
+  // block reduction of the parameter gradients
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * VN;
+    if (c < d) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { atomicAdd(&sm[c + i], ag[k][i]); atomicAdd(&sm[d + c + i], ab[k][i]); }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(dgamma + c, sm[c]);
+    atomicAdd(dbeta + c, sm[d + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gated RMSNorm forward: warp per (direction, natural token).  y is read at the token's scan
+// position, z from the natural row of zxbcdt; the result lands in natural order.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VN>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long long ldz, long long dstride, const int* __restrict__ lengths,
+                      const float* __restrict__ w, int ndir, int B, int L, int di, float eps, T* __restrict__ out,
+                      float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long T_ = (long long)B * L;
+  const long long idx = (long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
+  if (idx >= T_ * ndir) return;
+  const int dir = (int)(idx / T_);
+  const long long tok = idx % T_;
+  const int bi = (int)(tok / L), t = (int)(tok % L);
+  const int len = lengths ? lengths[bi] : L;
+  const int s = scan_to_nat(dir, t, len);                           // the map is an involution
+  const T* yr = y + ((long long)dir * T_ + (long long)bi * L + s) * di;
+  const T* zr = zx + tok * ldz + (long long)dir * dstride;
+  float q = 0.f;
+  for (int c = lane * VN; c < di; c += 32 * VN) {
+    float a[VN], z[VN];
+    ldv<T, VN>(yr + c, a); ldv<T, VN>(zr + c, z);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { const float g = a[i] * silu_f(z[i]); q += g * g; }
+  }
+  const float rs = rsqrtf(warp_sum(q) / di + eps);
+  if (lane == 0) rstd_out[(long long)dir * T_ + tok] = rs;
+  T* o = out + tok * ((long long)ndir * di) + (long long)dir * di;
+  const float* wr = w + (long long)dir * di;
+  for (int c = lane * VN; c < di; c += 32 * VN) {
+    float a[VN], z[VN], ww[VN];
+    ldv<T, VN>(yr + c, a); ldv<T, VN>(zr + c, z); ldv<float, VN>(wr + c, ww);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) a[i] = a[i] * silu_f(z[i]) * rs * ww[i];
+    stv<T, VN>(o + c, a);
+  }
+}
+
+// backward: dout (natural) -> dy (scan order), dz (natural, into dzxbcdt), dw (accumulated)
+template <typename T, int VN, int NV>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const T* __restrict__ zx, long long ldz, long long dstride,
+                      const int* __restrict__ lengths, const float* __restrict__ w, const float* __restrict__ rstd,
+                      int ndir, int B, int L, int di, T* __restrict__ dy, T* __restrict__ dzx,
+                      float* __restrict__ dw) {
+  extern __shared__ float sm[];                                     // [di]
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const long long T_ = (long long)B * L;
+  const int dir = blockIdx.y;
+  float aw[NV][VN], ww[NV][VN];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * VN;
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { aw[k][i] = 0.f; ww[k][i] = 0.f; }
+    if (c < di) ldv<float, VN>(w + (long long)dir * di + c, ww[k]);
+  }
+  for (long long tok = (long long)blockIdx.x * NORM_WARPS + wi; tok < T_; tok += (long long)gridDim.x * NORM_WARPS) {
+    const int bi = (int)(tok / L), t = (int)(tok % L);
+    const int len = lengths ? lengths[bi] : L;
+    const int s = scan_to_nat(dir, t, len);
+    const long long yoff = ((long long)dir * T_ + (long long)bi * L + s) * di;
+    const T* zr = zx + tok * ldz + (long long)dir * dstride;
+    const T* gr = dout + tok * ((long long)ndir * di) + (long long)dir * di;
+    const float rs = rstd[(long long)dir * T_ + tok];
+    float gh[NV][VN], dn[NV][VN], yv[NV][VN], zv[NV][VN];
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { gh[k][i] = 0.f; dn[k][i] = 0.f; yv[k][i] = 0.f; zv[k][i] = 0.f; }
+      if (c < di) {
+        float go[VN];
+        ldv<T, VN>(y + yoff + c, yv[k]); ldv<T, VN>(zr + c, zv[k]); ldv<T, VN>(gr + c, go);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          gh[k][i] = yv[k][i] * silu_f(zv[k][i]) * rs;              // normalised gated value
+          aw[k][i] += go[i] * gh[k][i];
+          dn[k][i] = go[i] * ww[k][i];
+          s2 += dn[k][i] * gh[k][i];
+        }
+      }
+    }
+    s2 = warp_sum(s2) / di;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+      if (c < di) {
+        float o1[VN], o2[VN];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          const float dg = rs * (dn[k][i] - gh[k][i] * s2);
+          const float sg = sigmoid_f(zv[k][i]);
+          o1[i] = dg * zv[k][i] * sg;                               // d y
+          o2[i] = dg * yv[k][i] * sg * (1.f + zv[k][i] * (1.f - sg));   // d z
+        }
+        stv<T, VN>(dy + yoff + c, o1);
+        stv<T, VN>(dzx + tok * ldz + (long long)dir * dstride + c, o2);
+      }
+    }
+  }
+  for (int c = threadIdx.x; c < di; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * VN;
+    if (c < di) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) atomicAdd(&sm[c + i], aw[k][i]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < di; c += blockDim.x) atomicAdd(dw + (long long)dir * di + c, sm[c]);
+}
+
+}  // namespace hnb
+
+using namespace hnb;
+
+static inline int esz(int dt) { return dt == HNB_BF16 ? 2 : 4; }
+static inline bool al(const void* p, int bytes) { return ((uintptr_t)p) % (size_t)bytes == 0; }
+
+extern "C" int hnb_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, long long rows,
+                                 int d, float eps, void* y, int y_dtype, float* mean, float* rstd, void* stream) {
+  HNB_CHECK_ARG(x && gamma && beta && y && mean && rstd && rows > 0 && d > 0, "layernorm_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = cdiv(rows, NORM_WARPS);
+  const bool v4 = d % 4 == 0 && al(x, 4 * esz(x_dtype)) && al(y, 4 * esz(y_dtype)) && al(gamma, 16) && al(beta, 16);
+#define RUN(TX, TY, VN) layernorm_fwd_kernel<TX, TY, VN><<<grid, NORM_WARPS * 32, 0, st>>>( \
+      (const TX*)x, gamma, beta, rows, d, eps, (TY*)y, mean, rstd)
+  HNB_DISPATCH_DTYPE(x_dtype, TX, HNB_DISPATCH_DTYPE(y_dtype, TY, { if (v4) RUN(TX, TY, 4); else RUN(TX, TY, 1); }));
+#undef RUN
+  HNB_LAUNCH_CHECK("layernorm_fwd");
+  return HNB_OK;
+}
+
+static int norm_grid(long long rows) {
+  int g = cdiv(rows, NORM_WARPS);
+  return g < 148 * 4 ? g : 148 * 4;                                 // 4 resident CTAs per SM, grid-stride over rows
+}
+
+extern "C" int hnb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                                 const float* mean, const float* rstd, const void* dres, long long rows, int d,
+                                 void* dx, int dx_dtype, float* dgamma, float* dbeta, void* stream) {
+  HNB_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0 && d > 0,
+                "layernorm_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = norm_grid(rows);
+  const bool v4 = d % 4 == 0 && al(x, 4 * esz(x_dtype)) && al(dy, 4 * esz(dy_dtype)) && al(dx, 4 * esz(dx_dtype)) &&
+                  (!dres || al(dres, 4 * esz(dx_dtype))) && al(gamma, 16);
+  const int vn = v4 ? 4 : 1;
+  const int nv = cdiv(d, 32 * vn);
+  HNB_CHECK_ARG(nv <= 16, "layernorm_bwd: d=%d too large", d);
+  const size_t smem = 2 * (size_t)d * sizeof(float);
+#define RUN2(A, Bx, C, VN, NV) layernorm_bwd_kernel<A, Bx, C, VN, NV><<<grid, NORM_WARPS * 32, smem, st>>>( \
+      (const A*)dy, (const Bx*)x, gamma, mean, rstd, (const C*)dres, rows, d, (C*)dx, dgamma, dbeta)
+#define RUN(A, Bx, C, VN)                                                                  \
+  do {                                                                                     \
+    if (nv <= 2) RUN2(A, Bx, C, VN, 2); else if (nv <= 3) RUN2(A, Bx, C, VN, 3);           \
+    else if (nv <= 4) RUN2(A, Bx, C, VN, 4); else if (nv <= 6) RUN2(A, Bx, C, VN, 6);      \
+    else RUN2(A, Bx, C, VN, 16);                                                           \
+  } while (0)
+  HNB_CHECK_ARG(x_dtype == dx_dtype, "layernorm_bwd: x and dx must share a dtype");
+  HNB_DISPATCH_DTYPE(dy_dtype, TA, HNB_DISPATCH_DTYPE(x_dtype, TB, {
+    if (v4) RUN(TA, TB, TB, 4); else RUN(TA, TB, TB, 1); }));
+#undef RUN
+#undef RUN2
+  HNB_LAUNCH_CHECK("layernorm_bwd");
+  return HNB_OK;
+}
+
+extern "C" int hnb_gated_norm_fwd(const void* y, const void* zxbcdt, int dtype, long long ldz, long long dstride, const int32_t* lengths,
+                                  const float* norm_w, int ndir, int B, int L, int di, float eps, void* out,
+                                  float* rstd, void* stream) {
+  HNB_CHECK_ARG(y && zxbcdt && norm_w && out && rstd && ndir >= 1 && ndir <= 2 && B > 0 && L > 0 && di > 0,
+                "gated_norm_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)B * L * ndir;
+  const int grid = cdiv(rows, NORM_WARPS);
+  const bool v4 = di % 4 == 0 && ldz % 4 == 0 && dstride % 4 == 0 && al(y, 4 * esz(dtype)) && al(zxbcdt, 4 * esz(dtype)) &&
+                  al(out, 4 * esz(dtype)) && al(norm_w, 16);
+#define RUN(T, VN) gated_norm_fwd_kernel<T, VN><<<grid, NORM_WARPS * 32, 0, st>>>( \
+      (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, ndir, B, L, di, eps, (T*)out, rstd)
+  HNB_DISPATCH_DTYPE(dtype, T, { if (v4) RUN(T, 4); else RUN(T, 1); });
+#undef RUN
+  HNB_LAUNCH_CHECK("gated_norm_fwd");
+  return HNB_OK;
+}
+
+extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* zxbcdt, int dtype, long long ldz, long long dstride,
+                                  const int32_t* lengths, const float* norm_w, const float* rstd, int ndir, int B,
+                                  int L, int di, void* dy, void* dzxbcdt, float* dnorm_w, void* stream) {
+  HNB_CHECK_ARG(dout && y && zxbcdt && norm_w && rstd && dy && dzxbcdt && dnorm_w, "gated_norm_bwd: null pointer");
+  HNB_CHECK_ARG(ndir >= 1 && ndir <= 2 && B > 0 && L > 0 && di > 0, "gated_norm_bwd: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)B * L;
+  int gx = norm_grid(rows) / ndir;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, ndir);
+  const bool v4 = di % 4 == 0 && ldz % 4 == 0 && dstride % 4 == 0 && al(y, 4 * esz(dtype)) && al(zxbcdt, 4 * esz(dtype)) &&
+                  al(dout, 4 * esz(dtype)) && al(dy, 4 * esz(dtype)) && al(dzxbcdt, 4 * esz(dtype)) && al(norm_w, 16);
+  const int vn = v4 ? 4 : 1;
+  const int nv = cdiv(di, 32 * vn);
+  HNB_CHECK_ARG(nv <= 16, "gated_norm_bwd: d_inner=%d too large", di);
+  const size_t smem = (size_t)di * sizeof(float);
+#define RUN2(T, VN, NV) gated_norm_bwd_kernel<T, VN, NV><<<grid, NORM_WARPS * 32, smem, st>>>( \
+      (const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w)
+#define RUN(T, VN)                                                             \
+  do {                                                                         \
+    if (nv <= 2) RUN2(T, VN, 2); else if (nv <= 4) RUN2(T, VN, 4);             \
+    else if (nv <= 6) RUN2(T, VN, 6); else if (nv <= 8) RUN2(T, VN, 8);        \
+    else if (nv <= 12) RUN2(T, VN, 12); else RUN2(T, VN, 16);                  \
+  } while (0)
+  HNB_DISPATCH_DTYPE(dtype, T, { if (v4) RUN(T, 4); else RUN(T, 1); });
+#undef RUN
+#undef RUN2
+  HNB_LAUNCH_CHECK("gated_norm_bwd");
+  return HNB_OK;
+}

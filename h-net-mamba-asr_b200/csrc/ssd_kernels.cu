@@ -1,0 +1,654 @@
+// SSD (Mamba-2 selective scan) in scan order, chunked dual form, fp32 arithmetic on CUDA cores.
+// This is the exact path (impl 0): it serves fp32 activations (decode / parity) and is the numerical
+// yard-stick for the tcgen05 kernels (impl 1, ssd_tcgen05.cu).
+//
+//   h_t = exp(dt_t A) h_{t-1} + dt_t B_t (x) x_t ,  y_t = C_t . h_t + D x_t      (per head; B, C shared)
+//
+// Chunk Q = 64.  Forward:  chunk_state -> state_pass -> chunk_scan.
+// Backward: chunk_state(dY, C) -> state_pass(reverse) -> bwd_chunk -> bwd_ddt.
+// Every small matmul is written as an outer-product loop over the contraction index k with the
+// lane-varying operand stored [k][lanes] in shared memory (conflict-free) and the other operand
+// broadcast.  Per-chunk states are stored [N][P] (p contiguous) so that no state tile is ever transposed.
+#include "common.cuh"
+
+namespace hnb {
+
+constexpr int SQ = 64;      // chunk length
+constexpr int SP = 64;      // head dim
+constexpr int SN = 128;     // state dim
+constexpr int ST = 256;     // threads per CTA
+constexpr int PADQ = SQ + 1;
+
+// cumulative log-decay of one (row, head, chunk): s_dt[q] = dt_q (0 beyond L), s_cs[q] = inclusive cumsum(dt*A)
+__device__ __forceinline__ void chunk_cumsum(const float* __restrict__ dtp, long long stride, int q_valid, float A,
+                                             float* s_dt, float* s_cs) {
+  const int tid = threadIdx.x;
+  if (tid < SQ) {
+    const float d = (tid < q_valid) ? dtp[(long long)tid * stride] : 0.f;
+    s_dt[tid] = d;
+    float v = d * A;
+    const int lane = tid & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    s_cs[tid] = v;
+  }
+  __syncthreads();
+  if (tid >= 32 && tid < SQ) s_cs[tid] += s_cs[31];
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// chunk_state: out[n][p] = sum_q w_q V[q][n] U[q][p]
+//   MODE 0 (forward):  U = x,  V = B,  w_q = exp(cs_last - cs_q) dt_q ; also writes decay = exp(cs_last)
+//   MODE 1 (backward): U = dy, V = C,  w_q = exp(cs_q)
+// grid (nchunks, ndir*B), loop over heads.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(ST)
+ssd_chunk_state_kernel(const T* __restrict__ U, long long ldu, const T* __restrict__ xconv, int C, int di,
+                       const float* __restrict__ dt, const float* __restrict__ A_log, int ndir, int B, int L, int H,
+                       int nc, float* __restrict__ states, float* __restrict__ decay) {
+  extern __shared__ float smem[];
+  float* Vs = smem;                       // [SQ][SN]
+  float* Us = Vs + SQ * SN;               // [SQ][SP] (pre-scaled by w_q)
+  float* s_dt = Us + SQ * SP;             // [SQ]
+  float* s_cs = s_dt + SQ;                // [SQ]
+  const int c = blockIdx.x, db = blockIdx.y, dir = db / B;
+  const int tid = threadIdx.x;
+  const int q0 = c * SQ, qv = min(SQ, L - q0);
+  const long long row0 = (long long)db * L + q0;
+  const int voff = di + (MODE == 0 ? 0 : SN);
+  for (int i = tid; i < SQ * SN / 4; i += ST) {
+    const int q = i / (SN / 4), n4 = (i % (SN / 4)) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < qv) ldv<T, 4>(xconv + (row0 + q) * C + voff + n4, v);
+    *reinterpret_cast<float4*>(Vs + q * SN + n4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  const int tp = tid & 15, tn = tid >> 4;
+  for (int h = 0; h < H; ++h) {
+    const float A = -__expf(A_log[dir * H + h]);
+    __syncthreads();
+    chunk_cumsum(dt + row0 * H + h, H, qv, A, s_dt, s_cs);
+    const float cs_last = s_cs[SQ - 1];
+    for (int i = tid; i < SQ * SP / 4; i += ST) {
+      const int q = i / (SP / 4), p4 = (i % (SP / 4)) * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (q < qv) ldv<T, 4>(U + (row0 + q) * ldu + h * SP + p4, v);
+      const float w = (MODE == 0) ? __expf(cs_last - s_cs[q]) * s_dt[q] : __expf(s_cs[q]);
+      *reinterpret_cast<float4*>(Us + q * SP + p4) = make_float4(v[0] * w, v[1] * w, v[2] * w, v[3] * w);
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int q = 0; q < SQ; ++q) {
+      float a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = Vs[q * SN + tn + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Us[q * SP + tp + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    float* out = states + (((long long)db * nc + c) * H + h) * (SN * SP);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[(tn + 16 * i) * SP + tp + 16 * j] = acc[i][j];
+    if (MODE == 0 && tid == 0) decay[((long long)db * H + h) * nc + c] = __expf(cs_last);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inter-chunk state pass (elementwise over the 128x64 state, sequential over chunks).
+//   forward: states[c] <- state entering chunk c;           running = decay_c running + local_c
+//   reverse: states[c] <- gradient w.r.t. the state LEAVING chunk c; running = decay_c running + local_c
+// ---------------------------------------------------------------------------------------------
+template <bool REV>
+__global__ void __launch_bounds__(256)
+ssd_state_pass_kernel(float* __restrict__ states, const float* __restrict__ decay, int H, int nc, long long total4) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;      // float4 index over [db][h][N*P/4]
+  if (i >= total4) return;
+  constexpr int PER = SN * SP / 4;
+  const long long dbh = i / PER;
+  const int e = (int)(i % PER);
+  const long long db = dbh / H;
+  const int h = (int)(dbh % H);
+  float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < nc; ++k) {
+    const int c = REV ? (nc - 1 - k) : k;
+    float4* p = reinterpret_cast<float4*>(states + (((long long)db * nc + c) * H + h) * (SN * SP)) + e;
+    const float4 loc = *p;
+    *p = run;
+    const float d = decay[((long long)db * H + h) * nc + c];
+    run.x = d * run.x + loc.x; run.y = d * run.y + loc.y; run.z = d * run.z + loc.z; run.w = d * run.w + loc.w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// chunk_scan (forward output): y = (L o C B^T)(dt x) + exp(cs) C S_in + D x
+// grid (nchunks, ndir*B), loop over heads; G = C B^T is computed once and kept in registers.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(ST)
+ssd_chunk_scan_kernel(const T* __restrict__ xconv, int C, int di, const float* __restrict__ dt,
+                      const float* __restrict__ A_log, const float* __restrict__ Dskip,
+                      const float* __restrict__ states, int ndir, int B, int L, int H, int nc, T* __restrict__ y) {
+  extern __shared__ float smem[];
+  float* Cn = smem;                        // [SQ][SN]
+  float* Bt = Cn + SQ * SN;                // [SN][PADQ]
+  float* Ms = Bt + SN * PADQ;              // [SQ][SQ]
+  float* Xs = Ms + SQ * SQ;                // [SQ][SP]
+  float* Ss = Xs + SQ * SP;                // [SN][SP]
+  float* s_dt = Ss + SN * SP;
+  float* s_cs = s_dt + SQ;
+  const int c = blockIdx.x, db = blockIdx.y, dir = db / B;
+  const int tid = threadIdx.x;
+  const int q0 = c * SQ, qv = min(SQ, L - q0);
+  const long long row0 = (long long)db * L + q0;
+  for (int i = tid; i < SQ * SN / 4; i += ST) {
+    const int q = i / (SN / 4), n4 = (i % (SN / 4)) * 4;
+    float vb[4] = {0.f, 0.f, 0.f, 0.f}, vc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < qv) { ldv<T, 4>(xconv + (row0 + q) * C + di + n4, vb); ldv<T, 4>(xconv + (row0 + q) * C + di + SN + n4, vc); }
+    *reinterpret_cast<float4*>(Cn + q * SN + n4) = make_float4(vc[0], vc[1], vc[2], vc[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Bt[(n4 + k) * PADQ + q] = vb[k];
+  }
+  __syncthreads();
+  const int tj = tid & 15, ti = tid >> 4;           // 64x64 tiles: rows ti+16i, cols tj+16j
+  float G[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) G[i][j] = 0.f;
+  for (int n = 0; n < SN; ++n) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = Cn[(ti + 16 * i) * SN + n];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Bt[n * PADQ + tj + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) G[i][j] += a[i] * b[j];
+  }
+  for (int h = 0; h < H; ++h) {
+    const float A = -__expf(A_log[dir * H + h]);
+    const float Dh = Dskip[dir * H + h];
+    __syncthreads();
+    chunk_cumsum(dt + row0 * H + h, H, qv, A, s_dt, s_cs);
+    for (int i = tid; i < SQ * SP / 4; i += ST) {
+      const int q = i / (SP / 4), p4 = (i % (SP / 4)) * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (q < qv) ldv<T, 4>(xconv + (row0 + q) * C + h * SP + p4, v);
+      *reinterpret_cast<float4*>(Xs + q * SP + p4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    const float4* sg = reinterpret_cast<const float4*>(states + (((long long)db * nc + c) * H + h) * (SN * SP));
+    for (int i = tid; i < SN * SP / 4; i += ST) reinterpret_cast<float4*>(Ss)[i] = sg[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = ti + 16 * i, s = tj + 16 * j;
+        Ms[t * SQ + s] = (s <= t) ? G[i][j] * __expf(s_cs[t] - s_cs[s]) * s_dt[s] : 0.f;
+      }
+    __syncthreads();
+    float acc[4][4], off[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; off[i][j] = 0.f; }
+    for (int s = 0; s < SQ; ++s) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Ms[(ti + 16 * i) * SQ + s];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Xs[s * SP + tj + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    for (int n = 0; n < SN; ++n) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Cn[(ti + 16 * i) * SN + n];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ss[n * SP + tj + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) off[i][j] += a[i] * b[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = ti + 16 * i;
+      if (t < qv) {
+        const float e = __expf(s_cs[t]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int p = tj + 16 * j;
+          y[(row0 + t) * di + h * SP + p] = from_f<T>(acc[i][j] + e * off[i][j] + Dh * Xs[t * SP + p]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward chunk kernel.  grid (nchunks, ndir*B), loop over heads.
+// Per head (x, dy, y of the head; S_in = state entering the chunk, Gst = d loss / d state leaving it):
+//   K[t,q] = G[t,q] e^{cs_t-cs_q}  (t>=q);   W[t,q] = <dy_t, x_q> dt_q e^{cs_t-cs_q}  (t>=q)
+//   du[q,p] = sum_t K[t,q] dy[t,p] + e^{cs_last-cs_q} sum_n B[q,n] Gst[n,p]
+//   dx = dt du + D dy ;  ddt_x[q] = <du_q, x_q> ;  dscal[t] = <dy_t, y_t - D x_t> - dt_t ddt_x[t]
+//   dC[t,n] += sum_q W[t,q] B[q,n] + e^{cs_t} sum_p dy[t,p] S_in[n,p]
+//   dB[q,n] += sum_t W[t,q] C[t,n] + e^{cs_last-cs_q} dt_q sum_p x[q,p] Gst[n,p]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(ST)
+ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, const T* __restrict__ yfw, int C, int di,
+                     const float* __restrict__ dt, const float* __restrict__ A_log, const float* __restrict__ Dskip,
+                     const float* __restrict__ states, const float* __restrict__ gstates, int ndir, int B, int L,
+                     int H, int nc, T* __restrict__ dxc, float* __restrict__ dBC, float* __restrict__ ddt_x,
+                     float* __restrict__ dscal, float* __restrict__ dD) {
+  extern __shared__ float smem[];
+  float* Bn = smem;                        // [SQ][SN]
+  float* Cn = Bn + SQ * SN;                // [SQ][SN]
+  float* Al = Cn + SQ * SN;                // aliased: Bt [SN][PADQ] first, then dYt [SP][PADQ] + Xt [SP][PADQ]
+  float* Bt = Al;
+  float* dYt = Al;
+  float* Xt = Al + SP * PADQ;
+  float* Gs = Al + SN * PADQ;              // [SQ][SQ]  C B^T
+  float* dYs = Gs + SQ * SQ;               // [SQ][SP]
+  float* Ks = dYs + SQ * SP;               // [SQ][SQ]
+  float* Ws = Ks + SQ * SQ;                // [SQ][SQ]
+  float* s_dt = Ws + SQ * SQ;
+  float* s_cs = s_dt + SQ;
+  float* s_red = s_cs + SQ;                // [32]
+  const int c = blockIdx.x, db = blockIdx.y, dir = db / B;
+  const int tid = threadIdx.x;
+  const int q0 = c * SQ, qv = min(SQ, L - q0);
+  const long long row0 = (long long)db * L + q0;
+  for (int i = tid; i < SQ * SN / 4; i += ST) {
+    const int q = i / (SN / 4), n4 = (i % (SN / 4)) * 4;
+    float vb[4] = {0.f, 0.f, 0.f, 0.f}, vc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < qv) { ldv<T, 4>(xconv + (row0 + q) * C + di + n4, vb); ldv<T, 4>(xconv + (row0 + q) * C + di + SN + n4, vc); }
+    *reinterpret_cast<float4*>(Bn + q * SN + n4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    *reinterpret_cast<float4*>(Cn + q * SN + n4) = make_float4(vc[0], vc[1], vc[2], vc[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Bt[(n4 + k) * PADQ + q] = vb[k];
+  }
+  __syncthreads();
+  const int tj = tid & 15, ti = tid >> 4;           // 64x64 tiles
+  const int wn = tid & 31, wt = tid >> 5;           // 64x128 tiles: rows wt+8i, cols wn+32j
+  {
+    float g[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[i][j] = 0.f;
+    for (int n = 0; n < SN; ++n) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Cn[(ti + 16 * i) * SN + n];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bt[n * PADQ + tj + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[i][j] += a[i] * b[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Gs[(ti + 16 * i) * SQ + tj + 16 * j] = g[i][j];
+  }
+  float accC[8][4], accB[8][4], accC2[8][4], accB2[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { accC[i][j] = 0.f; accB[i][j] = 0.f; accC2[i][j] = 0.f; accB2[i][j] = 0.f; }
+
+  for (int h = 0; h < H; ++h) {
+    const float A = -__expf(A_log[dir * H + h]);
+    const float Dh = Dskip[dir * H + h];
+    __syncthreads();                                // everyone is done with Bt / the previous head's tiles
+    chunk_cumsum(dt + row0 * H + h, H, qv, A, s_dt, s_cs);
+    const float cs_last = s_cs[SQ - 1];
+    for (int i = tid; i < SQ * SP / 4; i += ST) {
+      const int q = i / (SP / 4), p4 = (i % (SP / 4)) * 4;
+      float vx[4] = {0.f, 0.f, 0.f, 0.f}, vd[4] = {0.f, 0.f, 0.f, 0.f};
+      if (q < qv) { ldv<T, 4>(xconv + (row0 + q) * C + h * SP + p4, vx); ldv<T, 4>(dy + (row0 + q) * di + h * SP + p4, vd); }
+      *reinterpret_cast<float4*>(dYs + q * SP + p4) = make_float4(vd[0], vd[1], vd[2], vd[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { Xt[(p4 + k) * PADQ + q] = vx[k]; dYt[(p4 + k) * PADQ + q] = vd[k]; }
+    }
+    __syncthreads();
+    // K and W (64x64, rows t, cols q)
+    {
+      float r[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[i][j] = 0.f;
+      for (int p = 0; p < SP; ++p) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = dYs[(ti + 16 * i) * SP + p];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Xt[p * PADQ + tj + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r[i][j] += a[i] * b[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int t = ti + 16 * i, q = tj + 16 * j;
+          const float e = (q <= t) ? __expf(s_cs[t] - s_cs[q]) : 0.f;
+          Ks[t * SQ + q] = Gs[t * SQ + q] * e;
+          Ws[t * SQ + q] = r[i][j] * e * s_dt[q];
+        }
+    }
+    __syncthreads();
+    const float* Sin = states + (((long long)db * nc + c) * H + h) * (SN * SP);
+    const float* Gst = gstates + (((long long)db * nc + c) * H + h) * (SN * SP);
+    // ---- du (rows q = ti+16i, cols p = tj+16j)
+    {
+      float du1[4][4], du2[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { du1[i][j] = 0.f; du2[i][j] = 0.f; }
+      for (int t = 0; t < SQ; ++t) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = Ks[t * SQ + ti + 16 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = dYs[t * SP + tj + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) du1[i][j] += a[i] * b[j];
+      }
+      for (int n = 0; n < SN; ++n) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = Bn[(ti + 16 * i) * SN + n];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = __ldg(Gst + n * SP + tj + 16 * j);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) du2[i][j] += a[i] * b[j];
+      }
+      float dsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = ti + 16 * i;
+        const float eq = __expf(cs_last - s_cs[q]);
+        float dux = 0.f, dyy = 0.f;
+        if (q < qv) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int p = tj + 16 * j;
+            const float du = du1[i][j] + eq * du2[i][j];
+            const float xv = Xt[p * PADQ + q];
+            const float dv = dYs[q * SP + p];
+            const float yv = to_f(yfw[(row0 + q) * di + h * SP + p]);
+            dxc[(row0 + q) * di + h * SP + p] = from_f<T>(s_dt[q] * du + Dh * dv);
+            dux += du * xv;
+            dyy += dv * (yv - Dh * xv);
+            dsum += dv * xv;
+          }
+        }
+        // reduce over the 16 lanes that share this row
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) { dux += __shfl_xor_sync(0xffffffffu, dux, o); dyy += __shfl_xor_sync(0xffffffffu, dyy, o); }
+        if (tj == 0 && q < qv) {
+          ddt_x[(row0 + q) * H + h] = dux;
+          dscal[(row0 + q) * H + h] = dyy - s_dt[q] * dux;
+        }
+      }
+      dsum = block_sum(dsum, s_red);
+      if (tid == 0) atomicAdd(dD + dir * H + h, dsum);
+    }
+    // ---- dC1 / dB1 (rows wt+8i, cols n = wn+32j)
+    for (int k = 0; k < SQ; ++k) {
+      float aw[8], awt[8], bb[4], bc[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { aw[i] = Ws[(wt + 8 * i) * SQ + k]; awt[i] = Ws[k * SQ + wt + 8 * i]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { bb[j] = Bn[k * SN + wn + 32 * j]; bc[j] = Cn[k * SN + wn + 32 * j]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { accC[i][j] += aw[i] * bb[j]; accB[i][j] += awt[i] * bc[j]; }
+    }
+    // ---- dC2^T / dB2^T (rows n = ti+16i (i<8), cols t = tj+16j), scaled per head
+    {
+      float c2[8][4], b2[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c2[i][j] = 0.f; b2[i][j] = 0.f; }
+      for (int p = 0; p < SP; ++p) {
+        float as[8], ag[8], bd[4], bx[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { as[i] = __ldg(Sin + (ti + 16 * i) * SP + p); ag[i] = __ldg(Gst + (ti + 16 * i) * SP + p); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { bd[j] = dYt[p * PADQ + tj + 16 * j]; bx[j] = Xt[p * PADQ + tj + 16 * j]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { c2[i][j] += as[i] * bd[j]; b2[i][j] += ag[i] * bx[j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = tj + 16 * j;
+        const float et = __expf(s_cs[t]);
+        const float eq = __expf(cs_last - s_cs[t]) * s_dt[t];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { accC2[i][j] += et * c2[i][j]; accB2[i][j] += eq * b2[i][j]; }
+      }
+    }
+  }
+  // ---- write dB | dC for this chunk: first the (t, n)-mapped tiles, then add the (n, t)-mapped ones
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = wt + 8 * i;
+    if (t < qv) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = wn + 32 * j;
+        dBC[(row0 + t) * (2 * SN) + n] = accB[i][j];
+        dBC[(row0 + t) * (2 * SN) + SN + n] = accC[i][j];
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t = tj + 16 * j;
+    if (t < qv) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = ti + 16 * i;
+        dBC[(row0 + t) * (2 * SN) + n] += accB2[i][j];
+        dBC[(row0 + t) * (2 * SN) + SN + n] += accC2[i][j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ddt / dA: dloga_t = sum_{s>=t} dscal_s (suffix sum over the WHOLE row), ddt_t = dloga_t A + ddt_x_t,
+// dA_log = A * sum_t dloga_t dt_t.   One warp per (row, head).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ssd_bwd_ddt_kernel(const float* __restrict__ dscal, const float* __restrict__ ddt_x, const float* __restrict__ dt,
+                   const float* __restrict__ A_log, int ndir, int B, int L, int H, float* __restrict__ ddt,
+                   float* __restrict__ dA_log) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wid >= (long long)ndir * B * H) return;
+  const long long db = wid / H;
+  const int h = (int)(wid % H), dir = (int)(db / B);
+  const float A = -__expf(A_log[dir * H + h]);
+  float carry = 0.f, accA = 0.f;
+  for (int base = L - 1; base >= 0; base -= 32) {
+    const int t = base - lane;                                        // lane 0 holds the latest time
+    float v = (t >= 0) ? dscal[((long long)db * L + t) * H + h] : 0.f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    v += carry;
+    if (t >= 0) {
+      const long long idx = ((long long)db * L + t) * H + h;
+      ddt[idx] = v * A + ddt_x[idx];
+      accA += v * dt[idx];
+    }
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  accA = warp_sum(accA);
+  if (lane == 0) atomicAdd(dA_log + dir * H + h, accA * A);
+}
+
+}  // namespace hnb
+
+using namespace hnb;
+
+static size_t ssd_states_floats(int ndir, int B, int L, int H) {
+  const int nc = cdiv(L, SQ);
+  return (size_t)ndir * B * nc * H * SN * SP;
+}
+
+extern "C" int hnb_ssd_chunk(void) { return SQ; }
+
+extern "C" long long hnb_ssd_ws_bytes(int ndir, int B, int L, int di, int N, int H) {
+  (void)di; (void)N;
+  const int nc = cdiv(L, SQ);
+  const size_t fl = ssd_states_floats(ndir, B, L, H) + (size_t)ndir * B * H * nc + 2 * (size_t)ndir * B * L * H + 64;
+  return (long long)(fl * sizeof(float));
+}
+
+static int ssd_check(const char* who, int ndir, int B, int L, int di, int N, int H) {
+  if (!(ndir >= 1 && ndir <= 2 && B > 0 && L > 0 && H > 0)) { set_error("%s: bad sizes", who); return HNB_ERR_INVALID_ARG; }
+  if (N != SN || di != H * SP) {
+    set_error("%s: only d_state=128, headdim=64 are built (got N=%d, di=%d, H=%d)", who, N, di, H);
+    return HNB_ERR_UNSUPPORTED;
+  }
+  return HNB_OK;
+}
+
+int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B, int L,
+                   int di, int N, int H, void* y, void* states, void* stream);
+int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
+                   const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
+                   float* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream);
+
+template <typename T>
+static int ssd_fwd_impl(const T* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B,
+                        int L, int di, int H, T* y, float* ws, cudaStream_t st) {
+  const int nc = cdiv(L, SQ), C = di + 2 * SN;
+  float* states = ws;
+  float* decay = ws + ssd_states_floats(ndir, B, L, H);
+  const size_t sm1 = (SQ * SN + SQ * SP + 2 * SQ) * sizeof(float);
+  const size_t sm3 = (SQ * SN + SN * PADQ + SQ * SQ + SQ * SP + SN * SP + 2 * SQ) * sizeof(float);
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_chunk_state_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_chunk_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  dim3 grid(nc, ndir * B);
+  ssd_chunk_state_kernel<T, 0><<<grid, ST, sm1, st>>>(xconv, C, xconv, C, di, dt, A_log, ndir, B, L, H, nc, states, decay);
+  HNB_LAUNCH_CHECK("ssd_chunk_state");
+  const long long total4 = (long long)ndir * B * H * (SN * SP / 4);
+  ssd_state_pass_kernel<false><<<cdiv(total4, 256), 256, 0, st>>>(states, decay, H, nc, total4);
+  HNB_LAUNCH_CHECK("ssd_state_pass");
+  ssd_chunk_scan_kernel<T><<<grid, ST, sm3, st>>>(xconv, C, di, dt, A_log, Dskip, states, ndir, B, L, H, nc, y);
+  HNB_LAUNCH_CHECK("ssd_chunk_scan");
+  return HNB_OK;
+}
+
+extern "C" int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const float* A_log, const float* Dskip,
+                           int ndir, int B, int L, int di, int N, int H, void* y, void* states, int impl,
+                           void* stream) {
+  HNB_CHECK_ARG(xconv && dt && A_log && Dskip && y && states, "ssd_fwd: null pointer");
+  int rc = ssd_check("ssd_fwd", ndir, B, L, di, N, H);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 1) {
+    HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_fwd: the tcgen05 path takes bf16 activations");
+    return hnb_ssd_fwd_tc(xconv, dt, A_log, Dskip, ndir, B, L, di, N, H, y, states, stream);
+  }
+  if (dtype == HNB_BF16)
+    return ssd_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)xconv, dt, A_log, Dskip, ndir, B, L, di, H,
+                                       (__nv_bfloat16*)y, (float*)states, st);
+  if (dtype == HNB_F32)
+    return ssd_fwd_impl<float>((const float*)xconv, dt, A_log, Dskip, ndir, B, L, di, H, (float*)y, (float*)states, st);
+  set_error("ssd_fwd: unsupported dtype");
+  return HNB_ERR_INVALID_ARG;
+}
+
+template <typename T>
+static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt, const float* A_log,
+                        const float* Dskip, const float* ws, int ndir, int B, int L, int di, int H, T* dxc, float* dBC,
+                        float* ddt, float* dA_log, float* dD, float* ws2, cudaStream_t st) {
+  const int nc = cdiv(L, SQ), C = di + 2 * SN;
+  const size_t nst = ssd_states_floats(ndir, B, L, H);
+  const float* states = ws;
+  const float* decay = ws + nst;
+  float* gstates = ws2;
+  float* ddt_x = ws2 + nst + (size_t)ndir * B * H * nc;
+  float* dscal = ddt_x + (size_t)ndir * B * L * H;
+  const size_t sm1 = (SQ * SN + SQ * SP + 2 * SQ) * sizeof(float);
+  const size_t smb = (2 * SQ * SN + SN * PADQ + SQ * SQ + SQ * SP + 2 * SQ * SQ + 2 * SQ + 32) * sizeof(float);
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_chunk_state_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_chunk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+  dim3 grid(nc, ndir * B);
+  ssd_chunk_state_kernel<T, 1><<<grid, ST, sm1, st>>>(dy, di, xconv, C, di, dt, A_log, ndir, B, L, H, nc, gstates, nullptr);
+  HNB_LAUNCH_CHECK("ssd_bwd_dstate");
+  const long long total4 = (long long)ndir * B * H * (SN * SP / 4);
+  ssd_state_pass_kernel<true><<<cdiv(total4, 256), 256, 0, st>>>(gstates, decay, H, nc, total4);
+  HNB_LAUNCH_CHECK("ssd_state_pass_rev");
+  ssd_bwd_chunk_kernel<T><<<grid, ST, smb, st>>>(dy, xconv, y, C, di, dt, A_log, Dskip, states, gstates, ndir, B, L, H, nc,
+                                                 dxc, dBC, ddt_x, dscal, dD);
+  HNB_LAUNCH_CHECK("ssd_bwd_chunk");
+  ssd_bwd_ddt_kernel<<<cdiv((long long)ndir * B * H, 8), 256, 0, st>>>(dscal, ddt_x, dt, A_log, ndir, B, L, H, ddt, dA_log);
+  HNB_LAUNCH_CHECK("ssd_bwd_ddt");
+  return HNB_OK;
+}
+
+extern "C" int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int dtype, const float* dt,
+                           const float* A_log, const float* Dskip, const void* states, int ndir, int B, int L, int di,
+                           int N, int H, void* dxc, float* dBC, float* ddt, float* dA_log, float* dD, void* ws2,
+                           int impl, void* stream) {
+  HNB_CHECK_ARG(dy && xconv && y && dt && A_log && Dskip && states && dxc && dBC && ddt && dA_log && dD && ws2,
+                "ssd_bwd: null pointer");
+  int rc = ssd_check("ssd_bwd", ndir, B, L, di, N, H);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 1) {
+    HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_bwd: the tcgen05 path takes bf16 activations");
+    return hnb_ssd_bwd_tc(dy, xconv, y, dt, A_log, Dskip, states, ndir, B, L, di, N, H, dxc, dBC, ddt, dA_log, dD, ws2,
+                          stream);
+  }
+  if (dtype == HNB_BF16)
+    return ssd_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)xconv, (const __nv_bfloat16*)y,
+                                       dt, A_log, Dskip, (const float*)states, ndir, B, L, di, H, (__nv_bfloat16*)dxc,
+                                       dBC, ddt, dA_log, dD, (float*)ws2, st);
+  if (dtype == HNB_F32)
+    return ssd_bwd_impl<float>((const float*)dy, (const float*)xconv, (const float*)y, dt, A_log, Dskip,
+                               (const float*)states, ndir, B, L, di, H, (float*)dxc, dBC, ddt, dA_log, dD, (float*)ws2, st);
+  set_error("ssd_bwd: unsupported dtype");
+  return HNB_ERR_INVALID_ARG;
+}

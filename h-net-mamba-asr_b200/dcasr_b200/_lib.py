@@ -1,0 +1,116 @@
+"""ctypes binding of libhnet_b200.so, generated from include/hnet_b200.h.
+
+The product path has NO fallback: if the shared library is missing, or a kernel call is made with a
+non-CUDA tensor, this module raises.  Signatures are parsed from the header so the binding cannot
+drift from the declared C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhnet_b200.so")
+HEADER = os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "hnet_b200.h")
+
+F32, BF16 = 0, 1
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+class HnbError(RuntimeError):
+    pass
+
+
+def dtype_code(t: torch.dtype) -> int:
+    try:
+        return _DT[t]
+    except KeyError:
+        raise HnbError(f"hnet_b200 kernels take float32 or bfloat16 activations, got {t}") from None
+
+
+def parse_header(path: str = HEADER) -> dict[str, tuple[str, list[str]]]:
+    """name -> (return type, [arg C types]) for every function declared in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"(?:^|\n)\s*((?:const\s+)?[\w ]+?\**)\s*(hnb_\w+)\s*\(([^;{]*?)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if args in ("void", ""):
+            arg_types = []
+        else:
+            arg_types = []
+            for a in args.split(","):
+                a = a.strip()
+                ty = re.sub(r"\s*\w+$", "", a) if not a.endswith("*") else a   # drop the parameter name
+                arg_types.append(ty.strip())
+        out[name] = (ret, arg_types)
+    return out
+
+
+def _ctype(ty: str):
+    ty = ty.replace("const ", "").strip()
+    if ty.endswith("*"):
+        return ctypes.c_char_p if ty == "char*" else ctypes.c_void_p
+    return {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float,
+            "void": None}[ty]
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise HnbError(
+                f"{LIB_PATH} is missing: build it with `python h-net-mamba-asr_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.decls = parse_header()
+        self.fn = {}
+        for name, (ret, args) in self.decls.items():
+            f = getattr(self.cdll, name)
+            f.restype = _ctype(ret)
+            f.argtypes = [_ctype(a) for a in args]
+            self.fn[name] = f
+
+    def raw(self, name: str):
+        return self.fn["hnb_" + name]
+
+    def call(self, name: str, *args) -> None:
+        """Call int hnb_<name>(...) with tensors turned into device pointers; raise on non-zero status."""
+        conv = []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if not a.is_cuda:
+                    raise HnbError(f"hnb_{name}: got a {a.device} tensor; the hot path is CUDA-only")
+                if not a.is_contiguous():
+                    raise HnbError(f"hnb_{name}: tensor argument must be contiguous")
+                conv.append(a.data_ptr())
+            else:
+                conv.append(a)
+        rc = self.fn["hnb_" + name](*conv)
+        if rc != 0:
+            raise HnbError(f"hnb_{name} failed ({rc}): {self.cdll.hnb_last_error().decode()}")
+
+
+_LIB: _Lib | None = None
+
+
+def lib() -> _Lib:
+    global _LIB
+    if _LIB is None:
+        _LIB = _Lib()
+        _LIB.cdll.hnb_last_error.restype = ctypes.c_char_p
+    return _LIB
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().raw("launch_count")())
+
+
+def reset_launch_count() -> None:
+    lib().raw("reset_launch_count")()

@@ -1,0 +1,166 @@
+"""DC-ASR encoder assembly over the CUDA hot path — host-side mirror of ``dcasr.models.encoder``
+(/root/reference/src/dcasr/models/encoder.py: EncoderOutput :40-47, ConvSubsampling4 :55-70,
+DCASREncoder :77-144, build_chunker :33-37).  Same constructor, module tree / ``state_dict`` keys,
+forward signature, output contract and exceptions, so ``build_model`` / ``scripts/train.py`` /
+``scripts/decode.py`` of the reference run on it unchanged.
+
+In scope: the Mamba stacks, the chunk stage(s), proj_in/proj_out and the residual.
+``ConvSubsampling4`` stays on cuDNN/cuBLAS through torch: north_star does not name it (§8f "next").
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .hnet_chunk import DynamicChunker, _autocast_dtype
+from .mamba_block import MambaStack
+
+_CHUNKERS = {"dynamic": DynamicChunker}
+
+
+def register_chunker(name: str, cls) -> None:
+    """Extension seam for the reference's other chunkers (e.g. its pure-torch FixedPoolChunker control)."""
+    _CHUNKERS[str(name).lower()] = cls
+
+
+def build_chunker(kind: str, d_model: int, N, ema_smoothing: bool = True) -> nn.Module:
+    kind = str(kind).lower()
+    if kind not in _CHUNKERS:
+        raise ValueError(f"unknown chunker {kind!r}; choices: {sorted(_CHUNKERS)}")
+    return _CHUNKERS[kind](d_model, N, ema_smoothing=ema_smoothing)
+
+
+@dataclass
+class EncoderOutput:
+    features: torch.Tensor
+    lengths: torch.Tensor
+    ratio_loss: torch.Tensor
+    boundaries: list
+    chunk_embeddings: list
+    kept_fractions: list
+
+
+def _subsampled_length(lengths: torch.Tensor) -> torch.Tensor:
+    return (((lengths - 1) // 2 - 1) // 2).clamp_min(0)
+
+
+class ConvSubsampling4(nn.Module):
+    """x4 time downsample (two Conv2d k3 s2 + ReLU, then Linear).  Library kernels; outside the hot path."""
+
+    def __init__(self, n_mels: int, d_model: int):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv2d(1, d_model, kernel_size=3, stride=2), nn.ReLU(),
+            nn.Conv2d(d_model, d_model, kernel_size=3, stride=2), nn.ReLU())
+        self.proj = nn.Linear(d_model * (((n_mels - 1) // 2 - 1) // 2), d_model)
+
+    def forward(self, feats: torch.Tensor, lengths: torch.Tensor):
+        x = self.conv(feats.unsqueeze(1))
+        B, C, T, F = x.shape
+        return self.proj(x.transpose(1, 2).reshape(B, T, C * F)), _subsampled_length(lengths)
+
+
+class _LinearFn(torch.autograd.Function):
+    """nn.Linear on the tcgen05 GEMM (proj_in / proj_out): y = x W^T + b over [B, L, d_in]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        adt = _autocast_dtype() or x.dtype
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        xa = (x2 if x2.dtype == adt else x2.to(adt)).contiguous()
+        wa = w.to(adt)
+        y = ops.gemm(xa, wa, bias=b.float() if b is not None else None)
+        ctx.save_for_backward(xa, wa)
+        ctx.meta = (shp, x.dtype, w.dtype, b is not None)
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xa, wa = ctx.saved_tensors
+        shp, xdt, wdt, has_b = ctx.meta
+        d2 = dy.reshape(-1, dy.shape[-1])
+        da = (d2 if d2.dtype == xa.dtype else d2.to(xa.dtype)).contiguous()
+        dx = ops.gemm(da, wa, trans_b=True, out_dtype=xdt if xa.dtype == torch.bfloat16 else None)
+        sk = ops.wgrad_splitk(xa.shape[0], wa.shape[0], wa.shape[1]) if xa.dtype == torch.bfloat16 else 1
+        dw = ops.gemm(da, xa, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)
+        db = d2.float().sum(0) if has_b else None
+        return dx.to(xdt).view(shp), dw.to(wdt), (db.to(wdt) if has_b else None)
+
+
+def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    return _LinearFn.apply(x, mod.weight, mod.bias)
+
+
+class DCASREncoder(nn.Module):
+    """Type A (1-stage) or Type B (2-stage) Mamba-H-Net encoder (encoder.py:77-144)."""
+
+    def __init__(self, n_mels: int = 80, d_outer: int = 384, d_main: int = 512,
+                 n_enc: int = 4, n_main: int = 12, n_dec: int = 4, n_mid: int = 4,
+                 arch_type: str = "A", N: int = 1, bidirectional: bool = True,
+                 hnet_ema: bool = True, chunker: str = "dynamic"):
+        super().__init__()
+        if arch_type not in ("A", "B"):
+            raise ValueError(f"arch_type must be 'A' or 'B', got {arch_type!r}")
+        self.arch_type, self.N, self.chunker = arch_type, N, chunker
+        self.subsample = ConvSubsampling4(n_mels, d_outer)
+        self.enc = MambaStack(n_enc, d_outer, bidirectional)
+        self.dec = MambaStack(n_dec, d_outer, bidirectional)
+        if arch_type == "A":
+            self.chunk = build_chunker(chunker, d_outer, N, hnet_ema)
+            self.proj_in = nn.Linear(d_outer, d_main)
+            self.main = MambaStack(n_main, d_main, bidirectional)
+            self.proj_out = nn.Linear(d_main, d_outer)
+        else:
+            nb = math.sqrt(N)
+            self.chunk1 = build_chunker(chunker, d_outer, nb, hnet_ema)
+            self.proj1_in = nn.Linear(d_outer, d_main)
+            self.mid = MambaStack(n_mid, d_main, bidirectional)
+            self.chunk2 = build_chunker(chunker, d_main, nb, hnet_ema)
+            self.main = MambaStack(n_main, d_main, bidirectional)
+            self.mid_dec = MambaStack(n_mid, d_main, bidirectional)
+            self.proj1_out = nn.Linear(d_main, d_outer)
+
+    def forward(self, feats: torch.Tensor, feat_lengths: torch.Tensor) -> EncoderOutput:
+        x, lengths = self.subsample(feats, feat_lengths)
+        return self.forward_hot_path(x, lengths)
+
+    def forward_hot_path(self, x: torch.Tensor, lengths: torch.Tensor) -> EncoderOutput:
+        """Everything after ConvSubsampling4: the path north_star names."""
+        mask = torch.arange(x.shape[1], device=lengths.device)[None, :] < lengths[:, None]
+        l32 = lengths.to(torch.int32)
+        x_enc = self.enc(x, l32)
+        if self.arch_type == "A":
+            return self._forward_A(x_enc, mask, lengths, l32)
+        return self._forward_B(x_enc, mask, lengths, l32)
+
+    @staticmethod
+    def _dechunk_add(chunker, z, co, resid):
+        if isinstance(chunker, DynamicChunker):
+            return chunker.dechunk(z, co, residual=resid)        # fused gather + STE + residual
+        return resid + chunker.dechunk(z, co)
+
+    def _forward_A(self, x_enc, mask, lengths, l32) -> EncoderOutput:
+        co = self.chunk.chunk(x_enc, mask)
+        z = _linear(self.proj_in, co.z)
+        z = self.main(z, co.z_mask.sum(1))
+        z = _linear(self.proj_out, z)
+        x_out = self.dec(self._dechunk_add(self.chunk, z, co, x_enc), l32)
+        return EncoderOutput(x_out, lengths, co.ratio_loss, [(co.p, co.b)], [co.z], [co.kept_fraction])
+
+    def _forward_B(self, x_enc, mask, lengths, l32) -> EncoderOutput:
+        co1 = self.chunk1.chunk(x_enc, mask)
+        n1 = co1.z_mask.sum(1)
+        z1 = self.mid(_linear(self.proj1_in, co1.z), n1)
+        co2 = self.chunk2.chunk(z1, co1.z_mask)
+        z2 = self.main(co2.z, co2.z_mask.sum(1))
+        z1_dec = self.mid_dec(self._dechunk_add(self.chunk2, z2, co2, z1), n1)
+        x_dech_in = _linear(self.proj1_out, z1_dec)
+        x_out = self.dec(self._dechunk_add(self.chunk1, x_dech_in, co1, x_enc), l32)
+        return EncoderOutput(x_out, lengths, co1.ratio_loss + co2.ratio_loss,
+                             [(co1.p, co1.b), (co2.p, co2.b)], [co1.z, co2.z],
+                             [co1.kept_fraction, co2.kept_fraction])

@@ -1,0 +1,45 @@
+"""Drop-in installation under the reference package.
+
+    import dcasr_b200; dcasr_b200.install()      # before `import dcasr.tasks...`
+
+After this, ``from mamba_ssm import Mamba2`` (reference src/dcasr/models/mamba_block.py:12) resolves to
+the B200 mixer, and ``dcasr.models.hnet_chunk`` / ``.mamba_block`` / ``.encoder`` expose the B200 classes,
+so ``dcasr.tasks.asr_task.build_model`` (reference :129-146), ``scripts/train.py`` and
+``scripts/decode.py`` construct and run the CUDA hot path with no source change.
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+
+def install(patch_dcasr: bool = True) -> None:
+    from . import encoder, hnet_chunk, mamba_block
+
+    shim = types.ModuleType("mamba_ssm")
+    shim.Mamba2 = mamba_block.Mamba2
+    shim.__doc__ = "hnet_b200 stand-in for mamba_ssm (Mamba2 only)"
+    sys.modules["mamba_ssm"] = shim
+    if not patch_dcasr:
+        return
+    try:
+        import dcasr.models as ref_models                      # the reference package, if importable
+    except Exception:
+        return
+    import dcasr.models.hnet_chunk as ref_chunk
+    for name in ("ChunkOutput", "RoutingModule", "DynamicChunker", "ratio_loss"):
+        setattr(ref_chunk, name, getattr(hnet_chunk, name))
+        setattr(ref_models, name, getattr(hnet_chunk, name))
+    try:
+        from dcasr.models.fixed_pool import FixedPoolChunker
+        encoder.register_chunker("fixed", FixedPoolChunker)    # the reference's own pure-torch control
+    except Exception:
+        pass
+    import dcasr.models.mamba_block as ref_mb
+    for name in ("reverse_sequences", "MambaBlock", "MambaStack"):
+        setattr(ref_mb, name, getattr(mamba_block, name))
+    import dcasr.models.encoder as ref_enc
+    for name in ("DCASREncoder", "EncoderOutput", "ConvSubsampling4", "build_chunker"):
+        setattr(ref_enc, name, getattr(encoder, name))
+    if "dcasr.tasks.asr_task" in sys.modules:
+        sys.modules["dcasr.tasks.asr_task"].DCASREncoder = encoder.DCASREncoder

@@ -1,0 +1,251 @@
+"""Mamba-2 mixer, bidirectional pre-norm block and stack on the CUDA hot path — host-side mirror of
+``mamba_ssm.Mamba2`` (as used by the reference) and of ``dcasr.models.mamba_block``
+(/root/reference/src/dcasr/models/mamba_block.py: reverse_sequences :19-28, MambaBlock :31-56,
+MambaStack :59-73).  Parameter names, shapes and ``_no_weight_decay`` tags equal the upstream module
+(SURVEY.md §3.4), so reference checkpoints load unchanged.
+
+One ``MambaBlock`` call is ONE autograd node:
+    LayerNorm -> in_proj of BOTH directions as one GEMM -> conv1d+SiLU / softplus(dt) written in scan
+    order (the length-aware reversal is index arithmetic, never a gather) -> SSD scan -> gated RMSNorm
+    (back to natural order) -> out_proj of both directions as one GEMM with the residual add.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import HnbError
+from .hnet_chunk import _autocast_dtype
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def reverse_sequences(x: torch.Tensor, lengths: torch.Tensor | None = None) -> torch.Tensor:
+    """Reverse each row's valid span, padding left in place (mamba_block.py:19-28).  Kept for API parity;
+    the block itself never calls it (the kernels index through the same map)."""
+    if lengths is None:
+        return torch.flip(x, dims=[1])
+    B, T, _ = x.shape
+    pos = torch.arange(T, device=x.device).unsqueeze(0).expand(B, T)
+    L = lengths.to(x.device).view(B, 1)
+    idx = torch.where(pos < L, L - 1 - pos, pos).clamp_(0, T - 1)
+    return torch.gather(x, 1, idx.unsqueeze(-1).expand_as(x))
+
+
+class _RMSNormWeight(nn.Module):
+    def __init__(self, d: int, eps: float = 1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+        self.eps = eps
+
+
+class Mamba2(nn.Module):
+    """Drop-in for ``mamba_ssm.Mamba2(d_model, d_state, d_conv, expand, headdim)`` with package defaults
+    (ngroups=1, rmsnorm, norm_before_gate=False, no in/out bias, conv bias, dt_limit=(0, inf))."""
+
+    def __init__(self, d_model, d_state=128, d_conv=4, expand=2, headdim=64, ngroups=1,
+                 dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4, A_init_range=(1, 16), **unused):
+        super().__init__()
+        if ngroups != 1 or d_conv != 4:
+            raise HnbError("Mamba2: kernels are built for ngroups=1, d_conv=4")
+        self.d_model, self.d_state, self.d_conv, self.headdim = d_model, d_state, d_conv, headdim
+        self.d_inner = expand * d_model
+        if self.d_inner % headdim:
+            raise HnbError("Mamba2: expand*d_model must be divisible by headdim")
+        self.nheads = self.d_inner // headdim
+        conv_dim = self.d_inner + 2 * d_state
+        self.in_proj = nn.Linear(d_model, 2 * self.d_inner + 2 * d_state + self.nheads, bias=False)
+        self.conv1d = nn.Conv1d(conv_dim, conv_dim, d_conv, groups=conv_dim, padding=d_conv - 1, bias=True)
+        dt = torch.exp(torch.rand(self.nheads) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min))
+        dt = dt.clamp(min=dt_init_floor)
+        self.dt_bias = nn.Parameter(dt + torch.log(-torch.expm1(-dt)))
+        self.dt_bias._no_weight_decay = True
+        self.A_log = nn.Parameter(torch.log(torch.empty(self.nheads).uniform_(*A_init_range)))
+        self.A_log._no_weight_decay = True
+        self.D = nn.Parameter(torch.ones(self.nheads))
+        self.D._no_weight_decay = True
+        self.norm = _RMSNormWeight(self.d_inner)
+        self.out_proj = nn.Linear(self.d_inner, d_model, bias=False)
+
+    def _params(self):
+        return (self.in_proj.weight, self.conv1d.weight, self.conv1d.bias, self.dt_bias, self.A_log, self.D,
+                self.norm.weight, self.out_proj.weight)
+
+    def forward(self, u: torch.Tensor) -> torch.Tensor:
+        return _MixerFn.apply(u, None, None, None, 1, self.d_inner, self.d_state, self.nheads, False,
+                              *self._params())
+
+
+NP = 8   # parameters per direction, in _params() order
+
+
+def _mixer_forward(h2, lengths, B, L, ndir, di, N, H, params):
+    """h2 [B*L, d] (activation dtype) -> (ynorm [B*L, ndir*di], saved tensors)."""
+    adt = h2.dtype
+    dip = 2 * di + 2 * N + H
+    dstride = _round_up(dip, 8)
+    d = h2.shape[1]
+    if ndir == 1 and dstride == dip:
+        Win = params[0].to(adt)
+    else:
+        Win = h2.new_zeros((ndir * dstride, d))
+        for r in range(ndir):
+            Win[r * dstride: r * dstride + dip] = params[r * NP + 0]
+    zx = ops.gemm(h2, Win)                                               # [B*L, ndir*dstride]
+    C = di + 2 * N
+    conv_w = torch.stack([params[r * NP + 1].reshape(C, 4) for r in range(ndir)]).float().contiguous()
+    conv_b = torch.stack([params[r * NP + 2] for r in range(ndir)]).float().contiguous()
+    dt_bias = torch.stack([params[r * NP + 3] for r in range(ndir)]).float().contiguous()
+    A_log = torch.stack([params[r * NP + 4] for r in range(ndir)]).float().contiguous()
+    Dk = torch.stack([params[r * NP + 5] for r in range(ndir)]).float().contiguous()
+    norm_w = torch.stack([params[r * NP + 6] for r in range(ndir)]).float().contiguous()
+    xconv, dt = ops.conv_fwd(zx, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H)
+    y, ws = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H)
+    yn, rstd = ops.gated_norm_fwd(y, zx, dstride, lengths, norm_w, ndir, B, L, di)
+    Wout = (params[7] if ndir == 1 else torch.cat([params[r * NP + 7] for r in range(ndir)], 1)).to(adt)
+    saved = (Win, zx, conv_w, conv_b, dt_bias, A_log, Dk, norm_w, xconv, dt, y, ws, yn, rstd, Wout)
+    return yn, Wout, saved, dstride
+
+
+def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved):
+    """dyn = d loss / d ynorm [B*L, ndir*di] -> (dh2, per-direction parameter grads except out_proj)."""
+    Win, zx, conv_w, conv_b, dt_bias, A_log, Dk, norm_w, xconv, dt, y, ws, yn, rstd, Wout = saved
+    dip = 2 * di + 2 * N + H
+    dzx = torch.empty_like(zx)
+    if dstride != dip:
+        dzx.view(-1, ndir, dstride)[:, :, dip:] = 0                      # pad columns feed the GEMMs below
+    dy, dnorm_w = ops.gated_norm_bwd(dyn, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx)
+    dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H)
+    dconv_w, dconv_b, ddt_bias = ops.conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias,
+                                              ndir, B, L, di, N, H, dzx)
+    dh2 = ops.gemm(dzx, Win, trans_b=True)                               # dgrad [B*L, d]
+    sk = ops.wgrad_splitk(B * L, Win.shape[0], Win.shape[1]) if dzx.dtype == torch.bfloat16 else 1
+    dWin = ops.gemm(dzx, h2, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)   # [ndir*dstride, d]
+    grads = []
+    for r in range(ndir):
+        grads.append((dWin[r * dstride: r * dstride + dip], dconv_w[r].reshape(-1, 1, 4), dconv_b[r], ddt_bias[r],
+                      dA[r], dD[r], dnorm_w[r]))
+    return dh2, grads
+
+
+class _MixerFn(torch.autograd.Function):
+    """(optional LayerNorm) -> mixer(s) -> (optional residual).  Serves Mamba2 (1 direction, no norm, no
+    residual) and MambaBlock (norm + residual, 1 or 2 directions)."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, ln_w, ln_b, ndir, di, N, H, block, *params):
+        B, L, d = x.shape
+        adt = _autocast_dtype() or x.dtype
+        x2 = x.reshape(B * L, d)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        if lengths is not None:
+            lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+        if block:
+            h2, mean, rstd_ln = ops.layernorm_fwd(x2, ln_w.float(), ln_b.float(), 1e-5, adt)
+        else:
+            h2, mean, rstd_ln = (x2 if x2.dtype == adt else x2.to(adt)), None, None
+        yn, Wout, saved, dstride = _mixer_forward(h2, lengths, B, L, ndir, di, N, H, params)
+        if block:
+            # residual stream keeps the dtype it arrived in (reference: x + y under autocast)
+            if adt == torch.float32:
+                out2 = ops.gemm(yn, Wout, residual=x2)
+            elif x2.dtype == torch.float32:
+                out2 = ops.gemm(yn, Wout, residual=x2, out_dtype=torch.float32)
+            else:
+                out2 = ops.gemm(yn, Wout, residual=x2, out_dtype=torch.bfloat16)
+        else:
+            out2 = ops.gemm(yn, Wout)
+        ctx.save_for_backward(x2, lengths, ln_w, mean, rstd_ln, h2, *saved)
+        ctx.meta = (B, L, d, ndir, di, N, H, block, dstride, x.dtype, [p.dtype for p in params])
+        return out2.view(B, L, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, lengths, ln_w, mean, rstd_ln, h2, *saved = ctx.saved_tensors
+        B, L, d, ndir, di, N, H, block, dstride, xdt, pdts = ctx.meta
+        Wout, yn = saved[-1], saved[-3]
+        adt = h2.dtype
+        dout2 = dout.reshape(B * L, d)
+        dout2 = dout2 if dout2.is_contiguous() else dout2.contiguous()
+        da = dout2 if dout2.dtype == adt else dout2.to(adt)
+        dyn = ops.gemm(da, Wout, trans_b=True)                           # [B*L, ndir*di]
+        sk = ops.wgrad_splitk(B * L, d, ndir * di) if adt == torch.bfloat16 else 1
+        dWout = ops.gemm(da, yn, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)   # [d, ndir*di]
+        dh2, grads = _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved)
+        if block:
+            dres = dout2 if dout2.dtype == xdt else dout2.to(xdt)
+            dx2, dg, db = ops.layernorm_bwd(dh2, x2, ln_w.float(), mean, rstd_ln, dres)
+        else:
+            dx2, dg, db = (dh2 if dh2.dtype == xdt else dh2.to(xdt)), None, None
+        pg = []
+        for r in range(ndir):
+            g = list(grads[r]) + [dWout[:, r * di:(r + 1) * di]]
+            pg += [t.to(pdts[r * NP + i]) for i, t in enumerate(g)]
+        return (dx2.view(B, L, d), None, dg, db, None, None, None, None, None, *pg)
+
+
+class MambaBlock(nn.Module):
+    """y = x + Mamba2_fwd(norm(x)) [+ reverse(Mamba2_bwd(reverse(norm(x))))]  (mamba_block.py:31-56)."""
+
+    def __init__(self, d_model: int, bidirectional: bool = True, d_state: int = 128,
+                 d_conv: int = 4, expand: int = 2, headdim: int = 64):
+        super().__init__()
+        assert (expand * d_model) % headdim == 0, \
+            f"expand*d_model ({expand * d_model}) must be divisible by headdim ({headdim})"
+        self.bidirectional = bidirectional
+        self.norm = nn.LayerNorm(d_model)
+        kw = dict(d_model=d_model, d_state=d_state, d_conv=d_conv, expand=expand, headdim=headdim)
+        self.fwd = Mamba2(**kw)
+        self.bwd = Mamba2(**kw) if bidirectional else None
+
+    def forward(self, x: torch.Tensor, lengths: torch.Tensor | None = None) -> torch.Tensor:
+        m = self.fwd
+        params = m._params() + (self.bwd._params() if self.bwd is not None else ())
+        ndir = 2 if self.bwd is not None else 1
+        return _MixerFn.apply(x, lengths if ndir == 2 else None, self.norm.weight, self.norm.bias, ndir,
+                              m.d_inner, m.d_state, m.nheads, True, *params)
+
+
+class _FinalNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        B, L, d = x.shape
+        x2 = x.reshape(B * L, d)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        # autocast runs layer_norm in fp32: the stack output is fp32 under bf16 autocast
+        out_dtype = torch.float32 if _autocast_dtype() is not None else x.dtype
+        y, mean, rstd = ops.layernorm_fwd(x2, w.float(), b.float(), eps, out_dtype)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.meta = (B, L, d, w.dtype)
+        return y.view(B, L, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        B, L, d, wdt = ctx.meta
+        dy2 = dy.reshape(B * L, d)
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        dx, dg, db = ops.layernorm_bwd(dy2, x2, w.float(), mean, rstd, None)
+        return dx.view(B, L, d), dg.to(wdt), db.to(wdt), None
+
+
+class MambaStack(nn.Module):
+    """n_layers MambaBlocks + a final LayerNorm (mamba_block.py:59-73)."""
+
+    def __init__(self, n_layers: int, d_model: int, bidirectional: bool = True, **block_kw):
+        super().__init__()
+        self.layers = nn.ModuleList(
+            MambaBlock(d_model, bidirectional=bidirectional, **block_kw) for _ in range(n_layers))
+        self.norm = nn.LayerNorm(d_model)
+
+    def forward(self, x: torch.Tensor, lengths: torch.Tensor | None = None) -> torch.Tensor:
+        if lengths is not None and lengths.dtype != torch.int32:
+            lengths = lengths.to(torch.int32)
+        for layer in self.layers:
+            x = layer(x, lengths)
+        return _FinalNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps)

@@ -1,0 +1,253 @@
+"""Low-level wrappers over the C ABI (include/hnet_b200.h): tensor plumbing only, no arithmetic.
+
+Every function allocates its outputs with torch (PyTorch owns device memory), enqueues the kernels on
+torch's current CUDA stream through ctypes, and returns tensors.  There is no CPU path: a CPU tensor
+raises HnbError.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import BF16, F32, HnbError, dtype_code, lib, stream
+
+# ssd implementation selector: 0 = CUDA-core fp32 (exact), 1 = tcgen05 (bf16). "auto" picks by dtype.
+SSD_IMPL = "auto"
+# dense projections: "tcgen05" (own kernel) for bf16; fp32 always uses the exact CUDA-core GEMM
+GEMM_BF16_IMPL = "tcgen05"
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense projections
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias=None, residual=None,
+         out_dtype=None, splitk=1, out=None) -> torch.Tensor:
+    """C[M,N] = op(a) @ op(b)^T-convention of hnb_gemm_*:
+       trans_a=False: a is [M,K];  True: a is [K,M].   trans_b=False: b is [N,K] (nn.Linear weight);  True: b is [K,N].
+       2-D tensors whose rows are contiguous (stride(1) == 1); row strides are honoured."""
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise HnbError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    L = lib()
+    if a.dtype == torch.float32:
+        if b.dtype != torch.float32:
+            raise HnbError("gemm: mixed operand dtypes")
+        c = out if out is not None else _empty((M, N), torch.float32, a)
+        r = residual
+        L.call("gemm_f32", a, a.stride(0), int(trans_a), b, b.stride(0), int(trans_b), M, N, K,
+               bias, r, r.stride(0) if r is not None else 0, c, c.stride(0), 0, stream())
+        return c
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise HnbError(f"gemm: unsupported operand dtypes {a.dtype}, {b.dtype}")
+    od = out_dtype or torch.bfloat16
+    if splitk > 1:
+        c = out if out is not None else torch.zeros((M, N), dtype=torch.float32, device=a.device)
+        od = torch.float32
+    else:
+        c = out if out is not None else _empty((M, N), od, a)
+    r = residual
+    if r is not None and r.dtype != od:
+        raise HnbError("gemm: residual dtype must equal the output dtype")
+    L.call("gemm_bf16", a, a.stride(0), int(trans_a), b, b.stride(0), int(trans_b), M, N, K, bias,
+           r, r.stride(0) if r is not None else 0, c, c.stride(0), dtype_code(od), int(splitk), stream())
+    return c
+
+
+def wgrad_splitk(k_tokens: int, m: int, n: int) -> int:
+    """split-K factor for weight gradients (K = tokens): enough CTAs to cover 148 SMs x 2."""
+    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+    kb = (k_tokens + 63) // 64
+    return max(1, min(kb, (296 + tiles - 1) // tiles))
+
+
+# ------------------------------------------------------------------------------------------------
+# H-Net stage
+# ------------------------------------------------------------------------------------------------
+def router_fwd(qk, mask_u8, B, L, D, pb_dtype, N):
+    L_ = lib()
+    n = B * L
+    p = _empty((B, L), pb_dtype, qk)
+    b = _empty((B, L), pb_dtype, qk)
+    nblk = L_.raw("router_num_partials")(n)
+    partial = _empty((nblk * 4,), torch.float32, qk)
+    stats = _empty((8,), torch.float32, qk)
+    L_.call("router_fwd", qk, dtype_code(qk.dtype), qk.stride(0), mask_u8, B, L, D, 1e-6, p, b,
+            dtype_code(pb_dtype), partial, stream())
+    L_.call("ratio_finalize", partial, nblk, float(N), stats, stream())
+    return p, b, stats
+
+
+def router_bwd(qk, mask_u8, B, L, D, dp, dratio, stats, N):
+    dqk = torch.empty_like(qk)
+    lib().call("router_bwd", qk, dtype_code(qk.dtype), qk.stride(0), mask_u8, B, L, D, 1e-6, dp, dratio, stats,
+               float(N), dqk, stream())
+    return dqk
+
+
+def boundary_scan(b, B, L):
+    L_ = lib()
+    memb = _empty((B, L), torch.int64, b)
+    counts = _empty((B,), torch.int32, b)
+    ws = _empty((L_.raw("boundary_scan_ws_bytes")(B * L),), torch.uint8, b)
+    L_.call("boundary_scan", b, dtype_code(b.dtype), B, L, memb, counts, ws, stream())
+    return memb, counts
+
+
+def compact_rows(x, p, b, memb, counts, M):
+    B, L, D = x.shape
+    z = _empty((B, M, D), x.dtype, x)
+    zmask = _empty((B, M), torch.uint8, x)
+    P = _empty((B, M), torch.float32, x)
+    starts = _empty((B, M), torch.int32, x)
+    lib().call("compact_rows", x, dtype_code(x.dtype), p, b, dtype_code(p.dtype), memb, counts, B, L, D, M,
+               z, zmask, P, starts, stream())
+    return z, zmask, P, starts
+
+
+def compact_rows_bwd(dz, b, memb, L, dx=None):
+    B, M, D = dz.shape
+    acc = dx is not None
+    if dx is None:
+        dx = _empty((B, L, D), dz.dtype, dz)
+    lib().call("compact_rows_bwd", dz, dtype_code(dz.dtype), b, dtype_code(b.dtype), memb, B, L, D, M, dx,
+               int(acc), stream())
+    return dx
+
+
+def ema_fwd(x, P, p_clamp=1e-4):
+    B, M, D = x.shape
+    out = torch.empty_like(x)
+    lib().call("ema_fwd", x, dtype_code(x.dtype), P, B, M, D, float(p_clamp), out, stream())
+    return out
+
+
+def ema_bwd(dout, x, out, P, p_clamp=1e-4):
+    B, M, D = x.shape
+    dx = torch.empty_like(x)
+    dP = torch.zeros_like(P)
+    lib().call("ema_bwd", dout, x, out, dtype_code(x.dtype), P, B, M, D, float(p_clamp), dx, dP, stream())
+    return dx, dP
+
+
+def upsample_fwd(zbar, memb, p, b, resid, y_dtype):
+    B, M, D = zbar.shape
+    L = memb.shape[1]
+    y = _empty((B, L, D), y_dtype, zbar)
+    lib().call("upsample_fwd", zbar, dtype_code(zbar.dtype), memb, p, b, dtype_code(p.dtype), resid, B, L, D, M,
+               y, dtype_code(y_dtype), stream())
+    return y
+
+
+def upsample_bwd(dy, zbar, memb, starts, counts, p, b):
+    B, M, D = zbar.shape
+    L = memb.shape[1]
+    dz = torch.empty_like(zbar)
+    dp = _empty((B, L), torch.float32, zbar)
+    lib().call("upsample_bwd", dy, dtype_code(dy.dtype), zbar, dtype_code(zbar.dtype), memb, starts, counts, p, b,
+               dtype_code(p.dtype), B, L, D, M, dz, dp, stream())
+    return dz, dp
+
+
+def masked_ratio_stats(p, b, mask_u8, N):
+    L_ = lib()
+    n = p.numel()
+    nblk = (n + 255) // 256
+    partial = _empty((nblk * 4,), torch.float32, p)
+    stats = _empty((8,), torch.float32, p)
+    L_.call("masked_sums", p, b, dtype_code(p.dtype), mask_u8, n, partial, stream())
+    L_.call("ratio_finalize", partial, nblk, float(N), stats, stream())
+    return stats
+
+
+# ------------------------------------------------------------------------------------------------
+# Mamba-2 block
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x2, gamma, beta, eps, y_dtype):
+    rows, d = x2.shape
+    y = _empty((rows, d), y_dtype, x2)
+    mean = _empty((rows,), torch.float32, x2)
+    rstd = _empty((rows,), torch.float32, x2)
+    lib().call("layernorm_fwd", x2, dtype_code(x2.dtype), gamma, beta, rows, d, float(eps), y, dtype_code(y_dtype),
+               mean, rstd, stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x2, gamma, mean, rstd, dres):
+    rows, d = x2.shape
+    dx = torch.empty_like(x2)
+    dg = torch.zeros(d, dtype=torch.float32, device=x2.device)
+    db = torch.zeros(d, dtype=torch.float32, device=x2.device)
+    lib().call("layernorm_bwd", dy, dtype_code(dy.dtype), x2, dtype_code(x2.dtype), gamma, mean, rstd, dres, rows, d,
+               dx, dtype_code(dx.dtype), dg, db, stream())
+    return dx, dg, db
+
+
+def conv_fwd(zx, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H):
+    C = di + 2 * N
+    xconv = _empty((ndir, B * L, C), zx.dtype, zx)
+    dt = _empty((ndir, B * L, H), torch.float32, zx)
+    lib().call("conv_fwd", zx, dtype_code(zx.dtype), zx.stride(0), dstride, lengths, conv_w, conv_b, dt_bias,
+               ndir, B, L, di, N, H, xconv, dt, stream())
+    return xconv, dt
+
+
+def conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, dzx):
+    dw = torch.zeros_like(conv_w)
+    db = torch.zeros_like(conv_b)
+    ddtb = torch.zeros_like(dt_bias)
+    lib().call("conv_bwd", zx, dxc, dtype_code(zx.dtype), zx.stride(0), dstride, dBC, ddt, lengths, conv_w, conv_b,
+               dt_bias, ndir, B, L, di, N, H, dzx, dw, db, ddtb, stream())
+    return dw, db, ddtb
+
+
+def ssd_impl_for(dtype) -> int:
+    if SSD_IMPL == "auto":
+        return 0
+    return int(SSD_IMPL)
+
+
+def ssd_fwd(xconv, dt, A_log, D, ndir, B, L, di, N, H):
+    L_ = lib()
+    y = _empty((ndir, B * L, di), xconv.dtype, xconv)
+    ws = _empty((L_.raw("ssd_ws_bytes")(ndir, B, L, di, N, H) // 4,), torch.float32, xconv)
+    L_.call("ssd_fwd", xconv, dtype_code(xconv.dtype), dt, A_log, D, ndir, B, L, di, N, H, y, ws,
+            ssd_impl_for(xconv.dtype), stream())
+    return y, ws
+
+
+def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H):
+    L_ = lib()
+    dxc = torch.empty_like(dy)
+    dBC = _empty((ndir, B * L, 2 * N), torch.float32, dy)
+    ddt = torch.empty_like(dt)
+    dA = torch.zeros_like(A_log)
+    dD = torch.zeros_like(D)
+    ws2 = _empty((L_.raw("ssd_ws_bytes")(ndir, B, L, di, N, H) // 4,), torch.float32, dy)
+    L_.call("ssd_bwd", dy, xconv, y, dtype_code(dy.dtype), dt, A_log, D, ws, ndir, B, L, di, N, H, dxc, dBC, ddt,
+            dA, dD, ws2, ssd_impl_for(dy.dtype), stream())
+    return dxc, dBC, ddt, dA, dD
+
+
+def gated_norm_fwd(y, zx, dstride, lengths, norm_w, ndir, B, L, di, eps=1e-5):
+    out = _empty((B * L, ndir * di), y.dtype, y)
+    rstd = _empty((ndir, B * L), torch.float32, y)
+    lib().call("gated_norm_fwd", y, zx, dtype_code(y.dtype), zx.stride(0), dstride, lengths, norm_w, ndir, B, L, di,
+               float(eps), out, rstd, stream())
+    return out, rstd
+
+
+def gated_norm_bwd(dout, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx):
+    dy = torch.empty_like(y)
+    dw = torch.zeros_like(norm_w)
+    lib().call("gated_norm_bwd", dout, y, zx, dtype_code(y.dtype), zx.stride(0), dstride, lengths, norm_w, rstd,
+               ndir, B, L, di, dy, dzx, dw, stream())
+    return dy, dw

@@ -1,0 +1,196 @@
+/* hnet_b200 — C ABI of the B200-native H-Net / Mamba-2 encoder hot path.
+ *
+ * The reference (anshulk-cmu/H-Net-Mamba-ASR, package `dcasr`) has no FFI of its own: the
+ * boundary is Python class identity.  This header is the seam a maintainer
+ * binds with ctypes; every entry point names the reference code whose
+ * arithmetic it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *  - no allocation, no internal streams or threads: the caller owns every buffer and workspace;
+ *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns at once;
+ *  - return 0 on success, a HNB_ERR_* code otherwise; hnb_last_error() gives the message
+ *    (thread-local);
+ *  - activations are row-major [B, L, D] flattened to [B*L, D]; `dtype` says how they are stored,
+ *    arithmetic is always fp32 (tensor-core contractions: bf16 operands, fp32 accumulate);
+ *  - "scan order" (Mamba kernels): direction 0 is natural time; direction 1 walks each row's
+ *    valid span [0, len_b) back to front and leaves the right padding in place, which is the
+ *    reference's reverse_sequences() (src/dcasr/models/mamba_block.py:19-28) done by index
+ *    arithmetic instead of two gathers.
+ */
+#ifndef HNET_B200_H
+#define HNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HNB_OK 0
+#define HNB_ERR_INVALID_ARG 1
+#define HNB_ERR_CUDA 2
+#define HNB_ERR_UNSUPPORTED 3
+
+#define HNB_F32 0
+#define HNB_BF16 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int hnb_version(void);
+const char* hnb_last_error(void);
+/* number of kernels this library has launched since the last reset (bench.py: gpu_launches) */
+long long hnb_launch_count(void);
+void hnb_reset_launch_count(void);
+
+/* ---- H-Net dynamic chunking stage -------------------------------------------------------- */
+
+/* RoutingModule.forward epilogue (src/dcasr/models/hnet_chunk.py:98-108) fused with the
+ * ratio-loss partial sums (hnet_chunk.py:126-134).
+ * qk      [B*L, ldqk]  q in columns [0,D), k in columns [D,2D)   (the W_q/W_k GEMM output)
+ * mask    [B*L] uint8 (1 = valid) or NULL
+ * p, b    [B*L] out, stored as pb_dtype: p = 0.5(1-cos(q_t,k_{t-1})), p[:,0]=1, clamp, b=[p>=.5], *mask
+ * partial [nblk*4] float workspace, nblk = hnb_router_num_partials(B*L) */
+int hnb_router_num_partials(long long n_tokens);
+int hnb_router_fwd(const void* qk, int qk_dtype, long long ldqk, const uint8_t* mask,
+                   int B, int L, int D, float eps, void* p, void* b, int pb_dtype,
+                   float* partial, void* stream);
+
+/* ratio_loss (hnet_chunk.py:117-136) + kept_fraction (hnet_chunk.py:193-194) from the partial sums.
+ * stats[8] out: [0]=ratio loss, [1]=kept fraction, [2]=F, [3]=G, [4]=denominator, [5]=sum b, [6]=sum p */
+int hnb_ratio_finalize(const float* partial, int nblk, float N, float* stats, void* stream);
+
+/* backward of the two above: d qk from d p.
+ * dp_ext  [B*L] float or NULL : gradient arriving at p from other consumers (STE, EMA, user code)
+ * dratio  [1] float or NULL   : gradient arriving at the ratio-loss scalar */
+int hnb_router_bwd(const void* qk, int qk_dtype, long long ldqk, const uint8_t* mask,
+                   int B, int L, int D, float eps, const float* dp_ext, const float* dratio,
+                   const float* stats, float N, void* dqk, void* stream);
+
+/* membership = clamp(cumsum(b>0.5)-1, 0) (int64) and per-row counts (hnet_chunk.py:182-184) as ONE
+ * single-pass segmented decoupled-look-back scan over the flattened [B*L] flags.
+ * ws: workspace of hnb_boundary_scan_ws_bytes(B*L) bytes (zeroed by the call). */
+long long hnb_boundary_scan_ws_bytes(long long n_tokens);
+int hnb_boundary_scan(const void* b, int pb_dtype, int B, int L, int64_t* membership,
+                      int32_t* counts, void* ws, void* stream);
+
+/* downsample stream compaction (hnet_chunk.py:188-192 and :214-218): kept rows of x -> z[B,M,D]
+ * (pad slots zero-filled), z_mask, downsampled P, and starts[b,j] = frame index of the j-th kept frame
+ * (L for pad slots).  M = max(1, max counts) is read by the host between scan and compaction. */
+int hnb_compact_rows(const void* x, int x_dtype, const void* p, const void* b, int pb_dtype,
+                     const int64_t* membership, const int32_t* counts, int B, int L, int D, int M,
+                     void* z, uint8_t* z_mask, float* P, int32_t* starts, void* stream);
+
+/* backward of the compaction: dx[b,t] (+)= b>0.5 ? dz[b, membership[b,t]] : 0 */
+int hnb_compact_rows_bwd(const void* dz, int dtype, const void* b, int pb_dtype,
+                         const int64_t* membership, int B, int L, int D, int M,
+                         void* dx, int accumulate, void* stream);
+
+/* DynamicChunker._ema (hnet_chunk.py:226-248) as a linear-time scan:
+ * out_0 = x_0, out_t = pc_t x_t + (1-pc_t) out_{t-1}, pc = clamp(P, p_clamp, 1-p_clamp) */
+int hnb_ema_fwd(const void* x, int dtype, const float* P, int B, int M, int D, float p_clamp,
+                void* out, void* stream);
+/* backward: dx, dP (dP must be zero-initialised; zero gradient where P is outside the clamp band) */
+int hnb_ema_bwd(const void* dout, const void* x, const void* out, int dtype, const float* P,
+                int B, int M, int D, float p_clamp, void* dx, float* dP, void* stream);
+
+/* upsample gather + confidence STE (+ the encoder's residual add) (hnet_chunk.py:220-224,
+ * encoder.py:130):  y[b,t] = resid[b,t] + zbar[b, membership[b,t]] * (c + (1-c)),  c = b ? p : 1-p */
+int hnb_upsample_fwd(const void* zbar, int z_dtype, const int64_t* membership, const void* p,
+                     const void* b, int pb_dtype, const void* resid, int B, int L, int D, int M,
+                     void* y, int y_dtype, void* stream);
+/* backward: dzbar[b,j] = sum over the frames of chunk j of dy * ste;  dp[b,t] = +-<dy[b,t], zbar[b,j]> */
+int hnb_upsample_bwd(const void* dy, int y_dtype, const void* zbar, int z_dtype,
+                     const int64_t* membership, const int32_t* starts, const int32_t* counts,
+                     const void* p, const void* b, int pb_dtype, int B, int L, int D, int M,
+                     void* dzbar, float* dp, void* stream);
+
+/* masked sums for a stand-alone ratio_loss(p, b, N, mask) call: partial[nblk*4] as in hnb_router_fwd */
+int hnb_masked_sums(const void* p, const void* b, int pb_dtype, const uint8_t* mask, long long n,
+                    float* partial, void* stream);
+
+/* ---- Mamba-2 block ----------------------------------------------------------------------- */
+
+/* nn.LayerNorm (src/dcasr/models/mamba_block.py:51,73). mean/rstd [rows] float are saved for backward. */
+int hnb_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta,
+                      long long rows, int d, float eps, void* y, int y_dtype,
+                      float* mean, float* rstd, void* stream);
+/* dx = (dres ? dres : 0) + LN'(dy);  dgamma/dbeta [d] are ACCUMULATED (caller zero-initialises) */
+int hnb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                      const float* mean, const float* rstd, const void* dres, long long rows, int d,
+                      void* dx, int dx_dtype, float* dgamma, float* dbeta, void* stream);
+
+/* Layout of the fused in-projection output `zxbcdt` [B*L, ldz] used by the kernels below, for ndir
+ * directions, d_inner = di, d_state = N, heads = H, conv channels C = di + 2N.  Direction r owns the
+ * column block [r*dstride, r*dstride + 2di+2N+H) in mamba_ssm's own in_proj order  z | xBC | dt :
+ *   z   : [r*dstride, +di)      xBC : [r*dstride + di, +C)      dt : [r*dstride + di + C, +H)
+ * dstride >= 2di+2N+H is rounded up so that every block starts 16-byte aligned; the pad columns come out
+ * of the GEMM as zeros (zero weight rows) and are never read. */
+
+/* causal depthwise conv1d(k=4)+SiLU over xBC and dt = softplus(dt_raw + dt_bias), both written in
+ * SCAN ORDER (mamba_ssm causal_conv1d_fn + _chunk_cumsum_fwd's softplus).
+ * conv_w [ndir, C, 4], conv_b [ndir, C], dt_bias [ndir, H] float; lengths [B] int32 or NULL.
+ * xconv [ndir, B*L, C] (act dtype), dt [ndir, B*L, H] float. */
+int hnb_conv_fwd(const void* zxbcdt, int dtype, long long ldz, long long dstride, const int32_t* lengths,
+                 const float* conv_w, const float* conv_b, const float* dt_bias,
+                 int ndir, int B, int L, int di, int N, int H,
+                 void* xconv, float* dt, void* stream);
+/* backward: reads dxc [ndir,B*L,di] (act dtype, d wrt conv'd x), dBC [ndir,B*L,2N] float, ddt
+ * [ndir,B*L,H] float (all scan order); writes the xBC and dt columns of dzxbcdt (natural order) and
+ * ACCUMULATES dconv_w, dconv_b, ddt_bias. */
+int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long long ldz, long long dstride, const float* dBC,
+                 const float* ddt, const int32_t* lengths, const float* conv_w, const float* conv_b,
+                 const float* dt_bias, int ndir, int B, int L, int di, int N, int H,
+                 void* dzxbcdt, float* dconv_w, float* dconv_b, float* ddt_bias, void* stream);
+
+/* SSD selective scan in scan order (mamba_ssm mamba_chunk_scan_combined):
+ *   h_t = exp(dt_t A) h_{t-1} + dt_t B_t (x) x_t ,  y_t = C_t . h_t + D x_t
+ * xconv [ndir,B*L,C] holds x | B | C; dt [ndir,B*L,H]; A_log, Dskip [ndir,H] float.
+ * y [ndir,B*L,di] (act dtype).  states: workspace of hnb_ssd_ws_bytes() bytes (per-chunk states,
+ * kept for the backward).  impl: 0 = CUDA-core fp32 (exact, any dtype), 1 = tcgen05 (bf16 only). */
+long long hnb_ssd_ws_bytes(int ndir, int B, int L, int di, int N, int H);
+int hnb_ssd_chunk(void);
+int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const float* A_log, const float* Dskip,
+                int ndir, int B, int L, int di, int N, int H, void* y, void* states, int impl,
+                void* stream);
+/* backward.  dy [ndir,B*L,di].  Outputs: dxc [ndir,B*L,di] (act dtype), dBC [ndir,B*L,2N] float
+ * (zero-initialised by the call), ddt [ndir,B*L,H] float, and ACCUMULATED dA_log, dD [ndir,H].
+ * ws2: second workspace of hnb_ssd_ws_bytes() bytes. */
+int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int dtype, const float* dt,
+                const float* A_log, const float* Dskip, const void* states,
+                int ndir, int B, int L, int di, int N, int H,
+                void* dxc, float* dBC, float* ddt, float* dA_log, float* dD, void* ws2, int impl,
+                void* stream);
+
+/* gated RMSNorm  rmsnorm(y * silu(z)) * w  (mamba_ssm RMSNormGated, norm_before_gate=False, eps 1e-5)
+ * reading y in scan order and writing natural order: out [B*L, ndir*di] (the out-projection operand).
+ * norm_w [ndir, di] float; rstd [ndir, B*L] float saved for backward. */
+int hnb_gated_norm_fwd(const void* y, const void* zxbcdt, int dtype, long long ldz, long long dstride,
+                       const int32_t* lengths, const float* norm_w, int ndir, int B, int L, int di,
+                       float eps, void* out, float* rstd, void* stream);
+/* backward: dout [B*L, ndir*di] -> dy [ndir,B*L,di] (scan order), z columns of dzxbcdt, ACCUMULATED dnorm_w */
+int hnb_gated_norm_bwd(const void* dout, const void* y, const void* zxbcdt, int dtype, long long ldz,
+                       long long dstride, const int32_t* lengths, const float* norm_w, const float* rstd,
+                       int ndir, int B, int L, int di, void* dy, void* dzxbcdt, float* dnorm_w,
+                       void* stream);
+
+/* ---- dense projections (in_proj / out_proj / router W_q,W_k / proj_in,out) ---------------- */
+/* C[M,N] = op(A) op(B) (+ bias[N]) (+ R[M,N]) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
+ *   transA = 0: A is [M,K] row-major (lda >= K);  1: A is [K,M] row-major (lda >= M)
+ *   transB = 0: B is [N,K] row-major (ldb >= K), i.e. C = A B^T (nn.Linear);  1: B is [K,N] row-major
+ *   c_dtype: HNB_BF16 or HNB_F32;  bias float or NULL;  R (c_dtype, ldr) or NULL
+ *   splitk > 1: K is split and fp32 partial tiles are atomically added into C (C must be fp32 and
+ *   pre-initialised, e.g. zero) — used for weight gradients where K = tokens. */
+int hnb_gemm_bf16(const void* A, long long lda, int transA, const void* B, long long ldb, int transB,
+                  int M, int N, int K, const float* bias, const void* R, long long ldr,
+                  void* C, long long ldc, int c_dtype, int splitk, void* stream);
+/* exact fp32 GEMM on CUDA cores (decode / fp32 parity path), same operand conventions */
+int hnb_gemm_f32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
+                 int M, int N, int K, const float* bias, const float* R, long long ldr,
+                 float* C, long long ldc, int accumulate, void* stream);
+/* on-device self test of the tcgen05 descriptor variants; returns 0 and fills max_abs_err[4] (host) */
+int hnb_umma_selftest(float* max_abs_err_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNET_B200_H */
