@@ -5,7 +5,7 @@
 //   h_t = exp(dt_t A) h_{t-1} + dt_t B_t (x) x_t ,  y_t = C_t . h_t + D x_t      (per head; B, C shared)
 //
 // Chunk Q = 64.  Forward:  chunk_state -> state_pass -> chunk_scan.
-// Backward: chunk_state(dY, C) -> state_pass(reverse) -> bwd_chunk -> bwd_ddt.
+// Backward: chunk_state(dY, C) -> state_pass(reverse) -> bwd_chunk.
 // Every small matmul is written as an outer-product loop over the contraction index k with the
 // lane-varying operand stored [k][lanes] in shared memory (conflict-free) and the other operand
 // broadcast.  Per-chunk states are stored [N][P] (p contiguous) so that no state tile is ever transposed.
@@ -247,17 +247,18 @@ ssd_chunk_scan_kernel(const T* __restrict__ xconv, int C, int di, const float* _
 // Per head (x, dy, y of the head; S_in = state entering the chunk, Gst = d loss / d state leaving it):
 //   K[t,q] = G[t,q] e^{cs_t-cs_q}  (t>=q);   W[t,q] = <dy_t, x_q> dt_q e^{cs_t-cs_q}  (t>=q)
 //   du[q,p] = sum_t K[t,q] dy[t,p] + e^{cs_last-cs_q} sum_n B[q,n] Gst[n,p]
-//   dx = dt du + D dy ;  ddt_x[q] = <du_q, x_q> ;  dscal[t] = <dy_t, y_t - D x_t> - dt_t ddt_x[t]
+//   dx = dt du + D dy ;  ddt[q] = <du_q, x_q> + A * sum_{t>=q} d cs_t, with d cs gathered term by term
+//   (score matrix, Y_off, chunk state, inter-chunk decay) -- no difference of long sums, so bf16 inputs are safe
 //   dC[t,n] += sum_q W[t,q] B[q,n] + e^{cs_t} sum_p dy[t,p] S_in[n,p]
 //   dB[q,n] += sum_t W[t,q] C[t,n] + e^{cs_last-cs_q} dt_q sum_p x[q,p] Gst[n,p]
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(ST)
-ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, const T* __restrict__ yfw, int C, int di,
+ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, int C, int di,
                      const float* __restrict__ dt, const float* __restrict__ A_log, const float* __restrict__ Dskip,
                      const float* __restrict__ states, const float* __restrict__ gstates, int ndir, int B, int L,
-                     int H, int nc, T* __restrict__ dxc, float* __restrict__ dBC, float* __restrict__ ddt_x,
-                     float* __restrict__ dscal, float* __restrict__ dD) {
+                     int H, int nc, T* __restrict__ dxc, float* __restrict__ dBC, float* __restrict__ ddt,
+                     float* __restrict__ dA_log, float* __restrict__ dD) {
   extern __shared__ float smem[];
   float* Bn = smem;                        // [SQ][SN]
   float* Cn = Bn + SQ * SN;                // [SQ][SN]
@@ -272,6 +273,8 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, cons
   float* s_dt = Ws + SQ * SQ;
   float* s_cs = s_dt + SQ;
   float* s_red = s_cs + SQ;                // [32]
+  float* s_dcs = s_red + 32;               // [SQ]  d loss / d cs_t  (cs = inclusive cumulative log decay)
+  float* s_ddtx = s_dcs + SQ;              // [SQ]  <du_q, x_q>
   const int c = blockIdx.x, db = blockIdx.y, dir = db / B;
   const int tid = threadIdx.x;
   const int q0 = c * SQ, qv = min(SQ, L - q0);
@@ -320,6 +323,7 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, cons
     const float A = -__expf(A_log[dir * H + h]);
     const float Dh = Dskip[dir * H + h];
     __syncthreads();                                // everyone is done with Bt / the previous head's tiles
+    if (tid < SQ) { s_dcs[tid] = 0.f; s_ddtx[tid] = 0.f; }
     chunk_cumsum(dt + row0 * H + h, H, qv, A, s_dt, s_cs);
     const float cs_last = s_cs[SQ - 1];
     for (int i = tid; i < SQ * SP / 4; i += ST) {
@@ -349,15 +353,29 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, cons
 #pragma unroll
           for (int j = 0; j < 4; ++j) r[i][j] += a[i] * b[j];
       }
+      // Z[t,q] = W[t,q] G[t,q] = d loss / d (cs_t - cs_q):  d cs_t += sum_q Z,  d cs_q -= sum_t Z
+      float zrow[4] = {0.f, 0.f, 0.f, 0.f}, zcol[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int t = ti + 16 * i, q = tj + 16 * j;
           const float e = (q <= t) ? __expf(s_cs[t] - s_cs[q]) : 0.f;
-          Ks[t * SQ + q] = Gs[t * SQ + q] * e;
-          Ws[t * SQ + q] = r[i][j] * e * s_dt[q];
+          const float g = Gs[t * SQ + q];
+          const float wv = r[i][j] * e * s_dt[q];
+          Ks[t * SQ + q] = g * e;
+          Ws[t * SQ + q] = wv;
+          zrow[i] += wv * g; zcol[j] += wv * g;
         }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = zrow[i];                                           // the 16 lanes of a row group share t
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tj == 0) atomicAdd(&s_dcs[ti + 16 * i], v);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&s_dcs[tj + 16 * j], -zcol[j]);
     }
     __syncthreads();
     const float* Sin = states + (((long long)db * nc + c) * H + h) * (SN * SP);
@@ -396,7 +414,7 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, cons
       for (int i = 0; i < 4; ++i) {
         const int q = ti + 16 * i;
         const float eq = __expf(cs_last - s_cs[q]);
-        float dux = 0.f, dyy = 0.f;
+        float dux = 0.f;
         if (q < qv) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -404,20 +422,15 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, cons
             const float du = du1[i][j] + eq * du2[i][j];
             const float xv = Xt[p * PADQ + q];
             const float dv = dYs[q * SP + p];
-            const float yv = to_f(yfw[(row0 + q) * di + h * SP + p]);
             dxc[(row0 + q) * di + h * SP + p] = from_f<T>(s_dt[q] * du + Dh * dv);
             dux += du * xv;
-            dyy += dv * (yv - Dh * xv);
             dsum += dv * xv;
           }
         }
         // reduce over the 16 lanes that share this row
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) { dux += __shfl_xor_sync(0xffffffffu, dux, o); dyy += __shfl_xor_sync(0xffffffffu, dyy, o); }
-        if (tj == 0 && q < qv) {
-          ddt_x[(row0 + q) * H + h] = dux;
-          dscal[(row0 + q) * H + h] = dyy - s_dt[q] * dux;
-        }
+        for (int o = 8; o > 0; o >>= 1) dux += __shfl_xor_sync(0xffffffffu, dux, o);
+        if (tj == 0) s_ddtx[q] = dux;
       }
       dsum = block_sum(dsum, s_red);
       if (tid == 0) atomicAdd(dD + dir * H + h, dsum);
@@ -452,14 +465,46 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, cons
 #pragma unroll
           for (int j = 0; j < 4; ++j) { c2[i][j] += as[i] * bd[j]; b2[i][j] += ag[i] * bx[j]; }
       }
+      float dlast = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int t = tj + 16 * j;
         const float et = __expf(s_cs[t]);
         const float eq = __expf(cs_last - s_cs[t]) * s_dt[t];
+        float yoff = 0.f, sloc = 0.f;                               // <dy_t, Yoff_t> and <dS_c, its q-th term>
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { accC2[i][j] += et * c2[i][j]; accB2[i][j] += eq * b2[i][j]; }
+        for (int i = 0; i < 8; ++i) {
+          const float vc = et * c2[i][j], vb = eq * b2[i][j];
+          accC2[i][j] += vc; accB2[i][j] += vb;
+          yoff += vc * Cn[t * SN + ti + 16 * i];
+          sloc += vb * Bn[t * SN + ti + 16 * i];
+        }
+        atomicAdd(&s_dcs[t], yoff - sloc);                          // Yoff ~ e^{cs_t};  S_c term ~ e^{cs_last - cs_t}
+        dlast += sloc;
       }
+      // inter-chunk decay: S_in[c+1] = e^{cs_last} S_in[c] + S_c
+      float dot = 0.f;
+      for (int i = tid; i < SN * SP; i += ST) dot += __ldg(Gst + i) * __ldg(Sin + i);
+      dlast += __expf(cs_last) * dot;
+      dlast = block_sum(dlast, s_red);
+      if (tid == 0) s_dcs[SQ - 1] += dlast;
+    }
+    __syncthreads();
+    // d(dt_s A) = sum_{t >= s} d cs_t (reverse inclusive cumsum inside the chunk)
+    if (tid < 32) {
+      float v0 = s_dcs[SQ - 1 - tid], v1 = s_dcs[31 - tid];          // lane 0 holds the latest time of each half
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float u0 = __shfl_up_sync(0xffffffffu, v0, o), u1 = __shfl_up_sync(0xffffffffu, v1, o);
+        if (tid >= o) { v0 += u0; v1 += u1; }
+      }
+      v1 += __shfl_sync(0xffffffffu, v0, 31);
+      const int s0 = SQ - 1 - tid, s1 = 31 - tid;
+      float accA = v0 * s_dt[s0] + v1 * s_dt[s1];
+      if (s0 < qv) ddt[(row0 + s0) * H + h] = v0 * A + s_ddtx[s0];
+      if (s1 < qv) ddt[(row0 + s1) * H + h] = v1 * A + s_ddtx[s1];
+      accA = warp_sum(accA);
+      if (tid == 0) atomicAdd(dA_log + dir * H + h, accA * A);
     }
   }
   // ---- write dB | dC for this chunk: first the (t, n)-mapped tiles, then add the (n, t)-mapped ones
@@ -488,41 +533,6 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, cons
       }
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// ddt / dA: dloga_t = sum_{s>=t} dscal_s (suffix sum over the WHOLE row), ddt_t = dloga_t A + ddt_x_t,
-// dA_log = A * sum_t dloga_t dt_t.   One warp per (row, head).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ssd_bwd_ddt_kernel(const float* __restrict__ dscal, const float* __restrict__ ddt_x, const float* __restrict__ dt,
-                   const float* __restrict__ A_log, int ndir, int B, int L, int H, float* __restrict__ ddt,
-                   float* __restrict__ dA_log) {
-  const int lane = threadIdx.x & 31;
-  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (wid >= (long long)ndir * B * H) return;
-  const long long db = wid / H;
-  const int h = (int)(wid % H), dir = (int)(db / B);
-  const float A = -__expf(A_log[dir * H + h]);
-  float carry = 0.f, accA = 0.f;
-  for (int base = L - 1; base >= 0; base -= 32) {
-    const int t = base - lane;                                        // lane 0 holds the latest time
-    float v = (t >= 0) ? dscal[((long long)db * L + t) * H + h] : 0.f;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float u = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += u;
-    }
-    v += carry;
-    if (t >= 0) {
-      const long long idx = ((long long)db * L + t) * H + h;
-      ddt[idx] = v * A + ddt_x[idx];
-      accA += v * dt[idx];
-    }
-    carry = __shfl_sync(0xffffffffu, v, 31);
-  }
-  accA = warp_sum(accA);
-  if (lane == 0) atomicAdd(dA_log + dir * H + h, accA * A);
 }
 
 }  // namespace hnb
@@ -608,10 +618,8 @@ static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt
   const float* states = ws;
   const float* decay = ws + nst;
   float* gstates = ws2;
-  float* ddt_x = ws2 + nst + (size_t)ndir * B * H * nc;
-  float* dscal = ddt_x + (size_t)ndir * B * L * H;
   const size_t sm1 = (SQ * SN + SQ * SP + 2 * SQ) * sizeof(float);
-  const size_t smb = (2 * SQ * SN + SN * PADQ + SQ * SQ + SQ * SP + 2 * SQ * SQ + 2 * SQ + 32) * sizeof(float);
+  const size_t smb = (2 * SQ * SN + SN * PADQ + SQ * SQ + SQ * SP + 2 * SQ * SQ + 4 * SQ + 32) * sizeof(float);
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_chunk_state_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_chunk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
   dim3 grid(nc, ndir * B);
@@ -620,11 +628,10 @@ static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt
   const long long total4 = (long long)ndir * B * H * (SN * SP / 4);
   ssd_state_pass_kernel<true><<<cdiv(total4, 256), 256, 0, st>>>(gstates, decay, H, nc, total4);
   HNB_LAUNCH_CHECK("ssd_state_pass_rev");
-  ssd_bwd_chunk_kernel<T><<<grid, ST, smb, st>>>(dy, xconv, y, C, di, dt, A_log, Dskip, states, gstates, ndir, B, L, H, nc,
-                                                 dxc, dBC, ddt_x, dscal, dD);
+  (void)y;
+  ssd_bwd_chunk_kernel<T><<<grid, ST, smb, st>>>(dy, xconv, C, di, dt, A_log, Dskip, states, gstates, ndir, B, L, H, nc,
+                                                 dxc, dBC, ddt, dA_log, dD);
   HNB_LAUNCH_CHECK("ssd_bwd_chunk");
-  ssd_bwd_ddt_kernel<<<cdiv((long long)ndir * B * H, 8), 256, 0, st>>>(dscal, ddt_x, dt, A_log, ndir, B, L, H, ddt, dA_log);
-  HNB_LAUNCH_CHECK("ssd_bwd_ddt");
   return HNB_OK;
 }
 

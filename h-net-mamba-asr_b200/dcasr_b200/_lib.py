@@ -88,12 +88,34 @@ class _Lib:
                 conv.append(a.data_ptr())
             else:
                 conv.append(a)
-        rc = self.fn["hnb_" + name](*conv)
+        prof = _PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = self.fn["hnb_" + name](*conv)
+            e1.record()
+            prof.append((name, tuple(a for a in args if isinstance(a, (int, float))), e0, e1))
+        else:
+            rc = self.fn["hnb_" + name](*conv)
         if rc != 0:
             raise HnbError(f"hnb_{name} failed ({rc}): {self.cdll.hnb_last_error().decode()}")
 
 
 _LIB: _Lib | None = None
+_PROFILE: list | None = None      # when a list: every call appends (name, scalar args, start event, end event)
+
+
+def profile_start() -> None:
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_stop() -> list:
+    """-> [(kernel entry point, scalar args, milliseconds)] for every call since profile_start()."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    return [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in rec]
 
 
 def lib() -> _Lib:
