@@ -97,6 +97,9 @@ def cpu_reference_step_fn(batch: int, seconds: float):
     from oracle.encoder_ref import EncoderRef
     torch.manual_seed(1)
     enc = EncoderRef(**SMALL)
+    with torch.no_grad():                                  # same keep-fraction ~0.5 operating point as the GPU arm
+        g = torch.Generator().manual_seed(7)
+        enc.chunk.router.W_k.weight.copy_(torch.randn(384, 384, generator=g) / 384 ** 0.5)
     feats, lens = synth_batch(batch, seconds, 1)
 
     def step():
@@ -207,6 +210,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1)
     enc = dd.DCASREncoder(**SMALL).to(dev)
+    with torch.no_grad():
+        # Untrained identity routers keep ~0.3 % of the frames (the main stack would run on M ~ 1).  The metric's
+        # config is the TRAINED operating point, keep-fraction ~ 1/N = 0.5, so W_k is set to a seeded random matrix:
+        # cos(q_t, k_{t-1}) is then ~N(0, 1/D) and half of the frames cross p >= 0.5 (SURVEY.md §8d, config 5 note).
+        g = torch.Generator().manual_seed(7)
+        enc.chunk.router.W_k.weight.copy_(torch.randn(384, 384, generator=g) / 384 ** 0.5)
     if world > 1:                                   # identical replicas, as DDP's initial broadcast would make them
         for p in enc.parameters():
             dist.broadcast(p.data, 0)

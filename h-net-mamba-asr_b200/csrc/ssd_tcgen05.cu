@@ -1,15 +1,880 @@
-// tcgen05 SSD kernels (impl 1).  Placeholder entry points until the tensor-core path lands: they fail
-// loudly rather than fall back.
+// SSD (Mamba-2 selective scan) on tcgen05 tensor cores (impl 1): bf16 operands staged by TMA, fp32
+// accumulators in TMEM, chunk length 128.  Scan order in, scan order out (see ssd_kernels.cu for the maths).
+//
+// Forward: ONE persistent kernel.  A CTA owns a (row, head) pair and walks its chunks in order, carrying the
+// 128x64 state in registers (fp32) and in shared memory (bf16, the next chunk's MMA operand):
+//     G    = C B^T                        128x128x128   (TMEM cols   0..127)
+//     M    = bf16( G o L o dt )           epilogue 1    -> smem, K-major A operand
+//     Yd   = M X                          128x64x128    (TMEM cols 128..191)   X  : MN-major B operand (as TMA wrote it)
+//     Yo   = C S_in                       128x64x128    (TMEM cols 192..255)   S  : MN-major B operand
+//     dS   = B^T (w o X)                  128x64x128    (TMEM cols 256..319)   B^T: MN-major A operand
+//     y    = Yd + e^{cs} Yo + D x         epilogue 2    -> global (bf16)
+//     S    = e^{cs_last} S + dS           epilogue 3    -> registers, smem (bf16), global (bf16, for the backward)
+// The decay matrix L[t,s] = exp(cs_t - cs_s) is factored per 32-row block through a reference point (both factors
+// <= 1, so no overflow) and only the diagonal 32x32 blocks pay one exp per element: MUFU would otherwise pace
+// the kernel.  TMA for the next chunk is issued as soon as the current chunk's MMAs retire, so loads overlap the
+// output/state epilogues.
 #include "common.cuh"
+#include "umma.cuh"
+
+namespace hnb {
+namespace {
+
+constexpr int TQ = 128;                 // chunk length
+constexpr int TP = 64;                  // head dim
+constexpr int TN = 128;                 // state dim
+constexpr int TC_THREADS = 256;
+constexpr int HALF = TQ * 128;          // bytes of one [128 rows x 128 B] swizzled block (16 KB)
+
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr int OFF_C = 0;                // 2 blocks: n in [0,64) | [64,128)
+constexpr int OFF_B = OFF_C + 2 * HALF;
+constexpr int OFF_X = OFF_B + 2 * HALF; // 2 buffers (chunk parity)
+constexpr int OFF_XW = OFF_X + 2 * HALF;
+constexpr int OFF_M = OFF_XW + HALF;    // 2 blocks: s in [0,64) | [64,128)
+constexpr int OFF_S = OFF_M + 2 * HALF;
+constexpr int OFF_TAB = OFF_S + HALF;   // float tables (see build_tables)
+constexpr int TAB_FLOATS = 9 * TQ + 8 + 2 * TQ + 8;   // cs, dt, w, ecs, eq | f[4][128] | warp totals | dcs, ddtx, scalars
+constexpr int OFF_BAR = OFF_TAB + TAB_FLOATS * 4;
+constexpr int FWD_SMEM = OFF_BAR + 64 + 1024;
+
+struct FwdParams {
+  const float* dt;        // [ndir*B*L, H]
+  const float* A_log;     // [ndir, H]
+  const float* Dskip;     // [ndir, H]
+  __nv_bfloat16* y;       // [ndir*B*L, di]
+  __nv_bfloat16* states;  // [ndir*B, H, nc, 128(n), 64(p)]  state ENTERING each chunk
+  int ndirB, B, L, H, di, nc;
+};
+
+__device__ __forceinline__ uint32_t swz(int row, int chunk16) {          // byte offset inside a [rows x 128 B] SW128 block
+  return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return r;
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+// Per-chunk tables (all TC_THREADS threads call; ends with a block barrier):
+//   cs[t]  inclusive cumsum of dt*A      dt[t]  (0 beyond the row's length)
+//   w[t]   e^{cs_last - cs_t} dt_t       ecs[t] e^{cs_t}        eq[t] e^{cs_last - cs_t}
+//   f[I][s] = e^{cs_{32I-1} - cs_s}  for s < 32 I  (block factor of the decay matrix), else 0
+__device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int H, int qv, float A, float* tab) {
+  float* s_cs = tab; float* s_dt = tab + TQ; float* s_w = tab + 2 * TQ; float* s_ecs = tab + 3 * TQ;
+  float* s_eq = tab + 4 * TQ; float* s_f = tab + 5 * TQ; float* s_tot = tab + 9 * TQ;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < TQ) {
+    const float d = (tid < qv) ? dtp[(long long)tid * H] : 0.f;
+    s_dt[tid] = d;
+    float v = d * A;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    s_cs[tid] = v;
+    if (lane == 31) s_tot[tid >> 5] = v;
+  }
+  __syncthreads();
+  if (tid < TQ) {
+    float add = 0.f;
+    for (int w = 0; w < (tid >> 5); ++w) add += s_tot[w];
+    s_cs[tid] += add;
+  }
+  __syncthreads();
+  const float cs_last = s_cs[TQ - 1];
+  if (tid < TQ) {
+    const float cs = s_cs[tid];
+    const float eq = __expf(cs_last - cs);
+    s_eq[tid] = eq;
+    s_w[tid] = eq * s_dt[tid];
+    s_ecs[tid] = __expf(cs);
+  }
+  for (int i = tid; i < 4 * TQ; i += TC_THREADS) {
+    const int I = i >> 7, s = i & (TQ - 1);
+    s_f[i] = (I > 0 && s < 32 * I) ? __expf(s_cs[32 * I - 1] - s_cs[s]) : 0.f;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = base + OFF_C; uint8_t* sB = base + OFF_B; uint8_t* sX = base + OFF_X; uint8_t* sXw = base + OFF_XW;
+  uint8_t* sM = base + OFF_M; uint8_t* sS = base + OFF_S;
+  float* tab = reinterpret_cast<float*>(base + OFF_TAB);
+  const float* s_cs = tab; const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
+  const float* s_f = tab + 5 * TQ;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + OFF_BAR);
+  uint64_t* bar_g = bar_load + 1;
+  uint64_t* bar_y = bar_load + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, ch = warp >> 2;          // TMEM lane quarter, column half
+  const int row = lq * 32 + lane;
+
+  if (tid == 0) {
+    umma::prefetch_tmap(&tmX);
+    umma::mbar_init(bar_load, 1); umma::mbar_init(bar_g, 1); umma::mbar_init(bar_y, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
+
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc;
+  const int n_items = p.ndirB * H;
+  constexpr uint32_t idesc_g = umma::make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_y = umma::make_idesc_bf16(128, 64, 0, 1);
+  constexpr uint32_t idesc_s = umma::make_idesc_bf16(128, 64, 1, 1);
+
+  auto issue_load = [&](int item, int c, int buf) {                 // thread 0 only
+    const int db = item / H, h = item % H;
+    umma::mbar_expect_tx(bar_load, 5 * HALF);
+    umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
+    umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
+    umma::tma_load_3d(sB, &tmX, bar_load, di, c * TQ, db);
+    umma::tma_load_3d(sB + HALF, &tmX, bar_load, di + 64, c * TQ, db);
+    umma::tma_load_3d(sX + buf * HALF, &tmX, bar_load, h * TP, c * TQ, db);
+  };
+
+  uint32_t seq = 0;                                                   // (item, chunk) sequence number of this CTA
+  if (blockIdx.x < n_items && tid == 0) issue_load(blockIdx.x, 0, 0);
+
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int db = it / H, h = it % H, dir = db / p.B;
+    const float A = -__expf(p.A_log[dir * H + h]);
+    const float Dh = p.Dskip[dir * H + h];
+    float Sreg[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) Sreg[j] = 0.f;
+    for (int i = tid; i < HALF / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sS)[i] = make_uint4(0, 0, 0, 0);
+
+    for (int c = 0; c < nc; ++c, ++seq) {
+      const int buf = seq & 1;
+      const uint32_t par = seq & 1;
+      const int q0 = c * TQ, qv = min(TQ, L - q0);
+      const long long row0 = (long long)db * L + q0;
+      build_tables(p.dt + row0 * H + h, H, qv, A, tab);
+      {   // state entering this chunk, kept for the backward (thread = state row n, 32 of the 64 columns)
+        __nv_bfloat16* sg = p.states + ((((long long)db * H + h) * nc + c) * TN + row) * TP + 32 * ch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sg + 8 * k) = pack8(Sreg + 8 * k);
+      }
+      umma::mbar_wait(bar_load, par);
+      if (tid == 0) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + 0, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024), idesc_g, kb > 0);
+        }
+        umma::mma_commit(bar_g);
+      }
+      // Xw = w_s * X (same swizzled positions: the swizzle permutes 16-byte chunks inside a row only)
+      for (int i = tid; i < TQ * 8; i += TC_THREADS) {
+        const float w = s_w[i >> 3];
+        float v[8];
+        unpack8(reinterpret_cast<const uint4*>(sX + buf * HALF)[i], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= w;
+        reinterpret_cast<uint4*>(sXw)[i] = pack8(v);
+      }
+      umma::mbar_wait(bar_g, par);
+      umma::tc_fence_after();
+      // ---- epilogue 1: M[t,s] = G[t,s] e^{cs_t - cs_s} dt_s (s <= t), bf16, K-major swizzled
+      {
+        const int t = row, I = t >> 5;
+        const float cs_t = s_cs[t];
+        const float e_ref = (I > 0) ? __expf(cs_t - s_cs[32 * I - 1]) : 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int J = 2 * ch + cc, s0 = 32 * J;
+          float g[32];
+          if (J <= I) {
+            umma::tmem_ld32(t_lane + (uint32_t)s0, g);
+            umma::tmem_ld_wait();
+            if (J < I) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) g[j] *= e_ref * s_f[I * TQ + s0 + j] * s_dt[s0 + j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                g[j] = (s0 + j <= t) ? g[j] * __expf(cs_t - s_cs[s0 + j]) * s_dt[s0 + j] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[j] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sM + ch * HALF + swz(t, 4 * cc + k)) = pack8(g + 8 * k);
+        }
+      }
+      umma::fence_async_smem();
+      umma::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {                               // Yd = M X
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sM) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sX + buf * HALF) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
+        }
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {                               // Yo = C S_in
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + 192, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
+        }
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {                               // dS = B^T (w o X)
+          umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sXw) + kb * 2048, 1024, 1024), idesc_s, kb > 0);
+        }
+        umma::mma_commit(bar_y);
+      }
+      umma::mbar_wait(bar_y, par);
+      umma::tc_fence_after();
+      if (tid == 0) {                                                  // C, B and the other X buffer are free: prefetch
+        int nit = it, ncn = c + 1;
+        if (ncn == nc) { nit = it + gridDim.x; ncn = 0; }
+        if (nit < n_items) issue_load(nit, ncn, buf ^ 1);
+      }
+      // ---- epilogue 2: y = Yd + e^{cs_t} Yo + D x
+      {
+        const int t = row;
+        float yd[32], yo[32];
+        umma::tmem_ld32(t_lane + 128u + 32u * ch, yd);
+        umma::tmem_ld32(t_lane + 192u + 32u * ch, yo);
+        umma::tmem_ld_wait();
+        if (t < qv) {
+          const float ecs = s_ecs[t];
+          __nv_bfloat16* yg = p.y + (row0 + t) * di + h * TP + 32 * ch;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float x[8], o[8];
+            unpack8(*reinterpret_cast<const uint4*>(sX + buf * HALF + swz(t, 4 * ch + k)), x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = yd[8 * k + e] + ecs * yo[8 * k + e] + Dh * x[e];
+            *reinterpret_cast<uint4*>(yg + 8 * k) = pack8(o);
+          }
+        }
+      }
+      // ---- epilogue 3: S = e^{cs_last} S + dS  (thread = state row n)
+      {
+        float ds[32];
+        umma::tmem_ld32(t_lane + 256u + 32u * ch, ds);
+        umma::tmem_ld_wait();
+        const float decay = s_ecs[TQ - 1];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) Sreg[j] = decay * Sreg[j] + ds[j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sS + swz(row, 4 * ch + k)) = pack8(Sreg + 8 * k);
+      }
+      umma::fence_async_smem();
+      umma::tc_fence_before();
+      __syncthreads();
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+
+// =================================================================================================
+// Backward (three kernels, all in scan order):
+//   1. dstate : per (row, head), chunks in REVERSE order:  Gst[c] = d loss / d (state leaving chunk c)
+//               dS_local = C^T (e^{cs} o dY)   128x64x128,   G_run = e^{cs_last} G_run + dS_local
+//   2. dx     : per (row, chunk, head): du = K^T dY + e_q B Gst  ->  dx, ddt, dA_log, dD
+//   3. dbc    : per (row, chunk), heads accumulated in TMEM:   dC += W B + (e^{cs} dY) S_in^T,
+//                                                              dB += W^T C + (w X) Gst^T
+// with  K = (C B^T) o L,  W = (dY X^T) o L o dt,  L[t,q] = e^{cs_t - cs_q} (q <= t).
+// The gradient w.r.t. the cumulative log-decay cs is collected term by term (see ssd_kernels.cu).
+// =================================================================================================
+struct BwdParams {
+  const float* dt; const float* A_log; const float* Dskip;
+  __nv_bfloat16* gstates;        // [ndir*B, H, nc, 128, 64]
+  __nv_bfloat16* dxc;            // [ndir*B*L, di]
+  float* dBC;                    // [ndir*B*L, 2N]
+  float* ddt;                    // [ndir*B*L, H]
+  float* dA_log; float* dD;      // [ndir, H]
+  int ndirB, B, L, H, di, nc;
+};
+
+// decay factor L[t, s0+j] (j < 32) of row t (row block I) against column block J <= I
+__device__ __forceinline__ float decay_elem(int t, int I, int J, int s, float cs_t, float e_ref, const float* s_cs,
+                                            const float* s_f) {
+  if (J < I) return e_ref * s_f[I * TQ + s];
+  return (s <= t) ? __expf(cs_t - s_cs[s]) : 0.f;
+}
+
+// ---- 1. dstate ------------------------------------------------------------------------------------
+constexpr int D1_OFF_C = 0, D1_OFF_DY = 2 * HALF, D1_OFF_DYS = 3 * HALF, D1_OFF_TAB = 4 * HALF;
+constexpr int D1_OFF_BAR = D1_OFF_TAB + TAB_FLOATS * 4;
+constexpr int D1_SMEM = D1_OFF_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                         const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = base + D1_OFF_C; uint8_t* sdY = base + D1_OFF_DY; uint8_t* sdYs = base + D1_OFF_DYS;
+  float* tab = reinterpret_cast<float*>(base + D1_OFF_TAB);
+  const float* s_ecs = tab + 3 * TQ;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + D1_OFF_BAR);
+  uint64_t* bar_m = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, ch = warp >> 2, row = lq * 32 + lane;
+  if (tid == 0) {
+    umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY);
+    umma::mbar_init(bar_load, 1); umma::mbar_init(bar_m, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 64);
+  umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * H;
+  constexpr uint32_t idesc = umma::make_idesc_bf16(128, 64, 1, 1);
+  auto issue_load = [&](int item, int c) {
+    const int db = item / H, h = item % H;
+    umma::mbar_expect_tx(bar_load, 3 * HALF);
+    umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
+    umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
+    umma::tma_load_3d(sdY, &tmDY, bar_load, h * TP, c * TQ, db);
+  };
+  uint32_t seq = 0;
+  if (blockIdx.x < n_items && tid == 0) issue_load(blockIdx.x, nc - 1);
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int db = it / H, h = it % H, dir = db / p.B;
+    const float A = -__expf(p.A_log[dir * H + h]);
+    float Grun[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) Grun[j] = 0.f;
+    for (int c = nc - 1; c >= 0; --c, ++seq) {
+      const uint32_t par = seq & 1;
+      const int q0 = c * TQ, qv = min(TQ, L - q0);
+      const long long row0 = (long long)db * L + q0;
+      build_tables(p.dt + row0 * H + h, H, qv, A, tab);
+      {   // gradient w.r.t. the state LEAVING this chunk
+        __nv_bfloat16* gg = p.gstates + ((((long long)db * H + h) * nc + c) * TN + row) * TP + 32 * ch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(gg + 8 * k) = pack8(Grun + 8 * k);
+      }
+      umma::mbar_wait(bar_load, par);
+      for (int i = tid; i < TQ * 8; i += TC_THREADS) {
+        const float e = s_ecs[i >> 3];
+        float v[8];
+        unpack8(reinterpret_cast<const uint4*>(sdY)[i], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= e;
+        reinterpret_cast<uint4*>(sdYs)[i] = pack8(v);
+      }
+      umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
+      if (tid == 0) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb)
+          umma::mma_bf16_ss(tmem, umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sdYs) + kb * 2048, 1024, 1024), idesc, kb > 0);
+        umma::mma_commit(bar_m);
+      }
+      umma::mbar_wait(bar_m, par);
+      umma::tc_fence_after();
+      if (tid == 0) {
+        int nit = it, ncn = c - 1;
+        if (ncn < 0) { nit = it + gridDim.x; ncn = nc - 1; }
+        if (nit < n_items) issue_load(nit, ncn);
+      }
+      float ds[32];
+      umma::tmem_ld32(t_lane + 32u * ch, ds);
+      umma::tmem_ld_wait();
+      const float decay = s_ecs[TQ - 1];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Grun[j] = decay * Grun[j] + ds[j];
+      umma::tc_fence_before(); __syncthreads();
+    }
+  }
+  umma::tc_fence_before(); __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 64);
+}
+
+// ---- 2. dx / ddt / dA / dD --------------------------------------------------------------------------
+constexpr int D2_OFF_C = 0, D2_OFF_B = 2 * HALF, D2_OFF_X = 4 * HALF, D2_OFF_DY = 5 * HALF, D2_OFF_S = 6 * HALF,
+              D2_OFF_G = 7 * HALF, D2_OFF_K = 8 * HALF, D2_OFF_TAB = 10 * HALF;
+constexpr int D2_OFF_BAR = D2_OFF_TAB + TAB_FLOATS * 4;
+constexpr int D2_SMEM = D2_OFF_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                     const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
+                     const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = base + D2_OFF_C; uint8_t* sB = base + D2_OFF_B; uint8_t* sX = base + D2_OFF_X;
+  uint8_t* sdY = base + D2_OFF_DY; uint8_t* sS = base + D2_OFF_S; uint8_t* sG = base + D2_OFF_G;
+  uint8_t* sK = base + D2_OFF_K;
+  float* tab = reinterpret_cast<float*>(base + D2_OFF_TAB);
+  const float* s_cs = tab; const float* s_dt = tab + TQ; const float* s_ecs = tab + 3 * TQ; const float* s_eq = tab + 4 * TQ;
+  const float* s_f = tab + 5 * TQ;
+  float* s_tot = tab + 9 * TQ;           // [8] scratch
+  float* s_dcs = tab + 9 * TQ + 8;       // [128]
+  float* s_ddtx = s_dcs + TQ;            // [128]
+  float* s_sc = s_ddtx + TQ;             // [0] = d cs_last extra, [1] = dD
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + D2_OFF_BAR);
+  uint64_t* bar1 = bar_load + 1;
+  uint64_t* bar2 = bar_load + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, ch = warp >> 2, row = lq * 32 + lane;
+  if (tid == 0) {
+    umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
+    umma::mbar_init(bar_load, 1); umma::mbar_init(bar1, 1); umma::mbar_init(bar2, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * nc * H;
+  constexpr uint32_t idesc_kk128 = umma::make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_km64 = umma::make_idesc_bf16(128, 64, 0, 1);
+  constexpr uint32_t idesc_mm64 = umma::make_idesc_bf16(128, 64, 1, 1);
+  auto issue_load = [&](int item) {
+    const int h = item % H, c = (item / H) % nc, db = item / (H * nc);
+    const int srow = (((db * H + h) * nc) + c) * TN;
+    umma::mbar_expect_tx(bar_load, 8 * HALF);
+    umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
+    umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
+    umma::tma_load_3d(sB, &tmX, bar_load, di, c * TQ, db);
+    umma::tma_load_3d(sB + HALF, &tmX, bar_load, di + 64, c * TQ, db);
+    umma::tma_load_3d(sX, &tmX, bar_load, h * TP, c * TQ, db);
+    umma::tma_load_3d(sdY, &tmDY, bar_load, h * TP, c * TQ, db);
+    umma::tma_load_2d(sS, &tmS, bar_load, 0, srow);
+    umma::tma_load_2d(sG, &tmG, bar_load, 0, srow);
+  };
+  uint32_t seq = 0;
+  if (blockIdx.x < n_items && tid == 0) issue_load(blockIdx.x);
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++seq) {
+    const uint32_t par = seq & 1;
+    const int h = it % H, c = (it / H) % nc, db = it / (H * nc), dir = db / p.B;
+    const float A = -__expf(p.A_log[dir * H + h]);
+    const float Dh = p.Dskip[dir * H + h];
+    const int q0 = c * TQ, qv = min(TQ, L - q0);
+    const long long row0 = (long long)db * L + q0;
+    if (tid < TQ) { s_dcs[tid] = 0.f; s_ddtx[tid] = 0.f; }
+    if (tid < 2) s_sc[tid] = 0.f;
+    build_tables(p.dt + row0 * H + h, H, qv, A, tab);
+    umma::mbar_wait(bar_load, par);
+    if (tid == 0) {
+      umma::tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {                                 // G = C B^T
+        const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+        umma::mma_bf16_ss(tmem + 0, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                          umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024), idesc_kk128, kb > 0);
+      }
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb)                                   // R = dY X^T
+        umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sdY) + kb * 32, 16, 1024),
+                          umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), idesc_kk128, kb > 0);
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {                                 // Yo = C S_in (unscaled)
+        const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+        umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                          umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), idesc_km64, kb > 0);
+      }
+      umma::mma_commit(bar1);
+    }
+    {   // inter-chunk decay term: e^{cs_last} <Gst, S_in>  (same swizzle on both tiles: plain elementwise product)
+      float dot = 0.f;
+      for (int i = tid; i < TQ * 8; i += TC_THREADS) {
+        float a[8], b[8];
+        unpack8(reinterpret_cast<const uint4*>(sS)[i], a);
+        unpack8(reinterpret_cast<const uint4*>(sG)[i], b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dot += a[k] * b[k];
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) atomicAdd(&s_sc[0], s_ecs[TQ - 1] * dot);
+    }
+    umma::mbar_wait(bar1, par);
+    umma::tc_fence_after();
+    // ---- epilogue A: K = G o L -> smem;  d cs_t += sum_q W G  +  e^{cs_t} <dY_t, Yo_t>
+    {
+      const int t = row, I = t >> 5;
+      const float cs_t = s_cs[t];
+      const float e_ref = (I > 0) ? __expf(cs_t - s_cs[32 * I - 1]) : 0.f;
+      float acc = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int J = 2 * ch + cc, s0 = 32 * J;
+        float g[32];
+        if (J <= I) {
+          float r[32];
+          umma::tmem_ld32(t_lane + (uint32_t)s0, g);
+          umma::tmem_ld32(t_lane + 128u + (uint32_t)s0, r);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float l = decay_elem(t, I, J, s0 + j, cs_t, e_ref, s_cs, s_f);
+            g[j] *= l;
+            // the row sums must use K exactly as the tensor core will see it (bf16): the column sums come out of
+            // du1 = K^T dY, and the two cancel in the cumulative sum -- any rounding asymmetry would survive
+            acc += r[j] * s_dt[s0 + j] * __bfloat162float(__float2bfloat16_rn(g[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g[j] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sK + ch * HALF + swz(t, 4 * cc + k)) = pack8(g + 8 * k);
+      }
+      float yo[32], yd = 0.f;
+      umma::tmem_ld32(t_lane + 256u + 32u * ch, yo);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float d[8];
+        unpack8(*reinterpret_cast<const uint4*>(sdY + swz(t, 4 * ch + k)), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yd += d[e] * yo[8 * k + e];
+      }
+      atomicAdd(&s_dcs[t], acc + s_ecs[t] * yd);
+    }
+    umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
+    if (tid == 0) {
+      umma::tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb)                                   // du1 = K^T dY
+        umma::mma_bf16_ss(tmem + 320, umma::make_smem_desc(umma::smem_u32(sK) + kb * 2048, HALF, 1024),
+                          umma::make_smem_desc(umma::smem_u32(sdY) + kb * 2048, 1024, 1024), idesc_mm64, kb > 0);
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {                                 // du2 = B Gst
+        const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+        umma::mma_bf16_ss(tmem + 384, umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024),
+                          umma::make_smem_desc(umma::smem_u32(sG) + kb * 2048, 1024, 1024), idesc_km64, kb > 0);
+      }
+      umma::mma_commit(bar2);
+    }
+    umma::mbar_wait(bar2, par);
+    umma::tc_fence_after();
+    // ---- epilogue B (thread = row q): dx, and the remaining d cs terms
+    {
+      const int q = row;
+      float xr[32], dr[32];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unpack8(*reinterpret_cast<const uint4*>(sX + swz(q, 4 * ch + k)), xr + 8 * k);
+        unpack8(*reinterpret_cast<const uint4*>(sdY + swz(q, 4 * ch + k)), dr + 8 * k);
+      }
+      __syncthreads();                                                 // every smem operand has been consumed
+      if (tid == 0 && it + (int)gridDim.x < n_items) issue_load(it + gridDim.x);
+      float d1[32], d2[32];
+      umma::tmem_ld32(t_lane + 320u + 32u * ch, d1);
+      umma::tmem_ld32(t_lane + 384u + 32u * ch, d2);
+      umma::tmem_ld_wait();
+      const float eq = s_eq[q], dtq = s_dt[q];
+      float col = 0.f, sc = 0.f, dux = 0.f, dd = 0.f;
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float du = d1[j] + eq * d2[j];
+        o[j] = dtq * du + Dh * dr[j];
+        col += d1[j] * xr[j];
+        sc += d2[j] * xr[j];
+        dux += du * xr[j];
+        dd += dr[j] * xr[j];
+      }
+      col *= dtq; sc *= dtq * eq;
+      if (q < qv) {
+        __nv_bfloat16* og = p.dxc + (row0 + q) * di + h * TP + 32 * ch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(og + 8 * k) = pack8(o + 8 * k);
+      }
+      atomicAdd(&s_dcs[q], -(col + sc));
+      atomicAdd(&s_ddtx[q], dux);
+      sc = warp_sum(sc); dd = warp_sum(dd);
+      if (lane == 0) { atomicAdd(&s_sc[0], sc); atomicAdd(&s_sc[1], dd); }
+    }
+    __syncthreads();
+    // ---- reverse inclusive cumsum of d cs over the chunk -> ddt, dA_log
+    float v = 0.f;
+    if (tid < TQ) {
+      v = s_dcs[TQ - 1 - tid] + (tid == 0 ? s_sc[0] : 0.f);           // tid 0 holds the latest time
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+      if (lane == 31) s_tot[warp] = v;
+    }
+    __syncthreads();
+    if (tid < TQ) {
+      for (int w = 0; w < warp; ++w) v += s_tot[w];
+      const int t = TQ - 1 - tid;
+      float accA = v * s_dt[t];
+      if (t < qv) p.ddt[(row0 + t) * H + h] = v * A + s_ddtx[t];
+      accA = warp_sum(accA);
+      if (lane == 0) atomicAdd(p.dA_log + dir * H + h, accA * A);
+      if (tid == 0) atomicAdd(p.dD + dir * H + h, s_sc[1]);
+    }
+    umma::tc_fence_before(); __syncthreads();
+  }
+  umma::tc_fence_before(); __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// ---- 3. dB / dC ---------------------------------------------------------------------------------------
+constexpr int D3_OFF_C = 0, D3_OFF_B = 2 * HALF, D3_OFF_X = 4 * HALF, D3_OFF_DY = 5 * HALF, D3_OFF_XW = 6 * HALF,
+              D3_OFF_DYS = 7 * HALF, D3_OFF_S = 8 * HALF, D3_OFF_G = 9 * HALF, D3_OFF_W = 10 * HALF, D3_OFF_TAB = 12 * HALF;
+constexpr int D3_OFF_BAR = D3_OFF_TAB + TAB_FLOATS * 4;
+constexpr int D3_SMEM = D3_OFF_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                      const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
+                      const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = base + D3_OFF_C; uint8_t* sB = base + D3_OFF_B; uint8_t* sX = base + D3_OFF_X;
+  uint8_t* sdY = base + D3_OFF_DY; uint8_t* sXw = base + D3_OFF_XW; uint8_t* sdYs = base + D3_OFF_DYS;
+  uint8_t* sS = base + D3_OFF_S; uint8_t* sG = base + D3_OFF_G; uint8_t* sW = base + D3_OFF_W;
+  float* tab = reinterpret_cast<float*>(base + D3_OFF_TAB);
+  const float* s_cs = tab; const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
+  const float* s_f = tab + 5 * TQ;
+  uint64_t* bar_cb = reinterpret_cast<uint64_t*>(base + D3_OFF_BAR);
+  uint64_t* bar_h = bar_cb + 1;
+  uint64_t* bar_r = bar_cb + 2;
+  uint64_t* bar_m = bar_cb + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_cb + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, ch = warp >> 2, row = lq * 32 + lane;
+  if (tid == 0) {
+    umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
+    umma::mbar_init(bar_cb, 1); umma::mbar_init(bar_h, 1); umma::mbar_init(bar_r, 1); umma::mbar_init(bar_m, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * nc;
+  constexpr uint32_t i_kk = umma::make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t i_km = umma::make_idesc_bf16(128, 128, 0, 1);
+  constexpr uint32_t i_mm = umma::make_idesc_bf16(128, 128, 1, 1);
+  auto load_cb = [&](int item) {
+    const int c = item % nc, db = item / nc;
+    umma::mbar_expect_tx(bar_cb, 4 * HALF);
+    umma::tma_load_3d(sC, &tmX, bar_cb, di + TN, c * TQ, db);
+    umma::tma_load_3d(sC + HALF, &tmX, bar_cb, di + TN + 64, c * TQ, db);
+    umma::tma_load_3d(sB, &tmX, bar_cb, di, c * TQ, db);
+    umma::tma_load_3d(sB + HALF, &tmX, bar_cb, di + 64, c * TQ, db);
+  };
+  auto load_head = [&](int item, int h) {
+    const int c = item % nc, db = item / nc;
+    const int srow = (((db * H + h) * nc) + c) * TN;
+    umma::mbar_expect_tx(bar_h, 4 * HALF);
+    umma::tma_load_3d(sX, &tmX, bar_h, h * TP, c * TQ, db);
+    umma::tma_load_3d(sdY, &tmDY, bar_h, h * TP, c * TQ, db);
+    umma::tma_load_2d(sS, &tmS, bar_h, 0, srow);
+    umma::tma_load_2d(sG, &tmG, bar_h, 0, srow);
+  };
+  uint32_t iseq = 0, hseq = 0;
+  if (blockIdx.x < n_items && tid == 0) { load_cb(blockIdx.x); load_head(blockIdx.x, 0); }
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
+    const int c = it % nc, db = it / nc, dir = db / p.B;
+    const int q0 = c * TQ, qv = min(TQ, L - q0);
+    const long long row0 = (long long)db * L + q0;
+    for (int h = 0; h < H; ++h, ++hseq) {
+      const uint32_t par = hseq & 1;
+      const float A = -__expf(p.A_log[dir * H + h]);
+      build_tables(p.dt + row0 * H + h, H, qv, A, tab);
+      if (h == 0) umma::mbar_wait(bar_cb, iseq & 1);
+      umma::mbar_wait(bar_h, par);
+      if (tid == 0) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)                                 // R = dY X^T
+          umma::mma_bf16_ss(tmem + 0, umma::make_smem_desc(umma::smem_u32(sdY) + kb * 32, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), i_kk, kb > 0);
+        umma::mma_commit(bar_r);
+      }
+      for (int i = tid; i < TQ * 8; i += TC_THREADS) {                 // Xw = w_q X,  dYs = e^{cs_t} dY
+        const float w = s_w[i >> 3], e = s_ecs[i >> 3];
+        float a[8], b[8];
+        unpack8(reinterpret_cast<const uint4*>(sX)[i], a);
+        unpack8(reinterpret_cast<const uint4*>(sdY)[i], b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a[k] *= w; b[k] *= e; }
+        reinterpret_cast<uint4*>(sXw)[i] = pack8(a);
+        reinterpret_cast<uint4*>(sdYs)[i] = pack8(b);
+      }
+      umma::mbar_wait(bar_r, par);
+      umma::tc_fence_after();
+      {   // W[t,q] = R[t,q] L[t,q] dt_q
+        const int t = row, I = t >> 5;
+        const float cs_t = s_cs[t];
+        const float e_ref = (I > 0) ? __expf(cs_t - s_cs[32 * I - 1]) : 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int J = 2 * ch + cc, s0 = 32 * J;
+          float r[32];
+          if (J <= I) {
+            umma::tmem_ld32(t_lane + (uint32_t)s0, r);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] *= decay_elem(t, I, J, s0 + j, cs_t, e_ref, s_cs, s_f) * s_dt[s0 + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sW + ch * HALF + swz(t, 4 * cc + k)) = pack8(r + 8 * k);
+        }
+      }
+      umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
+      if (tid == 0) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {                               // dC += W B
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sW) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024), i_km, (h > 0 || kb > 0));
+        }
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)                                 // dC += (e^{cs} dY) S_in^T
+          umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sdYs) + kb * 32, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sS) + kb * 32, 16, 1024), i_kk, 1u);
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb)                                 // dB += W^T C
+          umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sW) + kb * 2048, HALF, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024), i_mm, (h > 0 || kb > 0));
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)                                 // dB += (w X) Gst^T
+          umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sXw) + kb * 32, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sG) + kb * 32, 16, 1024), i_kk, 1u);
+        umma::mma_commit(bar_m);
+      }
+      umma::mbar_wait(bar_m, par);
+      umma::tc_fence_after();
+      if (tid == 0) {
+        if (h + 1 < H) load_head(it, h + 1);
+        else if (it + (int)gridDim.x < n_items) { load_cb(it + gridDim.x); load_head(it + gridDim.x, 0); }
+      }
+    }
+    // ---- write dB | dC of this chunk (fp32)
+    {
+      const int t = row;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {                            // 0: dB (TMEM 256..383), 1: dC (TMEM 128..255)
+        const uint32_t tb = part == 0 ? 256u : 128u;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float v[32];
+          umma::tmem_ld32(t_lane + tb + 64u * ch + 32u * cc, v);
+          umma::tmem_ld_wait();
+          if (t < qv) {
+            float* og = p.dBC + (row0 + t) * (2 * TN) + part * TN + 64 * ch + 32 * cc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(og + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+    }
+    umma::tc_fence_before(); __syncthreads();
+  }
+  umma::tc_fence_before(); __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+}  // namespace hnb
+
 using namespace hnb;
 
-int hnb_ssd_fwd_tc(const void*, const float*, const float*, const float*, int, int, int, int, int, int, void*, void*,
-                   void*) {
-  set_error("ssd_fwd: tcgen05 implementation not built in this revision");
-  return HNB_ERR_UNSUPPORTED;
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
-int hnb_ssd_bwd_tc(const void*, const void*, const void*, const float*, const float*, const float*, const void*, int,
-                   int, int, int, int, int, void*, float*, float*, float*, float*, void*, void*) {
-  set_error("ssd_bwd: tcgen05 implementation not built in this revision");
-  return HNB_ERR_UNSUPPORTED;
+
+int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B, int L,
+                   int di, int N, int H, void* y, void* states, void* stream) {
+  HNB_CHECK_ARG(N == TN && di == H * TP, "ssd_fwd(tcgen05): built for d_state=128, headdim=64");
+  const int C = di + 2 * N;
+  CUtensorMap tm;
+  uint64_t dims[3] = {(uint64_t)C, (uint64_t)L, (uint64_t)ndir * B};
+  uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)L * C * 2};
+  uint32_t box[3] = {64, TQ, 1};
+  int rc = make_tmap_bf16(&tm, xconv, 3, dims, strides, box);
+  if (rc) return rc;
+  FwdParams p;
+  p.dt = dt; p.A_log = A_log; p.Dskip = Dskip;
+  p.y = (__nv_bfloat16*)y; p.states = (__nv_bfloat16*)states;
+  p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = cdiv(L, TQ);
+  const int items = ndir * B * H;
+  const int grid = items < sm_count() ? items : sm_count();
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  ssd_fwd_tc_kernel<<<grid, TC_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
+  HNB_LAUNCH_CHECK("ssd_fwd_tc");
+  return HNB_OK;
+}
+
+int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
+                   const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
+                   float* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream) {
+  (void)y;
+  HNB_CHECK_ARG(N == TN && di == H * TP, "ssd_bwd(tcgen05): built for d_state=128, headdim=64");
+  const int C = di + 2 * N, nc = cdiv(L, TQ);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmX, tmDY, tmS, tmG;
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)L, (uint64_t)ndir * B};
+    uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)L * C * 2};
+    uint32_t box[3] = {64, TQ, 1};
+    if ((rc = make_tmap_bf16(&tmX, xconv, 3, dims, strides, box))) return rc;
+    dims[0] = (uint64_t)di; strides[0] = (uint64_t)di * 2; strides[1] = (uint64_t)L * di * 2;
+    if ((rc = make_tmap_bf16(&tmDY, dy, 3, dims, strides, box))) return rc;
+    uint64_t d2[2] = {(uint64_t)TP, (uint64_t)ndir * B * H * nc * TN};
+    uint64_t s2[1] = {(uint64_t)TP * 2};
+    uint32_t b2[2] = {TP, TN};
+    if ((rc = make_tmap_bf16(&tmS, states, 2, d2, s2, b2))) return rc;
+    if ((rc = make_tmap_bf16(&tmG, ws2, 2, d2, s2, b2))) return rc;
+  }
+  BwdParams p;
+  p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.gstates = (__nv_bfloat16*)ws2; p.dxc = (__nv_bfloat16*)dxc;
+  p.dBC = dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
+  p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = nc;
+  const int sms = sm_count();
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dstate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D1_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
+  int items = ndir * B * H;
+  ssd_bwd_dstate_tc_kernel<<<items < 2 * sms ? items : 2 * sms, TC_THREADS, D1_SMEM, st>>>(tmX, tmDY, p);
+  HNB_LAUNCH_CHECK("ssd_bwd_dstate_tc");
+  items = ndir * B * nc * H;
+  ssd_bwd_dx_tc_kernel<<<items < sms ? items : sms, TC_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  HNB_LAUNCH_CHECK("ssd_bwd_dx_tc");
+  items = ndir * B * nc;
+  ssd_bwd_dbc_tc_kernel<<<items < sms ? items : sms, TC_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  HNB_LAUNCH_CHECK("ssd_bwd_dbc_tc");
+  return HNB_OK;
 }

@@ -211,21 +211,22 @@ def conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias, ndir,
 
 def ssd_impl_for(dtype) -> int:
     if SSD_IMPL == "auto":
-        return 0
+        return 1 if dtype == torch.bfloat16 else 0      # tcgen05 for bf16, exact CUDA-core path for fp32
     return int(SSD_IMPL)
 
 
-def ssd_fwd(xconv, dt, A_log, D, ndir, B, L, di, N, H):
+def ssd_fwd(xconv, dt, A_log, D, ndir, B, L, di, N, H, impl=None):
     L_ = lib()
+    impl = ssd_impl_for(xconv.dtype) if impl is None else impl
     y = _empty((ndir, B * L, di), xconv.dtype, xconv)
     ws = _empty((L_.raw("ssd_ws_bytes")(ndir, B, L, di, N, H) // 4,), torch.float32, xconv)
-    L_.call("ssd_fwd", xconv, dtype_code(xconv.dtype), dt, A_log, D, ndir, B, L, di, N, H, y, ws,
-            ssd_impl_for(xconv.dtype), stream())
+    L_.call("ssd_fwd", xconv, dtype_code(xconv.dtype), dt, A_log, D, ndir, B, L, di, N, H, y, ws, impl, stream())
     return y, ws
 
 
-def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H):
+def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H, impl=None):
     L_ = lib()
+    impl = ssd_impl_for(dy.dtype) if impl is None else impl
     dxc = torch.empty_like(dy)
     dBC = _empty((ndir, B * L, 2 * N), torch.float32, dy)
     ddt = torch.empty_like(dt)
@@ -233,7 +234,7 @@ def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H):
     dD = torch.zeros_like(D)
     ws2 = _empty((L_.raw("ssd_ws_bytes")(ndir, B, L, di, N, H) // 4,), torch.float32, dy)
     L_.call("ssd_bwd", dy, xconv, y, dtype_code(dy.dtype), dt, A_log, D, ws, ndir, B, L, di, N, H, dxc, dBC, ddt,
-            dA, dD, ws2, ssd_impl_for(dy.dtype), stream())
+            dA, dD, ws2, impl, stream())
     return dxc, dBC, ddt, dA, dD
 
 

@@ -150,6 +150,47 @@ def test_conv_ssd_norm_kernels_vs_oracle_fp32(B, L, lengths):
         assert rel_err(dcb[r], m.conv1d.bias.grad) < 1e-3
 
 
+def _ssd_inputs(ndir, B, L, H, seed=0):
+    torch.manual_seed(seed)
+    di, N = 64 * H, 128
+    xconv = (torch.randn(ndir, B * L, di + 2 * N, device=DEV) * 0.8).to(torch.bfloat16)
+    dt = F.softplus(torch.randn(ndir, B * L, H, device=DEV) - 2.0)
+    A_log = torch.log(torch.rand(ndir, H, device=DEV) * 15 + 1)
+    Dk = torch.randn(ndir, H, device=DEV)
+    return xconv, dt, A_log, Dk, di, N
+
+
+@pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 1498, 16), (1, 5, 77, 4)])
+def test_ssd_tcgen05_forward_vs_exact(ndir, B, L, H):
+    """tcgen05/TMEM SSD forward (impl 1) against the fp32 CUDA-core path (impl 0) on identical bf16 inputs."""
+    from dcasr_b200 import ops
+    xconv, dt, A_log, Dk, di, N = _ssd_inputs(ndir, B, L, H)
+    y0, _ = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=0)
+    y1, _ = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1)
+    torch.cuda.synchronize()
+    err = rel_err(y1, y0)
+    print("ssd tcgen05 fwd rel err vs exact:", err)
+    assert err < 1e-2        # bf16 rounding of M, S_in and w*x operands (the upstream kernels round the same tensors)
+
+
+@pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 700, 16), (1, 5, 77, 4)])
+def test_ssd_tcgen05_backward_vs_exact(ndir, B, L, H):
+    """tcgen05 SSD backward (3 kernels) against the fp32 CUDA-core backward on identical bf16 inputs."""
+    from dcasr_b200 import ops
+    xconv, dt, A_log, Dk, di, N = _ssd_inputs(ndir, B, L, H, seed=1)
+    dy = (torch.randn(ndir, B * L, di, device=DEV) * 0.5).to(torch.bfloat16)
+    y0, ws0 = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=0)
+    y1, ws1 = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1)
+    r0 = ops.ssd_bwd(dy, xconv, y0, dt, A_log, Dk, ws0, ndir, B, L, di, N, H, impl=0)
+    r1 = ops.ssd_bwd(dy, xconv, y1, dt, A_log, Dk, ws1, ndir, B, L, di, N, H, impl=1)
+    torch.cuda.synchronize()
+    names = ("dxc", "dBC", "ddt", "dA_log", "dD")
+    errs = {n: rel_err(a, b) for n, a, b in zip(names, r1, r0)}
+    print("ssd tcgen05 bwd rel err vs exact:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["dxc"] < 1e-2 and errs["dBC"] < 1e-2 and errs["dD"] < 1e-2
+    assert errs["ddt"] < 2e-2 and errs["dA_log"] < 3e-2
+
+
 @pytest.mark.parametrize("path", STACK, ids=[os.path.basename(p)[:-4] for p in STACK])
 def test_stack_matches_reference_golden_fp32(path):
     import dcasr_b200 as dd
