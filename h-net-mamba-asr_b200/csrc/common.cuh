@@ -112,6 +112,10 @@ template <typename T, int VN> __device__ __forceinline__ void ldv(const T* p, fl
 template <> __device__ __forceinline__ void ldv<float, 4>(const float* p, float* r) {
   float4 t = *reinterpret_cast<const float4*>(p); r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
 }
+template <> __device__ __forceinline__ void ldv<float, 8>(const float* p, float* r) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
 template <> __device__ __forceinline__ void ldv<float, 2>(const float* p, float* r) {
   float2 t = *reinterpret_cast<const float2*>(p); r[0] = t.x; r[1] = t.y;
 }

@@ -159,25 +159,25 @@ gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long lo
   }
 }
 
-// backward: dout (natural) -> dy (scan order), dz (natural, into dzxbcdt), dw (accumulated)
+// backward: dout (natural) -> dy (scan order), dz (natural, into dzxbcdt), dw (accumulated).
+// Two passes over the row (the second one hits L1) keep the live state to the per-lane dw accumulators, so
+// that several CTAs fit per SM; the first version held four row-sized register arrays and ran at 1 CTA/SM.
 template <typename T, int VN, int NV>
 __global__ void __launch_bounds__(NORM_WARPS * 32)
-gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const T* __restrict__ zx, long long ldz, long long dstride,
-                      const int* __restrict__ lengths, const float* __restrict__ w, const float* __restrict__ rstd,
-                      int ndir, int B, int L, int di, T* __restrict__ dy, T* __restrict__ dzx,
-                      float* __restrict__ dw) {
+gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const T* __restrict__ zx, long long ldz,
+                      long long dstride, const int* __restrict__ lengths, const float* __restrict__ w,
+                      const float* __restrict__ rstd, int ndir, int B, int L, int di, T* __restrict__ dy,
+                      T* __restrict__ dzx, float* __restrict__ dw) {
   extern __shared__ float sm[];                                     // [di]
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const long long T_ = (long long)B * L;
   const int dir = blockIdx.y;
-  float aw[NV][VN], ww[NV][VN];
+  const float* wr = w + (long long)dir * di;
+  float aw[NV][VN];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = (k * 32 + lane) * VN;
+  for (int k = 0; k < NV; ++k)
 #pragma unroll
-    for (int i = 0; i < VN; ++i) { aw[k][i] = 0.f; ww[k][i] = 0.f; }
-    if (c < di) ldv<float, VN>(w + (long long)dir * di + c, ww[k]);
-  }
+    for (int i = 0; i < VN; ++i) aw[k][i] = 0.f;
   for (long long tok = (long long)blockIdx.x * NORM_WARPS + wi; tok < T_; tok += (long long)gridDim.x * NORM_WARPS) {
     const int bi = (int)(tok / L), t = (int)(tok % L);
     const int len = lengths ? lengths[bi] : L;
@@ -186,23 +186,15 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
     const T* zr = zx + tok * ldz + (long long)dir * dstride;
     const T* gr = dout + tok * ((long long)ndir * di) + (long long)dir * di;
     const float rs = rstd[(long long)dir * T_ + tok];
-    float gh[NV][VN], dn[NV][VN], yv[NV][VN], zv[NV][VN];
     float s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * VN;
-#pragma unroll
-      for (int i = 0; i < VN; ++i) { gh[k][i] = 0.f; dn[k][i] = 0.f; yv[k][i] = 0.f; zv[k][i] = 0.f; }
       if (c < di) {
-        float go[VN];
-        ldv<T, VN>(y + yoff + c, yv[k]); ldv<T, VN>(zr + c, zv[k]); ldv<T, VN>(gr + c, go);
+        float yv[VN], zv[VN], go[VN], ww[VN];
+        ldv<T, VN>(y + yoff + c, yv); ldv<T, VN>(zr + c, zv); ldv<T, VN>(gr + c, go); ldv<float, VN>(wr + c, ww);
 #pragma unroll
-        for (int i = 0; i < VN; ++i) {
-          gh[k][i] = yv[k][i] * silu_f(zv[k][i]) * rs;              // normalised gated value
-          aw[k][i] += go[i] * gh[k][i];
-          dn[k][i] = go[i] * ww[k][i];
-          s2 += dn[k][i] * gh[k][i];
-        }
+        for (int i = 0; i < VN; ++i) s2 += go[i] * ww[i] * yv[i] * silu_f(zv[i]) * rs;
       }
     }
     s2 = warp_sum(s2) / di;
@@ -210,13 +202,16 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * VN;
       if (c < di) {
-        float o1[VN], o2[VN];
+        float yv[VN], zv[VN], go[VN], ww[VN], o1[VN], o2[VN];
+        ldv<T, VN>(y + yoff + c, yv); ldv<T, VN>(zr + c, zv); ldv<T, VN>(gr + c, go); ldv<float, VN>(wr + c, ww);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          const float dg = rs * (dn[k][i] - gh[k][i] * s2);
-          const float sg = sigmoid_f(zv[k][i]);
-          o1[i] = dg * zv[k][i] * sg;                               // d y
-          o2[i] = dg * yv[k][i] * sg * (1.f + zv[k][i] * (1.f - sg));   // d z
+          const float sg = sigmoid_f(zv[i]);
+          const float gh = yv[i] * zv[i] * sg * rs;                  // normalised gated value
+          aw[k][i] += go[i] * gh;
+          const float dg = rs * (go[i] * ww[i] - gh * s2);
+          o1[i] = dg * zv[i] * sg;                                   // d y
+          o2[i] = dg * yv[i] * sg * (1.f + zv[i] * (1.f - sg));      // d z
         }
         stv<T, VN>(dy + yoff + c, o1);
         stv<T, VN>(dzx + tok * ldz + (long long)dir * dstride + c, o2);
@@ -303,9 +298,12 @@ extern "C" int hnb_gated_norm_fwd(const void* y, const void* zxbcdt, int dtype, 
   const int grid = cdiv(rows, NORM_WARPS);
   const bool v4 = di % 4 == 0 && ldz % 4 == 0 && dstride % 4 == 0 && al(y, 4 * esz(dtype)) && al(zxbcdt, 4 * esz(dtype)) &&
                   al(out, 4 * esz(dtype)) && al(norm_w, 16);
+  const bool v8 = dtype == HNB_BF16 && di % 8 == 0 && ldz % 8 == 0 && dstride % 8 == 0 && al(y, 16) && al(zxbcdt, 16) &&
+                  al(out, 16) && al(norm_w, 16);
 #define RUN(T, VN) gated_norm_fwd_kernel<T, VN><<<grid, NORM_WARPS * 32, 0, st>>>( \
       (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, ndir, B, L, di, eps, (T*)out, rstd)
-  HNB_DISPATCH_DTYPE(dtype, T, { if (v4) RUN(T, 4); else RUN(T, 1); });
+  if (v8) RUN(__nv_bfloat16, 8);
+  else HNB_DISPATCH_DTYPE(dtype, T, { if (v4) RUN(T, 4); else RUN(T, 1); });
 #undef RUN
   HNB_LAUNCH_CHECK("gated_norm_fwd");
   return HNB_OK;
@@ -323,7 +321,9 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
   dim3 grid(gx, ndir);
   const bool v4 = di % 4 == 0 && ldz % 4 == 0 && dstride % 4 == 0 && al(y, 4 * esz(dtype)) && al(zxbcdt, 4 * esz(dtype)) &&
                   al(dout, 4 * esz(dtype)) && al(dy, 4 * esz(dtype)) && al(dzxbcdt, 4 * esz(dtype)) && al(norm_w, 16);
-  const int vn = v4 ? 4 : 1;
+  const bool v8 = dtype == HNB_BF16 && di % 8 == 0 && ldz % 8 == 0 && dstride % 8 == 0 && al(y, 16) && al(zxbcdt, 16) &&
+                  al(dout, 16) && al(dy, 16) && al(dzxbcdt, 16) && al(norm_w, 16);
+  const int vn = v8 ? 8 : (v4 ? 4 : 1);
   const int nv = cdiv(di, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "gated_norm_bwd: d_inner=%d too large", di);
   const size_t smem = (size_t)di * sizeof(float);
@@ -331,11 +331,13 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
       (const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w)
 #define RUN(T, VN)                                                             \
   do {                                                                         \
-    if (nv <= 2) RUN2(T, VN, 2); else if (nv <= 4) RUN2(T, VN, 4);             \
+    if (nv <= 1) RUN2(T, VN, 1); else if (nv <= 2) RUN2(T, VN, 2);             \
+    else if (nv <= 3) RUN2(T, VN, 3); else if (nv <= 4) RUN2(T, VN, 4);        \
     else if (nv <= 6) RUN2(T, VN, 6); else if (nv <= 8) RUN2(T, VN, 8);        \
     else if (nv <= 12) RUN2(T, VN, 12); else RUN2(T, VN, 16);                  \
   } while (0)
-  HNB_DISPATCH_DTYPE(dtype, T, { if (v4) RUN(T, 4); else RUN(T, 1); });
+  if (v8) RUN(__nv_bfloat16, 8);
+  else HNB_DISPATCH_DTYPE(dtype, T, { if (v4) RUN(T, 4); else RUN(T, 1); });
 #undef RUN
 #undef RUN2
   HNB_LAUNCH_CHECK("gated_norm_bwd");

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(ST)
 ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, int C, int di,
                      const float* __restrict__ dt, const float* __restrict__ A_log, const float* __restrict__ Dskip,
                      const float* __restrict__ states, const float* __restrict__ gstates, int ndir, int B, int L,
-                     int H, int nc, T* __restrict__ dxc, float* __restrict__ dBC, float* __restrict__ ddt,
+                     int H, int nc, T* __restrict__ dxc, T* __restrict__ dBC, float* __restrict__ ddt,
                      float* __restrict__ dA_log, float* __restrict__ dD) {
   extern __shared__ float smem[];
   float* Bn = smem;                        // [SQ][SN]
@@ -507,30 +507,30 @@ ssd_bwd_chunk_kernel(const T* __restrict__ dy, const T* __restrict__ xconv, int 
       if (tid == 0) atomicAdd(dA_log + dir * H + h, accA * A);
     }
   }
-  // ---- write dB | dC for this chunk: first the (t, n)-mapped tiles, then add the (n, t)-mapped ones
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int t = wt + 8 * i;
-    if (t < qv) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = wn + 32 * j;
-        dBC[(row0 + t) * (2 * SN) + n] = accB[i][j];
-        dBC[(row0 + t) * (2 * SN) + SN + n] = accC[i][j];
-      }
-    }
-  }
+  // ---- write dB | dC for this chunk.  The (t, n)-mapped and the (n, t)-mapped register tiles are summed in
+  // shared memory (Bn / Cn are dead by now; every element has one owner per pass) and stored once, coalesced.
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int t = tj + 16 * j;
-    if (t < qv) {
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int n = ti + 16 * i;
-        dBC[(row0 + t) * (2 * SN) + n] += accB2[i][j];
-        dBC[(row0 + t) * (2 * SN) + SN + n] += accC2[i][j];
-      }
+    for (int j = 0; j < 4; ++j) {
+      Bn[(wt + 8 * i) * SN + wn + 32 * j] = accB[i][j];
+      Cn[(wt + 8 * i) * SN + wn + 32 * j] = accC[i][j];
+    }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      Bn[(tj + 16 * j) * SN + ti + 16 * i] += accB2[i][j];
+      Cn[(tj + 16 * j) * SN + ti + 16 * i] += accC2[i][j];
+    }
+  __syncthreads();
+  for (int i = tid; i < SQ * SN / 4; i += ST) {
+    const int t = i / (SN / 4), n4 = (i % (SN / 4)) * 4;
+    if (t < qv) {
+      stv<T, 4>(dBC + (row0 + t) * (2 * SN) + n4, Bn + t * SN + n4);
+      stv<T, 4>(dBC + (row0 + t) * (2 * SN) + SN + n4, Cn + t * SN + n4);
     }
   }
 }
@@ -566,7 +566,7 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
                    int di, int N, int H, void* y, void* states, void* stream);
 int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
                    const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
-                   float* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream);
+                   void* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream);
 
 template <typename T>
 static int ssd_fwd_impl(const T* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B,
@@ -611,7 +611,7 @@ extern "C" int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const 
 
 template <typename T>
 static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt, const float* A_log,
-                        const float* Dskip, const float* ws, int ndir, int B, int L, int di, int H, T* dxc, float* dBC,
+                        const float* Dskip, const float* ws, int ndir, int B, int L, int di, int H, T* dxc, T* dBC,
                         float* ddt, float* dA_log, float* dD, float* ws2, cudaStream_t st) {
   const int nc = cdiv(L, SQ), C = di + 2 * SN;
   const size_t nst = ssd_states_floats(ndir, B, L, H);
@@ -637,7 +637,7 @@ static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt
 
 extern "C" int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int dtype, const float* dt,
                            const float* A_log, const float* Dskip, const void* states, int ndir, int B, int L, int di,
-                           int N, int H, void* dxc, float* dBC, float* ddt, float* dA_log, float* dD, void* ws2,
+                           int N, int H, void* dxc, void* dBC, float* ddt, float* dA_log, float* dD, void* ws2,
                            int impl, void* stream) {
   HNB_CHECK_ARG(dy && xconv && y && dt && A_log && Dskip && states && dxc && dBC && ddt && dA_log && dD && ws2,
                 "ssd_bwd: null pointer");
@@ -652,10 +652,10 @@ extern "C" int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int
   if (dtype == HNB_BF16)
     return ssd_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)xconv, (const __nv_bfloat16*)y,
                                        dt, A_log, Dskip, (const float*)states, ndir, B, L, di, H, (__nv_bfloat16*)dxc,
-                                       dBC, ddt, dA_log, dD, (float*)ws2, st);
+                                       (__nv_bfloat16*)dBC, ddt, dA_log, dD, (float*)ws2, st);
   if (dtype == HNB_F32)
     return ssd_bwd_impl<float>((const float*)dy, (const float*)xconv, (const float*)y, dt, A_log, Dskip,
-                               (const float*)states, ndir, B, L, di, H, (float*)dxc, dBC, ddt, dA_log, dD, (float*)ws2, st);
+                               (const float*)states, ndir, B, L, di, H, (float*)dxc, (float*)dBC, ddt, dA_log, dD, (float*)ws2, st);
   set_error("ssd_bwd: unsupported dtype");
   return HNB_ERR_INVALID_ARG;
 }

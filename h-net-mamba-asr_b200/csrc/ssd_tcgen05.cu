@@ -308,7 +308,7 @@ struct BwdParams {
   const float* dt; const float* A_log; const float* Dskip;
   __nv_bfloat16* gstates;        // [ndir*B, H, nc, 128, 64]
   __nv_bfloat16* dxc;            // [ndir*B*L, di]
-  float* dBC;                    // [ndir*B*L, 2N]
+  __nv_bfloat16* dBC;            // [ndir*B*L, 2N]
   float* ddt;                    // [ndir*B*L, H]
   float* dA_log; float* dD;      // [ndir, H]
   int ndirB, B, L, H, di, nc;
@@ -774,7 +774,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         else if (it + (int)gridDim.x < n_items) { load_cb(it + gridDim.x); load_head(it + gridDim.x, 0); }
       }
     }
-    // ---- write dB | dC of this chunk (fp32)
+    // ---- write dB | dC of this chunk (bf16, like the rest of the activation gradients)
     {
       const int t = row;
 #pragma unroll
@@ -786,9 +786,9 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           umma::tmem_ld32(t_lane + tb + 64u * ch + 32u * cc, v);
           umma::tmem_ld_wait();
           if (t < qv) {
-            float* og = p.dBC + (row0 + t) * (2 * TN) + part * TN + 64 * ch + 32 * cc;
+            __nv_bfloat16* og = p.dBC + (row0 + t) * (2 * TN) + part * TN + 64 * ch + 32 * cc;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(og + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(og + 8 * k) = pack8(v + 8 * k);
           }
         }
       }
@@ -839,7 +839,7 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
 
 int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
                    const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
-                   float* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream) {
+                   void* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream) {
   (void)y;
   HNB_CHECK_ARG(N == TN && di == H * TP, "ssd_bwd(tcgen05): built for d_state=128, headdim=64");
   const int C = di + 2 * N, nc = cdiv(L, TQ);
@@ -861,7 +861,7 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   }
   BwdParams p;
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.gstates = (__nv_bfloat16*)ws2; p.dxc = (__nv_bfloat16*)dxc;
-  p.dBC = dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
+  p.dBC = (__nv_bfloat16*)dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = nc;
   const int sms = sm_count();
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dstate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D1_SMEM));

@@ -228,7 +228,7 @@ def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H, impl=None):
     L_ = lib()
     impl = ssd_impl_for(dy.dtype) if impl is None else impl
     dxc = torch.empty_like(dy)
-    dBC = _empty((ndir, B * L, 2 * N), torch.float32, dy)
+    dBC = _empty((ndir, B * L, 2 * N), dy.dtype, dy)
     ddt = torch.empty_like(dt)
     dA = torch.zeros_like(A_log)
     dD = torch.zeros_like(D)

@@ -134,10 +134,10 @@ int hnb_conv_fwd(const void* zxbcdt, int dtype, long long ldz, long long dstride
                  const float* conv_w, const float* conv_b, const float* dt_bias,
                  int ndir, int B, int L, int di, int N, int H,
                  void* xconv, float* dt, void* stream);
-/* backward: reads dxc [ndir,B*L,di] (act dtype, d wrt conv'd x), dBC [ndir,B*L,2N] float, ddt
+/* backward: reads dxc [ndir,B*L,di] and dBC [ndir,B*L,2N] (both act dtype: d wrt conv'd x | B | C), ddt
  * [ndir,B*L,H] float (all scan order); writes the xBC and dt columns of dzxbcdt (natural order) and
  * ACCUMULATES dconv_w, dconv_b, ddt_bias. */
-int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long long ldz, long long dstride, const float* dBC,
+int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long long ldz, long long dstride, const void* dBC,
                  const float* ddt, const int32_t* lengths, const float* conv_w, const float* conv_b,
                  const float* dt_bias, int ndir, int B, int L, int di, int N, int H,
                  void* dzxbcdt, float* dconv_w, float* dconv_b, float* ddt_bias, void* stream);
@@ -158,7 +158,7 @@ int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const float* A_lo
 int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int dtype, const float* dt,
                 const float* A_log, const float* Dskip, const void* states,
                 int ndir, int B, int L, int di, int N, int H,
-                void* dxc, float* dBC, float* ddt, float* dA_log, float* dD, void* ws2, int impl,
+                void* dxc, void* dBC, float* ddt, float* dA_log, float* dD, void* ws2, int impl,
                 void* stream);
 
 /* gated RMSNorm  rmsnorm(y * silu(z)) * w  (mamba_ssm RMSNormGated, norm_before_gate=False, eps 1e-5)
