@@ -220,6 +220,8 @@ def run_ours(args):
         for p in enc.parameters():
             dist.broadcast(p.data, 0)
     params = [p for p in enc.parameters()]
+    from dcasr_b200.distributed import GradAllReducer
+    reducer = GradAllReducer(params) if world > 1 else None
     feats_h, lens_h = synth_batch(args.batch, args.seconds, 1 + rank)      # each rank its own shard of utterances
     feats_pin, lens_pin = feats_h.pin_memory(), lens_h.pin_memory()
     feats_d, lens_d = feats_h.to(dev), lens_h.to(dev)
@@ -233,10 +235,8 @@ def run_ours(args):
             out = enc(feats, lens)
         loss = out.features.float().pow(2).mean() + 0.03 * out.ratio_loss
         loss.backward()
-        if world > 1:                               # the one exchange of the path: gradient all-reduce (DDP semantics)
-            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-            dist.all_reduce(flat)
-            flat.div_(world)
+        if reducer is not None:                     # the one exchange of the path: gradient all-reduce (DDP semantics)
+            reducer()
         kept[0] = out.kept_fractions[0]
         return loss
 

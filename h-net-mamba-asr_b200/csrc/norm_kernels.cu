@@ -232,6 +232,53 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
   for (int c = threadIdx.x; c < di; c += blockDim.x) atomicAdd(dw + (long long)dir * di + c, sm[c]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-step parameter packing of one mixer direction (replaces ~10 torch cat/stack/cast launches per block):
+// in_proj.weight -> rows [dir*dstride, +dip) of Win (pad rows zeroed), out_proj.weight -> columns [dir*di, +di) of
+// Wout, both cast to the activation dtype; the small fp32 vectors are copied into their [ndir, ...] stacks.
+// ---------------------------------------------------------------------------------------------
+template <typename TW>
+__global__ void __launch_bounds__(256)
+pack_mixer_kernel(const float* __restrict__ in_w, const float* __restrict__ out_w, const float* __restrict__ conv_w,
+                  const float* __restrict__ conv_b, const float* __restrict__ dt_bias, const float* __restrict__ A_log,
+                  const float* __restrict__ Dk, const float* __restrict__ norm_w, int dir, int ndir, int d, int di,
+                  int N, int H, int dstride, TW* __restrict__ Win, TW* __restrict__ Wout, float* __restrict__ conv_w_o,
+                  float* __restrict__ conv_b_o, float* __restrict__ dt_bias_o, float* __restrict__ A_log_o,
+                  float* __restrict__ D_o, float* __restrict__ norm_w_o) {
+  const int dip = 2 * di + 2 * N + H, C = di + 2 * N;
+  const long long n_in = (long long)dstride * d / 4, n_out = (long long)d * di / 4;
+  const long long n_small = (long long)C * 4 + C + 3 * H + di;
+  const long long total = n_in + n_out + n_small;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_in) {                                          // d % 4 == 0 (checked on the host)
+      const long long e = i * 4;
+      const int r = (int)(e / d), c = (int)(e % d);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r < dip) ldv<float, 4>(in_w + (long long)r * d + c, v);
+      stv<TW, 4>(Win + ((long long)dir * dstride + r) * d + c, v);
+    } else if (i < n_in + n_out) {
+      const long long e = (i - n_in) * 4;
+      const int r = (int)(e / di), c = (int)(e % di);
+      float v[4];
+      ldv<float, 4>(out_w + (long long)r * di + c, v);
+      stv<TW, 4>(Wout + (long long)r * ndir * di + (long long)dir * di + c, v);
+    } else {
+      long long j = i - n_in - n_out;
+      if (j < (long long)C * 4) { conv_w_o[(long long)dir * C * 4 + j] = conv_w[j]; continue; }
+      j -= (long long)C * 4;
+      if (j < C) { conv_b_o[(long long)dir * C + j] = conv_b[j]; continue; }
+      j -= C;
+      if (j < H) { dt_bias_o[dir * H + j] = dt_bias[j]; continue; }
+      j -= H;
+      if (j < H) { A_log_o[dir * H + j] = A_log[j]; continue; }
+      j -= H;
+      if (j < H) { D_o[dir * H + j] = Dk[j]; continue; }
+      j -= H;
+      norm_w_o[(long long)dir * di + j] = norm_w[j];
+    }
+  }
+}
+
 }  // namespace hnb
 
 using namespace hnb;
@@ -341,5 +388,24 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
 #undef RUN
 #undef RUN2
   HNB_LAUNCH_CHECK("gated_norm_bwd");
+  return HNB_OK;
+}
+
+extern "C" int hnb_pack_mixer_params(const float* in_w, const float* out_w, const float* conv_w, const float* conv_b,
+                                     const float* dt_bias, const float* A_log, const float* Dk, const float* norm_w,
+                                     int dir, int ndir, int d, int di, int N, int H, int dstride, void* Win, void* Wout,
+                                     int w_dtype, float* conv_w_o, float* conv_b_o, float* dt_bias_o, float* A_log_o,
+                                     float* D_o, float* norm_w_o, void* stream) {
+  HNB_CHECK_ARG(in_w && out_w && conv_w && conv_b && dt_bias && A_log && Dk && norm_w && Win && Wout && conv_w_o &&
+                conv_b_o && dt_bias_o && A_log_o && D_o && norm_w_o, "pack_mixer_params: null pointer");
+  HNB_CHECK_ARG(d % 4 == 0 && di % 4 == 0 && dir >= 0 && dir < ndir && dstride >= 2 * di + 2 * N + H,
+                "pack_mixer_params: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = ((long long)dstride * d + (long long)d * di) / 4 + (long long)(di + 2 * N) * 5 + 3 * H + di;
+  int grid = cdiv(total, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<grid, 256, 0, st>>>(in_w, out_w, conv_w, conv_b, dt_bias, A_log,
+      Dk, norm_w, dir, ndir, d, di, N, H, dstride, (TW*)Win, (TW*)Wout, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o, norm_w_o)));
+  HNB_LAUNCH_CHECK("pack_mixer_params");
   return HNB_OK;
 }

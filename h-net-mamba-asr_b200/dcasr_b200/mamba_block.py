@@ -90,39 +90,35 @@ def _mixer_forward(h2, lengths, B, L, ndir, di, N, H, params):
     dip = 2 * di + 2 * N + H
     dstride = _round_up(dip, 8)
     d = h2.shape[1]
-    if ndir == 1 and dstride == dip:
-        Win = params[0].to(adt)
-    else:
-        Win = h2.new_zeros((ndir * dstride, d))
-        for r in range(ndir):
-            Win[r * dstride: r * dstride + dip] = params[r * NP + 0]
+    Win, Wout, conv_w, conv_b, dt_bias, A_log, Dk, norm_w = ops.pack_mixer_params(
+        [p_.detach() if p_.is_contiguous() else p_.detach().contiguous() for p_ in params], ndir, d, di, N, H, dstride,
+        adt, h2.device)
     zx = ops.gemm(h2, Win)                                               # [B*L, ndir*dstride]
     C = di + 2 * N
-    conv_w = torch.stack([params[r * NP + 1].reshape(C, 4) for r in range(ndir)]).float().contiguous()
-    conv_b = torch.stack([params[r * NP + 2] for r in range(ndir)]).float().contiguous()
-    dt_bias = torch.stack([params[r * NP + 3] for r in range(ndir)]).float().contiguous()
-    A_log = torch.stack([params[r * NP + 4] for r in range(ndir)]).float().contiguous()
-    Dk = torch.stack([params[r * NP + 5] for r in range(ndir)]).float().contiguous()
-    norm_w = torch.stack([params[r * NP + 6] for r in range(ndir)]).float().contiguous()
     xconv, dt = ops.conv_fwd(zx, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H)
     y, ws = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H)
     yn, rstd = ops.gated_norm_fwd(y, zx, dstride, lengths, norm_w, ndir, B, L, di)
-    Wout = (params[7] if ndir == 1 else torch.cat([params[r * NP + 7] for r in range(ndir)], 1)).to(adt)
     saved = (Win, zx, conv_w, conv_b, dt_bias, A_log, Dk, norm_w, xconv, dt, y, ws, yn, rstd, Wout)
     return yn, Wout, saved, dstride
 
 
-def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved):
-    """dyn = d loss / d ynorm [B*L, ndir*di] -> (dh2, per-direction parameter grads except out_proj)."""
+def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, ln_acc_d=0):
+    """dyn = d loss / d ynorm [B*L, ndir*di] -> (dh2, per-direction parameter grads except out_proj, LN accumulator)."""
     Win, zx, conv_w, conv_b, dt_bias, A_log, Dk, norm_w, xconv, dt, y, ws, yn, rstd, Wout = saved
     dip = 2 * di + 2 * N + H
+    C = di + 2 * N
     dzx = torch.empty_like(zx)
     if dstride != dip:
         dzx.view(-1, ndir, dstride)[:, :, dip:] = 0                      # pad columns feed the GEMMs below
-    dy, dnorm_w = ops.gated_norm_bwd(dyn, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx)
-    dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H)
+    # one zero-filled buffer for every accumulated parameter gradient of the block (one fill instead of ten)
+    sizes = [ndir * di, ndir * H, ndir * H, ndir * C * 4, ndir * C, ndir * H, 2 * ln_acc_d]
+    accs = torch.zeros(sum(sizes), dtype=torch.float32, device=zx.device).split(sizes)
+    a_nw, a_dA, a_dD = accs[0].view(ndir, di), accs[1].view(ndir, H), accs[2].view(ndir, H)
+    a_cw, a_cb, a_dtb = accs[3].view(ndir, C, 4), accs[4].view(ndir, C), accs[5].view(ndir, H)
+    dy, dnorm_w = ops.gated_norm_bwd(dyn, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx, acc=a_nw)
+    dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, acc=(a_dA, a_dD))
     dconv_w, dconv_b, ddt_bias = ops.conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias,
-                                              ndir, B, L, di, N, H, dzx)
+                                              ndir, B, L, di, N, H, dzx, acc=(a_cw, a_cb, a_dtb))
     dh2 = ops.gemm(dzx, Win, trans_b=True)                               # dgrad [B*L, d]
     sk = ops.wgrad_splitk(B * L, Win.shape[0], Win.shape[1]) if dzx.dtype == torch.bfloat16 else 1
     dWin = ops.gemm(dzx, h2, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)   # [ndir*dstride, d]
@@ -130,7 +126,7 @@ def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved):
     for r in range(ndir):
         grads.append((dWin[r * dstride: r * dstride + dip], dconv_w[r].reshape(-1, 1, 4), dconv_b[r], ddt_bias[r],
                       dA[r], dD[r], dnorm_w[r]))
-    return dh2, grads
+    return dh2, grads, (accs[6].view(2, ln_acc_d) if ln_acc_d else None)
 
 
 class _MixerFn(torch.autograd.Function):
@@ -176,10 +172,10 @@ class _MixerFn(torch.autograd.Function):
         dyn = ops.gemm(da, Wout, trans_b=True)                           # [B*L, ndir*di]
         sk = ops.wgrad_splitk(B * L, d, ndir * di) if adt == torch.bfloat16 else 1
         dWout = ops.gemm(da, yn, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)   # [d, ndir*di]
-        dh2, grads = _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved)
+        dh2, grads, ln_acc = _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, d if block else 0)
         if block:
             dres = dout2 if dout2.dtype == xdt else dout2.to(xdt)
-            dx2, dg, db = ops.layernorm_bwd(dh2, x2, ln_w.float(), mean, rstd_ln, dres)
+            dx2, dg, db = ops.layernorm_bwd(dh2, x2, ln_w.float(), mean, rstd_ln, dres, acc=ln_acc)
         else:
             dx2, dg, db = (dh2 if dh2.dtype == xdt else dh2.to(xdt)), None, None
         pg = []

@@ -181,11 +181,13 @@ def layernorm_fwd(x2, gamma, beta, eps, y_dtype):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x2, gamma, mean, rstd, dres):
+def layernorm_bwd(dy, x2, gamma, mean, rstd, dres, acc=None):
+    """acc: optional pre-zeroed fp32 [2, d] accumulator for (dgamma, dbeta)."""
     rows, d = x2.shape
     dx = torch.empty_like(x2)
-    dg = torch.zeros(d, dtype=torch.float32, device=x2.device)
-    db = torch.zeros(d, dtype=torch.float32, device=x2.device)
+    if acc is None:
+        acc = torch.zeros(2, d, dtype=torch.float32, device=x2.device)
+    dg, db = acc[0], acc[1]
     lib().call("layernorm_bwd", dy, dtype_code(dy.dtype), x2, dtype_code(x2.dtype), gamma, mean, rstd, dres, rows, d,
                dx, dtype_code(dx.dtype), dg, db, stream())
     return dx, dg, db
@@ -200,10 +202,11 @@ def conv_fwd(zx, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H
     return xconv, dt
 
 
-def conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, dzx):
-    dw = torch.zeros_like(conv_w)
-    db = torch.zeros_like(conv_b)
-    ddtb = torch.zeros_like(dt_bias)
+def conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, dzx, acc=None):
+    """acc: optional pre-zeroed (dconv_w, dconv_b, ddt_bias) accumulators."""
+    if acc is None:
+        acc = (torch.zeros_like(conv_w), torch.zeros_like(conv_b), torch.zeros_like(dt_bias))
+    dw, db, ddtb = acc
     lib().call("conv_bwd", zx, dxc, dtype_code(zx.dtype), zx.stride(0), dstride, dBC, ddt, lengths, conv_w, conv_b,
                dt_bias, ndir, B, L, di, N, H, dzx, dw, db, ddtb, stream())
     return dw, db, ddtb
@@ -224,14 +227,14 @@ def ssd_fwd(xconv, dt, A_log, D, ndir, B, L, di, N, H, impl=None):
     return y, ws
 
 
-def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H, impl=None):
+def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H, impl=None, acc=None):
+    """acc: optional pre-zeroed (dA_log, dD) accumulators."""
     L_ = lib()
     impl = ssd_impl_for(dy.dtype) if impl is None else impl
     dxc = torch.empty_like(dy)
     dBC = _empty((ndir, B * L, 2 * N), dy.dtype, dy)
     ddt = torch.empty_like(dt)
-    dA = torch.zeros_like(A_log)
-    dD = torch.zeros_like(D)
+    dA, dD = acc if acc is not None else (torch.zeros_like(A_log), torch.zeros_like(D))
     ws2 = _empty((L_.raw("ssd_ws_bytes")(ndir, B, L, di, N, H) // 4,), torch.float32, dy)
     L_.call("ssd_bwd", dy, xconv, y, dtype_code(dy.dtype), dt, A_log, D, ws, ndir, B, L, di, N, H, dxc, dBC, ddt,
             dA, dD, ws2, impl, stream())
@@ -246,9 +249,30 @@ def gated_norm_fwd(y, zx, dstride, lengths, norm_w, ndir, B, L, di, eps=1e-5):
     return out, rstd
 
 
-def gated_norm_bwd(dout, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx):
+def gated_norm_bwd(dout, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx, acc=None):
     dy = torch.empty_like(y)
-    dw = torch.zeros_like(norm_w)
+    dw = acc if acc is not None else torch.zeros_like(norm_w)
     lib().call("gated_norm_bwd", dout, y, zx, dtype_code(y.dtype), zx.stride(0), dstride, lengths, norm_w, rstd,
                ndir, B, L, di, dy, dzx, dw, stream())
     return dy, dw
+
+
+def pack_mixer_params(params, ndir, d, di, N, H, dstride, w_dtype, device):
+    """params: per direction (in_proj.w, conv1d.w, conv1d.b, dt_bias, A_log, D, norm.w, out_proj.w), fp32 CUDA.
+    -> Win [ndir*dstride, d], Wout [d, ndir*di] (w_dtype) and the fp32 stacks, with ndir kernel launches."""
+    C = di + 2 * N
+    Win = torch.empty((ndir * dstride, d), dtype=w_dtype, device=device)
+    Wout = torch.empty((d, ndir * di), dtype=w_dtype, device=device)
+    small = torch.empty(ndir * (C * 5 + 3 * H + di), dtype=torch.float32, device=device)
+    conv_w, conv_b, dt_bias, A_log, Dk, norm_w = small.split(
+        [ndir * C * 4, ndir * C, ndir * H, ndir * H, ndir * H, ndir * di])
+    L_ = lib()
+    for r in range(ndir):
+        inw, cw, cb, dtb, al, dk, nw, outw = params[r * 8:(r + 1) * 8]
+        for t in (inw, cw, cb, dtb, al, dk, nw, outw):
+            if t.dtype != torch.float32:
+                raise HnbError("mixer parameters must be fp32 masters")
+        L_.call("pack_mixer_params", inw, outw, cw, cb, dtb, al, dk, nw, r, ndir, d, di, N, H, dstride, Win, Wout,
+                dtype_code(w_dtype), conv_w, conv_b, dt_bias, A_log, Dk, norm_w, stream())
+    return (Win, Wout, conv_w.view(ndir, C, 4), conv_b.view(ndir, C), dt_bias.view(ndir, H), A_log.view(ndir, H),
+            Dk.view(ndir, H), norm_w.view(ndir, di))

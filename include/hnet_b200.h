@@ -173,6 +173,16 @@ int hnb_gated_norm_bwd(const void* dout, const void* y, const void* zxbcdt, int 
                        int ndir, int B, int L, int di, void* dy, void* dzxbcdt, float* dnorm_w,
                        void* stream);
 
+/* per-step packing of ONE direction's mixer parameters (fp32 masters, mamba_ssm layout) into the fused operands:
+ *   in_proj.weight [2di+2N+H, d] -> rows [dir*dstride, ...) of Win [ndir*dstride, d] (pad rows zeroed)
+ *   out_proj.weight [d, di]      -> columns [dir*di, +di) of Wout [d, ndir*di]          (both cast to w_dtype)
+ *   conv1d.weight [C,4], conv1d.bias [C], dt_bias/A_log/D [H], norm.weight [di] -> slot `dir` of their [ndir,...] stacks */
+int hnb_pack_mixer_params(const float* in_w, const float* out_w, const float* conv_w, const float* conv_b,
+                          const float* dt_bias, const float* A_log, const float* Dk, const float* norm_w,
+                          int dir, int ndir, int d, int di, int N, int H, int dstride, void* Win, void* Wout,
+                          int w_dtype, float* conv_w_o, float* conv_b_o, float* dt_bias_o, float* A_log_o,
+                          float* D_o, float* norm_w_o, void* stream);
+
 /* ---- dense projections (in_proj / out_proj / router W_q,W_k / proj_in,out) ---------------- */
 /* C[M,N] = op(A) op(B) (+ bias[N]) (+ R[M,N]) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
  *   transA = 0: A is [M,K] row-major (lda >= K);  1: A is [K,M] row-major (lda >= M)

@@ -1,0 +1,63 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of the path (utterance sharding + gradient all-reduce).
+The model is the CPU oracle (the CUDA kernels need a GPU); what is under test is dcasr_b200.distributed."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from _util import REPO, PKG_DIR
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, REPO); sys.path.insert(0, PKG_DIR); sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _util import fill_weights
+    from dcasr_b200.distributed import GradAllReducer, shard_indices
+    from oracle.encoder_ref import MambaStackRef
+    torch.manual_seed(0)
+    st = MambaStackRef(1, 64)
+    fill_weights(st, 3)
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(6, 20, 64, generator=g)                     # 6 utterances in the global batch
+    idx = shard_indices(6, rank, world)
+    st(X[idx]).pow(2).sum().backward()
+    red = GradAllReducer(st.parameters(), bucket_mb=0.05)       # several buckets
+    red()
+    torch.save({k: p.grad.clone() for k, p in st.named_parameters()}, os.path.join(out, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gradients_equal_mean_of_shards(tmp_path):
+    world, port = 2, 29531
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g0, g1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k                     # all ranks hold the same reduced gradient
+    # single-process truth: mean over ranks of the per-shard gradients
+    from _util import fill_weights
+    from dcasr_b200.distributed import shard_indices
+    from oracle.encoder_ref import MambaStackRef
+    X = torch.randn(6, 20, 64, generator=torch.Generator().manual_seed(5))
+    acc = None
+    for r in range(world):
+        st = MambaStackRef(1, 64)
+        fill_weights(st, 3)
+        st(X[shard_indices(6, r, world)]).pow(2).sum().backward()
+        gr = {k: p.grad for k, p in st.named_parameters()}
+        acc = gr if acc is None else {k: acc[k] + gr[k] for k in gr}
+    for k in g0:
+        assert torch.allclose(g0[k], acc[k] / world, rtol=1e-5, atol=1e-6), k
+
+
+def test_shard_indices_cover_and_balance():
+    from dcasr_b200.distributed import shard_indices
+    for n, w in ((40, 8), (41, 8), (7, 2), (3, 4)):
+        parts = [shard_indices(n, r, w) for r in range(w)]
+        assert len({len(p) for p in parts}) == 1
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(n - n % w))
