@@ -15,6 +15,8 @@
 // the kernel.  TMA for the next chunk is issued as soon as the current chunk's MMAs retire, so loads overlap the
 // output/state epilogues.
 #include "common.cuh"
+#include <cstdlib>
+
 #include "umma.cuh"
 
 namespace hnb {
@@ -104,8 +106,8 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int 
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
   uint8_t* sC = base + OFF_C; uint8_t* sB = base + OFF_B; uint8_t* sX = base + OFF_X; uint8_t* sXw = base + OFF_XW;
   uint8_t* sM = base + OFF_M; uint8_t* sS = base + OFF_S;
   float* tab = reinterpret_cast<float*>(base + OFF_TAB);
@@ -312,13 +314,21 @@ struct BwdParams {
   float* ddt;                    // [ndir*B*L, H]
   float* dA_log; float* dD;      // [ndir, H]
   int ndirB, B, L, H, di, nc;
+  long long* dbg;                // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
+  int mode;                      // debug experiments (0 = normal)
 };
 
-// decay factor L[t, s0+j] (j < 32) of row t (row block I) against column block J <= I
-__device__ __forceinline__ float decay_elem(int t, int I, int J, int s, float cs_t, float e_ref, const float* s_cs,
-                                            const float* s_f) {
-  if (J < I) return e_ref * s_f[I * TQ + s];
-  return (s <= t) ? __expf(cs_t - s_cs[s]) : 0.f;
+// decay factors l[j] = L[t, s0+j] (j < 32) of row t (row block I) against column block J <= I.  The case split is
+// warp-uniform and sits OUTSIDE the element loop.
+__device__ __forceinline__ void decay_row32(float* l, int t, int I, int J, int s0, float cs_t, float e_ref,
+                                            const float* s_cs, const float* s_f) {
+  if (J < I) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) l[j] = e_ref * s_f[I * TQ + s0 + j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) l[j] = (s0 + j <= t) ? __expf(cs_t - s_cs[s0 + j]) : 0.f;
+  }
 }
 
 // ---- 1. dstate ------------------------------------------------------------------------------------
@@ -329,8 +339,8 @@ constexpr int D1_SMEM = D1_OFF_BAR + 64 + 1024;
 __global__ void __launch_bounds__(TC_THREADS, 2)
 ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                          const BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
   uint8_t* sC = base + D1_OFF_C; uint8_t* sdY = base + D1_OFF_DY; uint8_t* sdYs = base + D1_OFF_DYS;
   float* tab = reinterpret_cast<float*>(base + D1_OFF_TAB);
   const float* s_ecs = tab + 3 * TQ;
@@ -423,8 +433,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                      const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
                      const BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
   uint8_t* sC = base + D2_OFF_C; uint8_t* sB = base + D2_OFF_B; uint8_t* sX = base + D2_OFF_X;
   uint8_t* sdY = base + D2_OFF_DY; uint8_t* sS = base + D2_OFF_S; uint8_t* sG = base + D2_OFF_G;
   uint8_t* sK = base + D2_OFF_K;
@@ -476,10 +486,13 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const float Dh = p.Dskip[dir * H + h];
     const int q0 = c * TQ, qv = min(TQ, L - q0);
     const long long row0 = (long long)db * L + q0;
+    long long tk0 = clock64();
     if (tid < TQ) { s_dcs[tid] = 0.f; s_ddtx[tid] = 0.f; }
     if (tid < 2) s_sc[tid] = 0.f;
     build_tables(p.dt + row0 * H + h, H, qv, A, tab);
+    long long tk1 = clock64();
     umma::mbar_wait(bar_load, par);
+    long long tk2 = clock64();
     if (tid == 0) {
       umma::tc_fence_after();
 #pragma unroll
@@ -514,6 +527,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     umma::mbar_wait(bar1, par);
     umma::tc_fence_after();
+    long long tk3 = clock64();
     // ---- epilogue A: K = G o L -> smem;  d cs_t += sum_q W G  +  e^{cs_t} <dY_t, Yo_t>
     {
       const int t = row, I = t >> 5;
@@ -529,10 +543,11 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           umma::tmem_ld32(t_lane + (uint32_t)s0, g);
           umma::tmem_ld32(t_lane + 128u + (uint32_t)s0, r);
           umma::tmem_ld_wait();
+          float l[32];
+          decay_row32(l, t, I, J, s0, cs_t, e_ref, s_cs, s_f);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float l = decay_elem(t, I, J, s0 + j, cs_t, e_ref, s_cs, s_f);
-            g[j] *= l;
+            g[j] *= l[j];
             // the row sums must use K exactly as the tensor core will see it (bf16): the column sums come out of
             // du1 = K^T dY, and the two cancel in the cumulative sum -- any rounding asymmetry would survive
             acc += r[j] * s_dt[s0 + j] * __bfloat162float(__float2bfloat16_rn(g[j]));
@@ -545,6 +560,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sK + ch * HALF + swz(t, 4 * cc + k)) = pack8(g + 8 * k);
       }
       float yo[32], yd = 0.f;
+      {
       umma::tmem_ld32(t_lane + 256u + 32u * ch, yo);
       umma::tmem_ld_wait();
 #pragma unroll
@@ -554,9 +570,11 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
         for (int e = 0; e < 8; ++e) yd += d[e] * yo[8 * k + e];
       }
+      }
       atomicAdd(&s_dcs[t], acc + s_ecs[t] * yd);
     }
     umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
+    long long tk4 = clock64();
     if (tid == 0) {
       umma::tc_fence_after();
 #pragma unroll
@@ -573,6 +591,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     umma::mbar_wait(bar2, par);
     umma::tc_fence_after();
+    long long tk5 = clock64();
     // ---- epilogue B (thread = row q): dx, and the remaining d cs terms
     {
       const int q = row;
@@ -631,6 +650,11 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (tid == 0) atomicAdd(p.dD + dir * H + h, s_sc[1]);
     }
     umma::tc_fence_before(); __syncthreads();
+    if (p.dbg && blockIdx.x == 0 && tid == 0) {
+      const long long tk6 = clock64();
+      p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
+      p.dbg[4] += tk5 - tk4; p.dbg[5] += tk6 - tk5; p.dbg[6] += 1;
+    }
   }
   umma::tc_fence_before(); __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
@@ -646,8 +670,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                       const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
                       const BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
   uint8_t* sC = base + D3_OFF_C; uint8_t* sB = base + D3_OFF_B; uint8_t* sX = base + D3_OFF_X;
   uint8_t* sdY = base + D3_OFF_DY; uint8_t* sXw = base + D3_OFF_XW; uint8_t* sdYs = base + D3_OFF_DYS;
   uint8_t* sS = base + D3_OFF_S; uint8_t* sG = base + D3_OFF_G; uint8_t* sW = base + D3_OFF_W;
@@ -734,8 +758,10 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           if (J <= I) {
             umma::tmem_ld32(t_lane + (uint32_t)s0, r);
             umma::tmem_ld_wait();
+            float l[32];
+            decay_row32(l, t, I, J, s0, cs_t, e_ref, s_cs, s_f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] *= decay_elem(t, I, J, s0 + j, cs_t, e_ref, s_cs, s_f) * s_dt[s0 + j];
+            for (int j = 0; j < 32; ++j) r[j] *= l[j] * s_dt[s0 + j];
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0.f;
@@ -863,6 +889,10 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.gstates = (__nv_bfloat16*)ws2; p.dxc = (__nv_bfloat16*)dxc;
   p.dBC = (__nv_bfloat16*)dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = nc;
+  p.dbg = nullptr;
+  p.mode = getenv("HNB_SSD_MODE") ? atoi(getenv("HNB_SSD_MODE")) : 0;
+  const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
+  if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, st); }
   const int sms = sm_count();
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dstate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D1_SMEM));
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
@@ -876,5 +906,14 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   items = ndir * B * nc;
   ssd_bwd_dbc_tc_kernel<<<items < sms ? items : sms, TC_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dbc_tc");
+  if (debug) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.dbg, 64, cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    const double n = h[6] > 0 ? (double)h[6] : 1.0;
+    fprintf(stderr, "[ssd_bwd_dx CTA0] items %lld | cycles/item: tables %.0f, wait load %.0f, mma1 wait(+dot) %.0f, epiA %.0f, "
+            "mma2 wait %.0f, epiB+cumsum %.0f\n", h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n);
+  }
   return HNB_OK;
 }

@@ -1,0 +1,14 @@
+import sys
+sys.path.insert(0, "tests"); import _util
+import torch, torch.nn.functional as F
+from dcasr_b200 import ops
+DEV = "cuda"; torch.manual_seed(0)
+ndir, B, L, H = 2, 40, 398, 12; di, N = 64 * H, 128
+xconv = (torch.randn(ndir, B * L, di + 2 * N, device=DEV) * 0.8).to(torch.bfloat16)
+dt = F.softplus(torch.randn(ndir, B * L, H, device=DEV) - 2.0)
+A_log = torch.log(torch.rand(ndir, H, device=DEV) * 15 + 1); Dk = torch.randn(ndir, H, device=DEV)
+dy = (torch.randn(ndir, B * L, di, device=DEV) * 0.5).to(torch.bfloat16)
+y, ws = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1)
+for _ in range(3):
+    ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, impl=1)
+torch.cuda.synchronize()
