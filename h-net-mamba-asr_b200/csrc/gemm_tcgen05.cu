@@ -1,13 +1,15 @@
-// bf16 GEMM on tcgen05 tensor cores: TMA (SWIZZLE_128B) -> 3-stage smem ring -> tcgen05.mma (128x128x16,
-// fp32 accumulator in TMEM) -> tcgen05.ld epilogue with fused bias / residual / dtype cast / split-K atomics.
+// bf16 GEMM on tcgen05 tensor cores: TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (128 x 256 x 16,
+// fp32 accumulators in TMEM) -> tcgen05.ld epilogue with fused bias / residual / dtype cast / split-K atomics.
 // Serves the in/out projections of the mixer (both directions fused into one GEMM each), the router
 // W_q|W_k projection, proj_in/proj_out, and every dgrad / wgrad of those.
 //
 //   C[M,N] = A(M,K) . B(N,K)^T      A: K-major [M,K] or MN-major [K,M];  B: K-major [N,K] or MN-major [K,N]
 //
-// One 128x128 output tile per CTA, 128 threads, 2 CTAs per SM (96 KB smem, 128 TMEM columns each) so that one
-// CTA's epilogue overlaps the other's main loop.  Warp 0 lane 0 drives TMA, warp 1 lane 0 issues MMAs, all four
-// warps drain TMEM (warp w owns TMEM lanes [32w, 32w+32)).
+// Persistent and warp-specialised: one CTA per SM walks 128 x 256 (or 128 x 128) output tiles; warp 0 drives TMA
+// through a 4-6 stage smem ring, warp 1 issues the MMAs into one of two TMEM accumulators, eight epilogue warps
+// drain the other accumulator (TMEM lane quarter = warp % 4), so the epilogue of tile i overlaps the main loop of
+// tile i+1.  The projections of this model have K = 384..512 (6-8 k-blocks per tile): without that overlap the
+// prologue/epilogue, not the tensor pipe, sets the pace.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -48,13 +50,22 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int TILE_BYTES = 128 * BK * 2;                    // 16 KB per operand per stage
-constexpr int GEMM_SMEM = STAGES * 2 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64;
+constexpr int A_STAGE = BM * BK * 2;                          // 16 KB
+constexpr int GEMM_THREADS = 64 + 256;                        // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr int EPI_WARPS = 8;
+
+constexpr int EPI_STAGE_FLOATS = 32 * 33;                     // per-warp [32 rows][33] fp32 transpose buffer
+template <int BN> struct GemmCfg {
+  static constexpr int B_STAGE = BN * BK * 2;                 // 16 / 32 KB
+  static constexpr int STAGES = BN == 256 ? 3 : 4;
+  static constexpr int RING = STAGES * (A_STAGE + B_STAGE);
+  static constexpr int SMEM = RING + EPI_WARPS * EPI_STAGE_FLOATS * 4 + 256 + 1024;
+};
 
 struct GemmParams {
   int M, N, K;
-  int kblocks_per_split;
+  int tiles_m, tiles_n, splitk, kblocks_per_split, total_kb;
   const float* bias;
   const void* R;
   long long ldr;
@@ -64,155 +75,206 @@ struct GemmParams {
   int atomic;
 };
 
-template <int TA, int TB>
-__global__ void __launch_bounds__(128, 2)
+// Persistent, warp-specialised: each CTA walks work items (k-split, n-tile, m-tile) with a static stride.
+//   TMA warp  -> smem ring (full/empty mbarriers)
+//   MMA warp  -> tcgen05.mma 128 x BN x 16 into one of TWO TMEM accumulators (tmem_full/tmem_empty mbarriers)
+//   8 epilogue warps drain accumulator i while the MMA warp already fills accumulator i^1.
+template <int TA, int TB, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES, B_STAGE = Cfg::B_STAGE;
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * TILE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * STAGES * TILE_BYTES);
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  float* sEpi = reinterpret_cast<float*>(smem + Cfg::RING);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING + EPI_WARPS * EPI_STAGE_FLOATS * 4);
   uint64_t* empty = full + STAGES;
-  uint64_t* accum_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* tmem_full = empty + STAGES;                       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int total_kb = (p.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * p.kblocks_per_split;
-  const int kb1 = min(kb0 + p.kblocks_per_split, total_kb);
-  const int nkb = kb1 - kb0;
+  const int n_items = p.tiles_m * p.tiles_n * p.splitk;
 
   if (warp == 0 && lane == 0) {
     umma::prefetch_tmap(&tmA);
     umma::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
-    umma::mbar_init(accum_full, 1);
+    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], EPI_WARPS); }
     umma::fence_barrier_init();
   }
-  if (warp == 1) umma::tmem_alloc(tmem_slot, BN);
+  if (warp == 1) umma::tmem_alloc(tmem_slot, 2 * BN);
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
-  if (nkb > 0) {
-    if (warp == 0 && lane == 0) {
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
+    const int tm = item % p.tiles_m;
+    const int r = item / p.tiles_m;
+    const int tn = r % p.tiles_n, ks = r / p.tiles_n;
+    m0 = tm * BM; n0 = tn * BN;
+    kb0 = ks * p.kblocks_per_split;
+    nkb = min(p.kblocks_per_split, p.total_kb - kb0);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
       // ---------------- TMA producer ----------------
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        umma::mbar_wait(&empty[s], ph ^ 1);
-        umma::mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-        const int k0 = (kb0 + i) * BK;
-        uint8_t* a = sA + s * TILE_BYTES;
-        uint8_t* b = sB + s * TILE_BYTES;
-        if (TA == 0) {
-          umma::tma_load_2d(a, &tmA, &full[s], k0, m0);                    // box {64 k, 128 m}
-        } else {
-          umma::tma_load_2d(a, &tmA, &full[s], m0, k0);                    // box {64 m, 64 k} x 2
-          umma::tma_load_2d(a + TILE_BYTES / 2, &tmA, &full[s], m0 + 64, k0);
-        }
-        if (TB == 0) {
-          umma::tma_load_2d(b, &tmB, &full[s], k0, n0);
-        } else {
-          umma::tma_load_2d(b, &tmB, &full[s], n0, k0);
-          umma::tma_load_2d(b + TILE_BYTES / 2, &tmB, &full[s], n0 + 64, k0);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        decode(item, m0, n0, kb0, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          umma::mbar_wait(&empty[s], ph ^ 1);
+          umma::mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
+          const int k0 = (kb0 + i) * BK;
+          uint8_t* a = sA + s * A_STAGE;
+          uint8_t* b = sB + s * B_STAGE;
+          if (TA == 0) {
+            umma::tma_load_2d(a, &tmA, &full[s], k0, m0);                  // box {64 k, 128 m}
+          } else {
+            umma::tma_load_2d(a, &tmA, &full[s], m0, k0);                  // boxes {64 m, 64 k}
+            umma::tma_load_2d(a + 8192, &tmA, &full[s], m0 + 64, k0);
+          }
+          if (TB == 0) {
+            umma::tma_load_2d(b, &tmB, &full[s], k0, n0);                  // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) umma::tma_load_2d(b + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);
+          }
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma::make_idesc_bf16(BM, BN, TA, TB);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        umma::mbar_wait(&full[s], ph);
+      uint32_t it = 0, li = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+        int m0, n0, kb0, nkb;
+        decode(item, m0, n0, kb0, nkb);
+        const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+        umma::mbar_wait(&tmem_empty[acc], aph ^ 1);                        // the epilogue has drained this accumulator
         umma::tc_fence_after();
-        const uint32_t a = umma::smem_u32(sA + s * TILE_BYTES);
-        const uint32_t b = umma::smem_u32(sB + s * TILE_BYTES);
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          umma::mbar_wait(&full[s], ph);
+          umma::tc_fence_after();
+          const uint32_t a = umma::smem_u32(sA + s * A_STAGE);
+          const uint32_t b = umma::smem_u32(sB + s * B_STAGE);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = (TA == 0) ? umma::make_smem_desc(a + k * 32, 16, 1024)
-                                        : umma::make_smem_desc(a + k * 2048, TILE_BYTES / 2, 1024);
-          const uint64_t db = (TB == 0) ? umma::make_smem_desc(b + k * 32, 16, 1024)
-                                        : umma::make_smem_desc(b + k * 2048, TILE_BYTES / 2, 1024);
-          umma::mma_bf16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = (TA == 0) ? umma::make_smem_desc(a + k * 32, 16, 1024)
+                                          : umma::make_smem_desc(a + k * 2048, 8192, 1024);
+            const uint64_t db = (TB == 0) ? umma::make_smem_desc(b + k * 32, 16, 1024)
+                                          : umma::make_smem_desc(b + k * 2048, 8192, 1024);
+            umma::mma_bf16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma::mma_commit(&empty[s]);                                     // frees the smem slot when the MMAs retire
         }
-        umma::mma_commit(&empty[s]);                                       // frees the smem slot when the MMAs retire
+        umma::mma_commit(&tmem_full[acc]);
       }
-      umma::mma_commit(accum_full);
     }
-  }
-  __syncwarp();
-
-  // ---------------- epilogue: TMEM -> registers -> global ----------------
-  if (nkb > 0) {
-    umma::mbar_wait(accum_full, 0);
-    umma::tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    const bool row_ok = row < p.M;
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    const int ew = warp - 2;                      // 0..7
+    const int lq = warp & 3;                      // TMEM lane quarter this warp may read
+    const int chalf = ew >> 2;                    // column half of the tile
+    uint32_t li = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+      int m0, n0, kb0, nkb;
+      decode(item, m0, n0, kb0, nkb);
+      const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+      umma::mbar_wait(&tmem_full[acc], aph);
+      umma::tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16);
+      float* st = sEpi + ew * EPI_STAGE_FLOATS;
+      const int rsub = lane >> 2, cgrp = lane & 3;          // after the transpose: lane -> (row within 8, 8-column group)
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      umma::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      umma::tmem_ld_wait();
-      const int col0 = n0 + c0;
-      if (row_ok && col0 < p.N) {
-        const int ncols = min(32, p.N - col0);
-        if (p.bias) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+        const int col0 = n0 + c0;
+        if (col0 >= p.N) break;                             // warp-uniform
+        float v[32];
+        umma::tmem_ld32(t_addr + (uint32_t)c0, v);
+        umma::tmem_ld_wait();
+        // TMEM hands each lane one ROW; a direct store would touch 32 different lines per instruction.  Transpose
+        // through a padded per-warp buffer so that 4 lanes cover 32 consecutive columns of one row.
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += p.bias[col0 + j];
-        }
-        if (p.atomic) {
-          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int col = col0 + cgrp * 8;
+        const bool full8 = col + 8 <= p.N;
+        float bias8[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(c + j, v[j]);
-        } else if (p.c_is_f32) {
-          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-          const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
-          const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0) &&
-                           (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0);
-          if (vec) {
+        for (int e = 0; e < 8; ++e) bias8[e] = (p.bias && col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (r) { const float4 t = *reinterpret_cast<const float4*>(r + j); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              *reinterpret_cast<float4*>(c + j) = o;
-            }
-          } else {
+        for (int i = 0; i < 4; ++i) {
+          const int rl = i * 8 + rsub;
+          const int row = m0 + lq * 32 + rl;
+          float o[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = v[j] + (r ? r[j] : 0.f);
-          }
-        } else {
-          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
-          const __nv_bfloat16* r = p.R ? reinterpret_cast<const __nv_bfloat16*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
-          const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0) &&
-                           (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0);
-          if (vec) {
+          for (int e = 0; e < 8; ++e) o[e] = st[rl * 33 + cgrp * 8 + e] + bias8[e];
+          if (row < p.M && col < p.N) {
+            if (p.atomic) {
+              float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+              if (full8 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+              } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = v[j + e];
-              if (r) {
-                float t[8];
-                ldv<__nv_bfloat16, 8>(r + j, t);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] += t[e];
+                for (int e = 0; e < 8; ++e) if (col + e < p.N) atomicAdd(c + e, o[e]);
               }
-              stv<__nv_bfloat16, 8>(c + j, o);
-            }
-          } else {
+            } else if (p.c_is_f32) {
+              float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+              const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col : nullptr;
+              if (full8 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+                if (r) {
+                  float t[8];
+                  ldv<float, 8>(r, t);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) c[j] = __float2bfloat16_rn(v[j] + (r ? __bfloat162float(r[j]) : 0.f));
+                  for (int e = 0; e < 8; ++e) o[e] += t[e];
+                }
+                *reinterpret_cast<float4*>(c) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (col + e < p.N) c[e] = o[e] + (r ? r[e] : 0.f);
+              }
+            } else {
+              __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col;
+              const __nv_bfloat16* r = p.R ? reinterpret_cast<const __nv_bfloat16*>(p.R) + (long long)row * p.ldr + col : nullptr;
+              if (full8 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+                if (r) {
+                  float t[8];
+                  ldv<__nv_bfloat16, 8>(r, t);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] += t[e];
+                }
+                stv<__nv_bfloat16, 8>(c, o);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (col + e < p.N) c[e] = __float2bfloat16_rn(o[e] + (r ? __bfloat162float(r[e]) : 0.f));
+              }
+            }
           }
         }
+        __syncwarp();
       }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tmem_empty[acc]);
     }
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem_d, BN);
+  if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // naive reference for the self test
@@ -257,6 +319,9 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   HNB_CHECK_ARG(c_dtype == HNB_F32 || c_dtype == HNB_BF16, "gemm_bf16: bad output dtype");
   if (splitk < 1) splitk = 1;
   HNB_CHECK_ARG(splitk == 1 || (c_dtype == HNB_F32 && !bias && !R), "gemm_bf16: split-K needs fp32 C and no bias/residual");
+  // tile width: 256 columns unless that would waste more than ~10 % of the MMA work on the ragged last tile
+  const int waste256 = cdiv(N, 256) * 256 - N;
+  const int BN = (N >= 256 && waste256 * 10 <= N) ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc;
   {
@@ -266,7 +331,7 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
     else         { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
     st[0] = (uint64_t)lda * 2;
     if ((rc = make_tmap_bf16(&tmA, A, 2, dims, st, box))) return rc;
-    if (!transB) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = BN; }
+    if (!transB) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)BN; }
     else         { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
     st[0] = (uint64_t)ldb * 2;
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, st, box))) return rc;
@@ -275,22 +340,30 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   if (splitk > total_kb) splitk = total_kb;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
+  p.total_kb = total_kb;
   p.kblocks_per_split = cdiv(total_kb, splitk);
-  splitk = cdiv(total_kb, p.kblocks_per_split);
+  p.splitk = cdiv(total_kb, p.kblocks_per_split);
+  p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
   p.bias = bias; p.R = R; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.c_is_f32 = (c_dtype == HNB_F32);
-  p.atomic = splitk > 1;
-  dim3 grid(cdiv(N, BN), cdiv(M, BM), splitk);
+  p.atomic = p.splitk > 1;
+  const int n_items = p.tiles_m * p.tiles_n * p.splitk;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int grid = n_items < sms ? n_items : sms;
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(TA, TB)                                                                                              \
-  do {                                                                                                              \
-    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
-    gemm_bf16_kernel<TA, TB><<<grid, 128, GEMM_SMEM, st>>>(tmA, tmB, p);                                            \
+#define LAUNCH(TA, TB, BN_)                                                                                          \
+  do {                                                                                                               \
+    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_kernel<TA, TB, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       GemmCfg<BN_>::SMEM));                                                         \
+    gemm_bf16_kernel<TA, TB, BN_><<<grid, GEMM_THREADS, GemmCfg<BN_>::SMEM, st>>>(tmA, tmB, p);                       \
   } while (0)
-  if (!transA && !transB) LAUNCH(0, 0);
-  else if (!transA && transB) LAUNCH(0, 1);
-  else if (transA && !transB) LAUNCH(1, 0);
-  else LAUNCH(1, 1);
+#define LAUNCH_BN(TA, TB) do { if (BN == 256) LAUNCH(TA, TB, 256); else LAUNCH(TA, TB, 128); } while (0)
+  if (!transA && !transB) LAUNCH_BN(0, 0);
+  else if (!transA && transB) LAUNCH_BN(0, 1);
+  else if (transA && !transB) LAUNCH_BN(1, 0);
+  else LAUNCH_BN(1, 1);
+#undef LAUNCH_BN
 #undef LAUNCH
   HNB_LAUNCH_CHECK("gemm_bf16");
   return HNB_OK;
