@@ -10,13 +10,23 @@
 //     dS   = B^T (w o X)                  128x64x128    (TMEM cols 256..319)   B^T: MN-major A operand
 //     y    = Yd + e^{cs} Yo + D x         epilogue 2    -> global (bf16)
 //     S    = e^{cs_last} S + dS           epilogue 3    -> registers, smem (bf16), global (bf16, for the backward)
-// The decay matrix L[t,s] = exp(cs_t - cs_s) is factored per 32-row block through a reference point (both factors
-// <= 1, so no overflow) and only the diagonal 32x32 blocks pay one exp per element: MUFU would otherwise pace
-// the kernel.  TMA for the next chunk is issued as soon as the current chunk's MMAs retire, so loads overlap the
-// output/state epilogues.
-#include "common.cuh"
+//
+// Backward (three kernels):
+//   1. dstate : per (row, head), chunks in REVERSE order:  Gst[c] = d loss / d (state leaving chunk c)
+//   2. dx     : per (row, chunk, head): du = K^T dY + e_q B Gst  ->  dx, ddt, dA_log, dD
+//   3. dbc    : per (row, chunk), heads accumulated in TMEM:   dC += W B + (e^{cs} dY) S_in^T,
+//                                                              dB += W^T C + (w X) Gst^T
+// with  K = (C B^T) o L,  W = (dY X^T) o L o dt,  L[t,q] = e^{cs_t - cs_q} (q <= t).
+//
+// These kernels are paced by the CUDA-core epilogues between the MMAs (decay matrix, casts, row dots), not by the
+// tensor pipe, so: 8-16 warps per CTA (warp w reads TMEM lane quarter w%4, column group w/4; the last warp issues TMA
+// and MMAs while the others build tables), every table in the .shared address space, the decay matrix L factored per 32-row block through a reference
+// point (both factors <= 1: no overflow; only the diagonal 32x32 blocks pay one exp per element), the per-chunk
+// tables of the NEXT step built while the current step's MMAs run, and TMA for the next step issued as soon as the
+// current operands are consumed.
 #include <cstdlib>
 
+#include "common.cuh"
 #include "umma.cuh"
 
 namespace hnb {
@@ -25,29 +35,12 @@ namespace {
 constexpr int TQ = 128;                 // chunk length
 constexpr int TP = 64;                  // head dim
 constexpr int TN = 128;                 // state dim
-constexpr int TC_THREADS = 256;
+constexpr int FWD_THREADS = 512;          // forward: 16 warps
+constexpr int BWD_THREADS = 512;          // dx / dbc
 constexpr int HALF = TQ * 128;          // bytes of one [128 rows x 128 B] swizzled block (16 KB)
-
-// shared-memory map (offsets from the 1024-aligned base)
-constexpr int OFF_C = 0;                // 2 blocks: n in [0,64) | [64,128)
-constexpr int OFF_B = OFF_C + 2 * HALF;
-constexpr int OFF_X = OFF_B + 2 * HALF; // 2 buffers (chunk parity)
-constexpr int OFF_XW = OFF_X + 2 * HALF;
-constexpr int OFF_M = OFF_XW + HALF;    // 2 blocks: s in [0,64) | [64,128)
-constexpr int OFF_S = OFF_M + 2 * HALF;
-constexpr int OFF_TAB = OFF_S + HALF;   // float tables (see build_tables)
-constexpr int TAB_FLOATS = 9 * TQ + 8 + 2 * TQ + 8;   // cs, dt, w, ecs, eq | f[4][128] | warp totals | dcs, ddtx, scalars
-constexpr int OFF_BAR = OFF_TAB + TAB_FLOATS * 4;
-constexpr int FWD_SMEM = OFF_BAR + 64 + 1024;
-
-struct FwdParams {
-  const float* dt;        // [ndir*B*L, H]
-  const float* A_log;     // [ndir, H]
-  const float* Dskip;     // [ndir, H]
-  __nv_bfloat16* y;       // [ndir*B*L, di]
-  __nv_bfloat16* states;  // [ndir*B, H, nc, 128(n), 64(p)]  state ENTERING each chunk
-  int ndirB, B, L, H, di, nc;
-};
+constexpr int TAB_FLOATS = 9 * TQ + 8;  // cs, dt, w, ecs, eq [128 each] | f[4][128] | warp totals
+constexpr int TAB_BYTES = TAB_FLOATS * 4;
+constexpr int EXTRA_FLOATS = 2 * TQ + 8;
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk16) {          // byte offset inside a [rows x 128 B] SW128 block
   return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
@@ -65,16 +58,21 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* v) {
   for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 
-// Per-chunk tables (all TC_THREADS threads call; ends with a block barrier):
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Per-chunk tables.  Called by the first `nt` threads of the CTA (every warp but the MMA-issuing one, so that the
+// tables of the next step are built WHILE the issuer feeds the tensor core); synchronises them on named barrier 1.
 //   cs[t]  inclusive cumsum of dt*A      dt[t]  (0 beyond the row's length)
 //   w[t]   e^{cs_last - cs_t} dt_t       ecs[t] e^{cs_t}        eq[t] e^{cs_last - cs_t}
 //   f[I][s] = e^{cs_{32I-1} - cs_s}  for s < 32 I  (block factor of the decay matrix), else 0
-__device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int H, int qv, float A, float* tab) {
+__device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int H, int qv, float A, float* tab, int nt) {
   float* s_cs = tab; float* s_dt = tab + TQ; float* s_w = tab + 2 * TQ; float* s_ecs = tab + 3 * TQ;
   float* s_eq = tab + 4 * TQ; float* s_f = tab + 5 * TQ; float* s_tot = tab + 9 * TQ;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < TQ) {
-    const float d = (tid < qv) ? dtp[(long long)tid * H] : 0.f;
+    const float d = (tid < qv) ? __ldg(dtp + (long long)tid * H) : 0.f;
     s_dt[tid] = d;
     float v = d * A;
 #pragma unroll
@@ -82,13 +80,13 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int 
     s_cs[tid] = v;
     if (lane == 31) s_tot[tid >> 5] = v;
   }
-  __syncthreads();
+  named_sync(1, nt);
   if (tid < TQ) {
     float add = 0.f;
     for (int w = 0; w < (tid >> 5); ++w) add += s_tot[w];
     s_cs[tid] += add;
   }
-  __syncthreads();
+  named_sync(1, nt);
   const float cs_last = s_cs[TQ - 1];
   if (tid < TQ) {
     const float cs = s_cs[tid];
@@ -97,30 +95,71 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int 
     s_w[tid] = eq * s_dt[tid];
     s_ecs[tid] = __expf(cs);
   }
-  for (int i = tid; i < 4 * TQ; i += TC_THREADS) {
+  for (int i = tid; i < 4 * TQ; i += nt) {
     const int I = i >> 7, s = i & (TQ - 1);
     s_f[i] = (I > 0 && s < 32 * I) ? __expf(s_cs[32 * I - 1] - s_cs[s]) : 0.f;
   }
-  __syncthreads();
+  named_sync(1, nt);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// decay factors l[j] = L[t, s0+j] (j < 32) of row t (row block I) against column block J <= I.  The case split is
+// warp-uniform and sits OUTSIDE the element loop.
+__device__ __forceinline__ void decay_row32(float* l, int t, int I, int J, int s0, const float* tab) {
+  const float* s_cs = tab; const float* s_f = tab + 5 * TQ;
+  const float cs_t = s_cs[t];
+  if (J < I) {
+    const float e_ref = __expf(cs_t - s_cs[32 * I - 1]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) l[j] = e_ref * s_f[I * TQ + s0 + j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) l[j] = (s0 + j <= t) ? __expf(cs_t - s_cs[s0 + j]) : 0.f;
+  }
+}
+
+// ===================================================================================================
+// forward
+// ===================================================================================================
+constexpr int OFF_C = 0;                // 2 blocks: n in [0,64) | [64,128)
+constexpr int OFF_B = OFF_C + 2 * HALF;
+constexpr int OFF_X = OFF_B + 2 * HALF; // 2 buffers (chunk parity)
+constexpr int OFF_XW = OFF_X + 2 * HALF;
+constexpr int OFF_M = OFF_XW + HALF;    // 2 blocks: s in [0,64) | [64,128)
+constexpr int OFF_S = OFF_M + 2 * HALF;
+constexpr int OFF_TAB = OFF_S + HALF;   // two table buffers (current / next chunk)
+constexpr int OFF_BAR = OFF_TAB + 2 * TAB_BYTES;
+constexpr int FWD_SMEM = OFF_BAR + 64 + 1024;
+
+struct FwdParams {
+  const float* dt;        // [ndir*B*L, H]
+  const float* A_log;     // [ndir, H]
+  const float* Dskip;     // [ndir, H]
+  __nv_bfloat16* y;       // [ndir*B*L, di]
+  __nv_bfloat16* states;  // [ndir*B, H, nc, 128(n), 64(p)]  state ENTERING each chunk
+  int ndirB, B, L, H, di, nc;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
+  constexpr int NCG = NT / 128;           // column groups: warp w -> TMEM lane quarter w%4, column group w/4
+  constexpr int NB = 4 / NCG;             // 32-column blocks (of 128) and 16-column blocks (of 64) per thread
+  constexpr int NTAB = NT - 32;           // table builders: every warp but the last, which issues the MMAs
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
   uint8_t* sC = base + OFF_C; uint8_t* sB = base + OFF_B; uint8_t* sX = base + OFF_X; uint8_t* sXw = base + OFF_XW;
   uint8_t* sM = base + OFF_M; uint8_t* sS = base + OFF_S;
-  float* tab = reinterpret_cast<float*>(base + OFF_TAB);
-  const float* s_cs = tab; const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
-  const float* s_f = tab + 5 * TQ;
+  float* tabs = reinterpret_cast<float*>(base + OFF_TAB);
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + OFF_BAR);
   uint64_t* bar_g = bar_load + 1;
   uint64_t* bar_y = bar_load + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lq = warp & 3, ch = warp >> 2;          // TMEM lane quarter, column half
+  const int lq = warp & 3, cg = warp >> 2;
   const int row = lq * 32 + lane;
+  const bool issuer = tid == NTAB;                   // lane 0 of the last warp: TMA + MMA issue
+  const bool tabber = tid < NTAB;
 
   if (tid == 0) {
     umma::prefetch_tmap(&tmX);
@@ -140,7 +179,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   constexpr uint32_t idesc_y = umma::make_idesc_bf16(128, 64, 0, 1);
   constexpr uint32_t idesc_s = umma::make_idesc_bf16(128, 64, 1, 1);
 
-  auto issue_load = [&](int item, int c, int buf) {                 // thread 0 only
+  auto issue_load = [&](int item, int c, int buf) {                 // issuer only
     const int db = item / H, h = item % H;
     umma::mbar_expect_tx(bar_load, 5 * HALF);
     umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
@@ -149,32 +188,43 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
     umma::tma_load_3d(sB + HALF, &tmX, bar_load, di + 64, c * TQ, db);
     umma::tma_load_3d(sX + buf * HALF, &tmX, bar_load, h * TP, c * TQ, db);
   };
+  auto tables_for = [&](int item, int c, float* tab) {              // tabber threads
+    const int db = item / H, h = item % H, dir = db / p.B;
+    const int q0 = c * TQ;
+    build_tables(p.dt + ((long long)db * L + q0) * H + h, H, min(TQ, L - q0), -__expf(p.A_log[dir * H + h]), tab, NTAB);
+  };
 
   uint32_t seq = 0;                                                   // (item, chunk) sequence number of this CTA
-  if (blockIdx.x < n_items && tid == 0) issue_load(blockIdx.x, 0, 0);
+  if (blockIdx.x < n_items) {
+    if (issuer) issue_load(blockIdx.x, 0, 0);
+    if (tabber) tables_for(blockIdx.x, 0, tabs);
+  }
+  __syncthreads();
 
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int db = it / H, h = it % H, dir = db / p.B;
-    const float A = -__expf(p.A_log[dir * H + h]);
     const float Dh = p.Dskip[dir * H + h];
-    float Sreg[32];
+    float Sreg[16 * NB];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) Sreg[j] = 0.f;
-    for (int i = tid; i < HALF / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sS)[i] = make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < 16 * NB; ++j) Sreg[j] = 0.f;
+    for (int i = tid; i < HALF / 16; i += NT) reinterpret_cast<uint4*>(sS)[i] = make_uint4(0, 0, 0, 0);
 
     for (int c = 0; c < nc; ++c, ++seq) {
       const int buf = seq & 1;
       const uint32_t par = seq & 1;
+      const float* tab = tabs + buf * TAB_FLOATS;
+      const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
       const int q0 = c * TQ, qv = min(TQ, L - q0);
       const long long row0 = (long long)db * L + q0;
-      build_tables(p.dt + row0 * H + h, H, qv, A, tab);
-      {   // state entering this chunk, kept for the backward (thread = state row n, 32 of the 64 columns)
-        __nv_bfloat16* sg = p.states + ((((long long)db * H + h) * nc + c) * TN + row) * TP + 32 * ch;
+      int nit = it, ncn = c + 1;                                       // the step after this one
+      if (ncn == nc) { nit = it + gridDim.x; ncn = 0; }
+      {   // state entering this chunk, kept for the backward (thread = state row n, 64/NCG of the 64 columns)
+        __nv_bfloat16* sg = p.states + ((((long long)db * H + h) * nc + c) * TN + row) * TP + 16 * NB * cg;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sg + 8 * k) = pack8(Sreg + 8 * k);
+        for (int k = 0; k < 2 * NB; ++k) *reinterpret_cast<uint4*>(sg + 8 * k) = pack8(Sreg + 8 * k);
       }
       umma::mbar_wait(bar_load, par);
-      if (tid == 0) {
+      if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {
@@ -185,7 +235,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
         umma::mma_commit(bar_g);
       }
       // Xw = w_s * X (same swizzled positions: the swizzle permutes 16-byte chunks inside a row only)
-      for (int i = tid; i < TQ * 8; i += TC_THREADS) {
+      for (int i = tid; i < TQ * 8; i += NT) {
         const float w = s_w[i >> 3];
         float v[8];
         unpack8(reinterpret_cast<const uint4*>(sX + buf * HALF)[i], v);
@@ -196,37 +246,29 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       umma::mbar_wait(bar_g, par);
       umma::tc_fence_after();
       // ---- epilogue 1: M[t,s] = G[t,s] e^{cs_t - cs_s} dt_s (s <= t), bf16, K-major swizzled
-      {
-        const int t = row, I = t >> 5;
-        const float cs_t = s_cs[t];
-        const float e_ref = (I > 0) ? __expf(cs_t - s_cs[32 * I - 1]) : 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int J = 2 * ch + cc, s0 = 32 * J;
-          float g[32];
-          if (J <= I) {
-            umma::tmem_ld32(t_lane + (uint32_t)s0, g);
-            umma::tmem_ld_wait();
-            if (J < I) {
+      for (int bb = 0; bb < NB; ++bb) {
+        const int t = row, I = t >> 5, J = NB * cg + bb, s0 = 32 * J;
+        float g[32];
+        if (J <= I) {
+          umma::tmem_ld32(t_lane + (uint32_t)s0, g);
+          umma::tmem_ld_wait();
+          float l[32];
+          decay_row32(l, t, I, J, s0, tab);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) g[j] *= e_ref * s_f[I * TQ + s0 + j] * s_dt[s0 + j];
-            } else {
+          for (int j = 0; j < 32; ++j) g[j] *= l[j] * s_dt[s0 + j];
+        } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                g[j] = (s0 + j <= t) ? g[j] * __expf(cs_t - s_cs[s0 + j]) * s_dt[s0 + j] : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) g[j] = 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sM + ch * HALF + swz(t, 4 * cc + k)) = pack8(g + 8 * k);
+          for (int j = 0; j < 32; ++j) g[j] = 0.f;
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(sM + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(g + 8 * k);
       }
       umma::fence_async_smem();
       umma::tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {                               // Yd = M X
@@ -247,27 +289,25 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
         }
         umma::mma_commit(bar_y);
       }
+      if (tabber && nit < n_items) tables_for(nit, ncn, tabs + (buf ^ 1) * TAB_FLOATS);   // while the MMAs are issued and run
       umma::mbar_wait(bar_y, par);
       umma::tc_fence_after();
-      if (tid == 0) {                                                  // C, B and the other X buffer are free: prefetch
-        int nit = it, ncn = c + 1;
-        if (ncn == nc) { nit = it + gridDim.x; ncn = 0; }
-        if (nit < n_items) issue_load(nit, ncn, buf ^ 1);
-      }
-      // ---- epilogue 2: y = Yd + e^{cs_t} Yo + D x
-      {
-        const int t = row;
-        float yd[32], yo[32];
-        umma::tmem_ld32(t_lane + 128u + 32u * ch, yd);
-        umma::tmem_ld32(t_lane + 192u + 32u * ch, yo);
+      if (issuer && nit < n_items) issue_load(nit, ncn, buf ^ 1);      // C, B and the other X buffer are free
+      // ---- epilogue 2: y = Yd + e^{cs_t} Yo + D x          (thread = row t, 64/NCG of the 64 columns)
+#pragma unroll
+      for (int bb = 0; bb < NB; ++bb) {
+        const int t = row, c16 = NB * cg + bb;                         // 16-column block of the 64
+        float yd[16], yo[16];
+        umma::tmem_ld16(t_lane + 128u + 16u * c16, yd);
+        umma::tmem_ld16(t_lane + 192u + 16u * c16, yo);
         umma::tmem_ld_wait();
         if (t < qv) {
           const float ecs = s_ecs[t];
-          __nv_bfloat16* yg = p.y + (row0 + t) * di + h * TP + 32 * ch;
+          __nv_bfloat16* yg = p.y + (row0 + t) * di + h * TP + 16 * c16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 2; ++k) {
             float x[8], o[8];
-            unpack8(*reinterpret_cast<const uint4*>(sX + buf * HALF + swz(t, 4 * ch + k)), x);
+            unpack8(*reinterpret_cast<const uint4*>(sX + buf * HALF + swz(t, 2 * c16 + k)), x);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = yd[8 * k + e] + ecs * yo[8 * k + e] + Dh * x[e];
             *reinterpret_cast<uint4*>(yg + 8 * k) = pack8(o);
@@ -276,14 +316,18 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       }
       // ---- epilogue 3: S = e^{cs_last} S + dS  (thread = state row n)
       {
-        float ds[32];
-        umma::tmem_ld32(t_lane + 256u + 32u * ch, ds);
-        umma::tmem_ld_wait();
         const float decay = s_ecs[TQ - 1];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) Sreg[j] = decay * Sreg[j] + ds[j];
+        for (int bb = 0; bb < NB; ++bb) {
+          const int c16 = NB * cg + bb;
+          float ds[16];
+          umma::tmem_ld16(t_lane + 256u + 16u * c16, ds);
+          umma::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sS + swz(row, 4 * ch + k)) = pack8(Sreg + 8 * k);
+          for (int j = 0; j < 16; ++j) Sreg[16 * bb + j] = decay * Sreg[16 * bb + j] + ds[j];
+          *reinterpret_cast<uint4*>(sS + swz(row, 2 * c16)) = pack8(Sreg + 16 * bb);
+          *reinterpret_cast<uint4*>(sS + swz(row, 2 * c16 + 1)) = pack8(Sreg + 16 * bb + 8);
+        }
       }
       umma::fence_async_smem();
       umma::tc_fence_before();
@@ -295,17 +339,9 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
-
-// =================================================================================================
-// Backward (three kernels, all in scan order):
-//   1. dstate : per (row, head), chunks in REVERSE order:  Gst[c] = d loss / d (state leaving chunk c)
-//               dS_local = C^T (e^{cs} o dY)   128x64x128,   G_run = e^{cs_last} G_run + dS_local
-//   2. dx     : per (row, chunk, head): du = K^T dY + e_q B Gst  ->  dx, ddt, dA_log, dD
-//   3. dbc    : per (row, chunk), heads accumulated in TMEM:   dC += W B + (e^{cs} dY) S_in^T,
-//                                                              dB += W^T C + (w X) Gst^T
-// with  K = (C B^T) o L,  W = (dY X^T) o L o dt,  L[t,q] = e^{cs_t - cs_q} (q <= t).
-// The gradient w.r.t. the cumulative log-decay cs is collected term by term (see ssd_kernels.cu).
-// =================================================================================================
+// ===================================================================================================
+// backward
+// ===================================================================================================
 struct BwdParams {
   const float* dt; const float* A_log; const float* Dskip;
   __nv_bfloat16* gstates;        // [ndir*B, H, nc, 128, 64]
@@ -315,32 +351,19 @@ struct BwdParams {
   float* dA_log; float* dD;      // [ndir, H]
   int ndirB, B, L, H, di, nc;
   long long* dbg;                // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
-  int mode;                      // debug experiments (0 = normal)
 };
 
-// decay factors l[j] = L[t, s0+j] (j < 32) of row t (row block I) against column block J <= I.  The case split is
-// warp-uniform and sits OUTSIDE the element loop.
-__device__ __forceinline__ void decay_row32(float* l, int t, int I, int J, int s0, float cs_t, float e_ref,
-                                            const float* s_cs, const float* s_f) {
-  if (J < I) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) l[j] = e_ref * s_f[I * TQ + s0 + j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) l[j] = (s0 + j <= t) ? __expf(cs_t - s_cs[s0 + j]) : 0.f;
-  }
-}
-
-// ---- 1. dstate ------------------------------------------------------------------------------------
+// ---- 1. dstate (256 threads, 2 CTAs per SM) -----------------------------------------------------------
+constexpr int D1_THREADS = 256;
 constexpr int D1_OFF_C = 0, D1_OFF_DY = 2 * HALF, D1_OFF_DYS = 3 * HALF, D1_OFF_TAB = 4 * HALF;
-constexpr int D1_OFF_BAR = D1_OFF_TAB + TAB_FLOATS * 4;
+constexpr int D1_OFF_BAR = D1_OFF_TAB + TAB_BYTES;
 constexpr int D1_SMEM = D1_OFF_BAR + 64 + 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(D1_THREADS, 2)
 ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                          const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
   uint8_t* sC = base + D1_OFF_C; uint8_t* sdY = base + D1_OFF_DY; uint8_t* sdYs = base + D1_OFF_DYS;
   float* tab = reinterpret_cast<float*>(base + D1_OFF_TAB);
   const float* s_ecs = tab + 3 * TQ;
@@ -379,14 +402,14 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       const uint32_t par = seq & 1;
       const int q0 = c * TQ, qv = min(TQ, L - q0);
       const long long row0 = (long long)db * L + q0;
-      build_tables(p.dt + row0 * H + h, H, qv, A, tab);
+      build_tables(p.dt + row0 * H + h, H, qv, A, tab, D1_THREADS);
       {   // gradient w.r.t. the state LEAVING this chunk
         __nv_bfloat16* gg = p.gstates + ((((long long)db * H + h) * nc + c) * TN + row) * TP + 32 * ch;
 #pragma unroll
         for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(gg + 8 * k) = pack8(Grun + 8 * k);
       }
       umma::mbar_wait(bar_load, par);
-      for (int i = tid; i < TQ * 8; i += TC_THREADS) {
+      for (int i = tid; i < TQ * 8; i += D1_THREADS) {
         const float e = s_ecs[i >> 3];
         float v[8];
         unpack8(reinterpret_cast<const uint4*>(sdY)[i], v);
@@ -426,31 +449,32 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 // ---- 2. dx / ddt / dA / dD --------------------------------------------------------------------------
 constexpr int D2_OFF_C = 0, D2_OFF_B = 2 * HALF, D2_OFF_X = 4 * HALF, D2_OFF_DY = 5 * HALF, D2_OFF_S = 6 * HALF,
               D2_OFF_G = 7 * HALF, D2_OFF_K = 8 * HALF, D2_OFF_TAB = 10 * HALF;
-constexpr int D2_OFF_BAR = D2_OFF_TAB + TAB_FLOATS * 4;
+constexpr int D2_OFF_EXTRA = D2_OFF_TAB + 2 * TAB_BYTES;
+constexpr int D2_OFF_BAR = D2_OFF_EXTRA + EXTRA_FLOATS * 4;
 constexpr int D2_SMEM = D2_OFF_BAR + 64 + 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                      const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
                      const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
+  constexpr int NCG = NT / 128, NB = 4 / NCG, NTAB = NT - 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
   uint8_t* sC = base + D2_OFF_C; uint8_t* sB = base + D2_OFF_B; uint8_t* sX = base + D2_OFF_X;
   uint8_t* sdY = base + D2_OFF_DY; uint8_t* sS = base + D2_OFF_S; uint8_t* sG = base + D2_OFF_G;
   uint8_t* sK = base + D2_OFF_K;
-  float* tab = reinterpret_cast<float*>(base + D2_OFF_TAB);
-  const float* s_cs = tab; const float* s_dt = tab + TQ; const float* s_ecs = tab + 3 * TQ; const float* s_eq = tab + 4 * TQ;
-  const float* s_f = tab + 5 * TQ;
-  float* s_tot = tab + 9 * TQ;           // [8] scratch
-  float* s_dcs = tab + 9 * TQ + 8;       // [128]
-  float* s_ddtx = s_dcs + TQ;            // [128]
-  float* s_sc = s_ddtx + TQ;             // [0] = d cs_last extra, [1] = dD
+  float* tabs = reinterpret_cast<float*>(base + D2_OFF_TAB);
+  float* s_dcs = reinterpret_cast<float*>(base + D2_OFF_EXTRA);    // [128]  d loss / d cs_t
+  float* s_ddtx = s_dcs + TQ;                                       // [128]  <du_q, x_q>
+  float* s_sc = s_ddtx + TQ;                                        // [0] extra d cs_last, [1] dD, [4..7] warp totals
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + D2_OFF_BAR);
   uint64_t* bar1 = bar_load + 1;
   uint64_t* bar2 = bar_load + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lq = warp & 3, ch = warp >> 2, row = lq * 32 + lane;
+  const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
+  const bool issuer = tid == NTAB, tabber = tid < NTAB;
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
     umma::mbar_init(bar_load, 1); umma::mbar_init(bar1, 1); umma::mbar_init(bar2, 1);
@@ -477,23 +501,33 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     umma::tma_load_2d(sS, &tmS, bar_load, 0, srow);
     umma::tma_load_2d(sG, &tmG, bar_load, 0, srow);
   };
+  auto tables_for = [&](int item, float* tab) {
+    const int h = item % H, c = (item / H) % nc, db = item / (H * nc), dir = db / p.B;
+    const int q0 = c * TQ;
+    build_tables(p.dt + ((long long)db * L + q0) * H + h, H, min(TQ, L - q0), -__expf(p.A_log[dir * H + h]), tab, NTAB);
+  };
   uint32_t seq = 0;
-  if (blockIdx.x < n_items && tid == 0) issue_load(blockIdx.x);
+  if (blockIdx.x < n_items) {
+    if (issuer) issue_load(blockIdx.x);
+    if (tabber) tables_for(blockIdx.x, tabs);
+  }
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++seq) {
     const uint32_t par = seq & 1;
+    const float* tab = tabs + (seq & 1) * TAB_FLOATS;
+    const float* s_dt = tab + TQ; const float* s_ecs = tab + 3 * TQ; const float* s_eq = tab + 4 * TQ;
     const int h = it % H, c = (it / H) % nc, db = it / (H * nc), dir = db / p.B;
     const float A = -__expf(p.A_log[dir * H + h]);
     const float Dh = p.Dskip[dir * H + h];
     const int q0 = c * TQ, qv = min(TQ, L - q0);
     const long long row0 = (long long)db * L + q0;
+    const int nit = it + gridDim.x;
     long long tk0 = clock64();
     if (tid < TQ) { s_dcs[tid] = 0.f; s_ddtx[tid] = 0.f; }
     if (tid < 2) s_sc[tid] = 0.f;
-    build_tables(p.dt + row0 * H + h, H, qv, A, tab);
-    long long tk1 = clock64();
+    __syncthreads();                                                   // zeroing (and the first tables) visible
     umma::mbar_wait(bar_load, par);
-    long long tk2 = clock64();
-    if (tid == 0) {
+    long long tk1 = clock64();
+    if (issuer) {
       umma::tc_fence_after();
 #pragma unroll
       for (int kb = 0; kb < 8; ++kb) {                                 // G = C B^T
@@ -513,9 +547,11 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
       umma::mma_commit(bar1);
     }
-    {   // inter-chunk decay term: e^{cs_last} <Gst, S_in>  (same swizzle on both tiles: plain elementwise product)
+    // while the MMAs are issued and run: tables of the next item, and the decay term e^{cs_last} <Gst, S_in>
+    if (tabber && nit < n_items) tables_for(nit, tabs + ((seq & 1) ^ 1) * TAB_FLOATS);
+    {
       float dot = 0.f;
-      for (int i = tid; i < TQ * 8; i += TC_THREADS) {
+      for (int i = tid; i < TQ * 8; i += NT) {                         // same swizzle on both tiles: elementwise product
         float a[8], b[8];
         unpack8(reinterpret_cast<const uint4*>(sS)[i], a);
         unpack8(reinterpret_cast<const uint4*>(sG)[i], b);
@@ -527,24 +563,22 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     umma::mbar_wait(bar1, par);
     umma::tc_fence_after();
-    long long tk3 = clock64();
-    // ---- epilogue A: K = G o L -> smem;  d cs_t += sum_q W G  +  e^{cs_t} <dY_t, Yo_t>
+    long long tk2 = clock64();
+    // ---- epilogue A (thread = row t, 128/NCG of the 128 columns): K = G o L -> smem;
+    //      d cs_t += sum_q W G  +  e^{cs_t} <dY_t, Yo_t>
     {
       const int t = row, I = t >> 5;
-      const float cs_t = s_cs[t];
-      const float e_ref = (I > 0) ? __expf(cs_t - s_cs[32 * I - 1]) : 0.f;
       float acc = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int J = 2 * ch + cc, s0 = 32 * J;
+      for (int bb = 0; bb < NB; ++bb) {
+        const int J = NB * cg + bb, s0 = 32 * J;
         float g[32];
         if (J <= I) {
-          float r[32];
+          float r[32], l[32];
           umma::tmem_ld32(t_lane + (uint32_t)s0, g);
           umma::tmem_ld32(t_lane + 128u + (uint32_t)s0, r);
           umma::tmem_ld_wait();
-          float l[32];
-          decay_row32(l, t, I, J, s0, cs_t, e_ref, s_cs, s_f);
+          decay_row32(l, t, I, J, s0, tab);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             g[j] *= l[j];
@@ -557,25 +591,29 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           for (int j = 0; j < 32; ++j) g[j] = 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sK + ch * HALF + swz(t, 4 * cc + k)) = pack8(g + 8 * k);
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(sK + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(g + 8 * k);
       }
-      float yo[32], yd = 0.f;
-      {
-      umma::tmem_ld32(t_lane + 256u + 32u * ch, yo);
-      umma::tmem_ld_wait();
+      float yd = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float d[8];
-        unpack8(*reinterpret_cast<const uint4*>(sdY + swz(t, 4 * ch + k)), d);
+      for (int bb = 0; bb < NB; ++bb) {
+        const int c16 = NB * cg + bb;
+        float yo[16];
+        umma::tmem_ld16(t_lane + 256u + 16u * c16, yo);
+        umma::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 8; ++e) yd += d[e] * yo[8 * k + e];
-      }
+        for (int k = 0; k < 2; ++k) {
+          float d[8];
+          unpack8(*reinterpret_cast<const uint4*>(sdY + swz(t, 2 * c16 + k)), d);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) yd += d[e] * yo[8 * k + e];
+        }
       }
       atomicAdd(&s_dcs[t], acc + s_ecs[t] * yd);
     }
     umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
-    long long tk4 = clock64();
-    if (tid == 0) {
+    long long tk3 = clock64();
+    if (issuer) {
       umma::tc_fence_after();
 #pragma unroll
       for (int kb = 0; kb < 8; ++kb)                                   // du1 = K^T dY
@@ -589,42 +627,47 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
       umma::mma_commit(bar2);
     }
+    // operands of epilogue B that live in TMA-owned buffers: fetch them now so the buffers can be refilled
+    const int q = row;
+    float xr[16 * NB], dr[16 * NB];
+#pragma unroll
+    for (int k = 0; k < 2 * NB; ++k) {
+      unpack8(*reinterpret_cast<const uint4*>(sX + swz(q, 2 * NB * cg + k)), xr + 8 * k);
+      unpack8(*reinterpret_cast<const uint4*>(sdY + swz(q, 2 * NB * cg + k)), dr + 8 * k);
+    }
     umma::mbar_wait(bar2, par);
     umma::tc_fence_after();
-    long long tk5 = clock64();
-    // ---- epilogue B (thread = row q): dx, and the remaining d cs terms
+    long long tk4 = clock64();
+    __syncthreads();                                                   // every smem operand has been consumed
+    if (issuer && nit < n_items) issue_load(nit);
+    // ---- epilogue B (thread = row q, 64/NCG of the 64 columns): dx, and the remaining d cs terms
     {
-      const int q = row;
-      float xr[32], dr[32];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        unpack8(*reinterpret_cast<const uint4*>(sX + swz(q, 4 * ch + k)), xr + 8 * k);
-        unpack8(*reinterpret_cast<const uint4*>(sdY + swz(q, 4 * ch + k)), dr + 8 * k);
-      }
-      __syncthreads();                                                 // every smem operand has been consumed
-      if (tid == 0 && it + (int)gridDim.x < n_items) issue_load(it + gridDim.x);
-      float d1[32], d2[32];
-      umma::tmem_ld32(t_lane + 320u + 32u * ch, d1);
-      umma::tmem_ld32(t_lane + 384u + 32u * ch, d2);
-      umma::tmem_ld_wait();
       const float eq = s_eq[q], dtq = s_dt[q];
       float col = 0.f, sc = 0.f, dux = 0.f, dd = 0.f;
-      float o[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float du = d1[j] + eq * d2[j];
-        o[j] = dtq * du + Dh * dr[j];
-        col += d1[j] * xr[j];
-        sc += d2[j] * xr[j];
-        dux += du * xr[j];
-        dd += dr[j] * xr[j];
+      for (int bb = 0; bb < NB; ++bb) {
+        const int c16 = NB * cg + bb;
+        float d1[16], d2[16], o[16];
+        umma::tmem_ld16(t_lane + 320u + 16u * c16, d1);
+        umma::tmem_ld16(t_lane + 384u + 16u * c16, d2);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float xv = xr[16 * bb + j], dv = dr[16 * bb + j];
+          const float du = d1[j] + eq * d2[j];
+          o[j] = dtq * du + Dh * dv;
+          col += d1[j] * xv;
+          sc += d2[j] * xv;
+          dux += du * xv;
+          dd += dv * xv;
+        }
+        if (q < qv) {
+          __nv_bfloat16* og = p.dxc + (row0 + q) * di + h * TP + 16 * c16;
+          *reinterpret_cast<uint4*>(og) = pack8(o);
+          *reinterpret_cast<uint4*>(og + 8) = pack8(o + 8);
+        }
       }
       col *= dtq; sc *= dtq * eq;
-      if (q < qv) {
-        __nv_bfloat16* og = p.dxc + (row0 + q) * di + h * TP + 32 * ch;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(og + 8 * k) = pack8(o + 8 * k);
-      }
       atomicAdd(&s_dcs[q], -(col + sc));
       atomicAdd(&s_ddtx[q], dux);
       sc = warp_sum(sc); dd = warp_sum(dd);
@@ -637,11 +680,11 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       v = s_dcs[TQ - 1 - tid] + (tid == 0 ? s_sc[0] : 0.f);           // tid 0 holds the latest time
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-      if (lane == 31) s_tot[warp] = v;
+      if (lane == 31) s_sc[4 + warp] = v;
     }
     __syncthreads();
     if (tid < TQ) {
-      for (int w = 0; w < warp; ++w) v += s_tot[w];
+      for (int w = 0; w < warp; ++w) v += s_sc[4 + w];
       const int t = TQ - 1 - tid;
       float accA = v * s_dt[t];
       if (t < qv) p.ddt[(row0 + t) * H + h] = v * A + s_ddtx[t];
@@ -651,9 +694,9 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     umma::tc_fence_before(); __syncthreads();
     if (p.dbg && blockIdx.x == 0 && tid == 0) {
-      const long long tk6 = clock64();
+      const long long tk5 = clock64();
       p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
-      p.dbg[4] += tk5 - tk4; p.dbg[5] += tk6 - tk5; p.dbg[6] += 1;
+      p.dbg[4] += tk5 - tk4; p.dbg[6] += 1;
     }
   }
   umma::tc_fence_before(); __syncthreads();
@@ -663,28 +706,29 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // ---- 3. dB / dC ---------------------------------------------------------------------------------------
 constexpr int D3_OFF_C = 0, D3_OFF_B = 2 * HALF, D3_OFF_X = 4 * HALF, D3_OFF_DY = 5 * HALF, D3_OFF_XW = 6 * HALF,
               D3_OFF_DYS = 7 * HALF, D3_OFF_S = 8 * HALF, D3_OFF_G = 9 * HALF, D3_OFF_W = 10 * HALF, D3_OFF_TAB = 12 * HALF;
-constexpr int D3_OFF_BAR = D3_OFF_TAB + TAB_FLOATS * 4;
+constexpr int D3_OFF_BAR = D3_OFF_TAB + 2 * TAB_BYTES;
 constexpr int D3_SMEM = D3_OFF_BAR + 64 + 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                       const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
                       const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
+  constexpr int NCG = NT / 128, NB = 4 / NCG, NTAB = NT - 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
   uint8_t* sC = base + D3_OFF_C; uint8_t* sB = base + D3_OFF_B; uint8_t* sX = base + D3_OFF_X;
   uint8_t* sdY = base + D3_OFF_DY; uint8_t* sXw = base + D3_OFF_XW; uint8_t* sdYs = base + D3_OFF_DYS;
   uint8_t* sS = base + D3_OFF_S; uint8_t* sG = base + D3_OFF_G; uint8_t* sW = base + D3_OFF_W;
-  float* tab = reinterpret_cast<float*>(base + D3_OFF_TAB);
-  const float* s_cs = tab; const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
-  const float* s_f = tab + 5 * TQ;
+  float* tabs = reinterpret_cast<float*>(base + D3_OFF_TAB);
   uint64_t* bar_cb = reinterpret_cast<uint64_t*>(base + D3_OFF_BAR);
   uint64_t* bar_h = bar_cb + 1;
   uint64_t* bar_r = bar_cb + 2;
   uint64_t* bar_m = bar_cb + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_cb + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lq = warp & 3, ch = warp >> 2, row = lq * 32 + lane;
+  const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
+  const bool issuer = tid == NTAB, tabber = tid < NTAB;
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
     umma::mbar_init(bar_cb, 1); umma::mbar_init(bar_h, 1); umma::mbar_init(bar_r, 1); umma::mbar_init(bar_m, 1);
@@ -715,19 +759,30 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     umma::tma_load_2d(sS, &tmS, bar_h, 0, srow);
     umma::tma_load_2d(sG, &tmG, bar_h, 0, srow);
   };
+  auto tables_for = [&](int item, int h, float* tab) {
+    const int c = item % nc, db = item / nc, dir = db / p.B;
+    const int q0 = c * TQ;
+    build_tables(p.dt + ((long long)db * L + q0) * H + h, H, min(TQ, L - q0), -__expf(p.A_log[dir * H + h]), tab, NTAB);
+  };
   uint32_t iseq = 0, hseq = 0;
-  if (blockIdx.x < n_items && tid == 0) { load_cb(blockIdx.x); load_head(blockIdx.x, 0); }
+  if (blockIdx.x < n_items) {
+    if (issuer) { load_cb(blockIdx.x); load_head(blockIdx.x, 0); }
+    if (tabber) tables_for(blockIdx.x, 0, tabs);
+  }
+  __syncthreads();
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
-    const int c = it % nc, db = it / nc, dir = db / p.B;
+    const int c = it % nc, db = it / nc;
     const int q0 = c * TQ, qv = min(TQ, L - q0);
     const long long row0 = (long long)db * L + q0;
     for (int h = 0; h < H; ++h, ++hseq) {
       const uint32_t par = hseq & 1;
-      const float A = -__expf(p.A_log[dir * H + h]);
-      build_tables(p.dt + row0 * H + h, H, qv, A, tab);
+      const float* tab = tabs + (hseq & 1) * TAB_FLOATS;
+      const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
+      int nit = it, nh = h + 1;                                        // the head-step after this one
+      if (nh == H) { nit = it + gridDim.x; nh = 0; }
       if (h == 0) umma::mbar_wait(bar_cb, iseq & 1);
       umma::mbar_wait(bar_h, par);
-      if (tid == 0) {
+      if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)                                 // R = dY X^T
@@ -735,7 +790,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), i_kk, kb > 0);
         umma::mma_commit(bar_r);
       }
-      for (int i = tid; i < TQ * 8; i += TC_THREADS) {                 // Xw = w_q X,  dYs = e^{cs_t} dY
+      for (int i = tid; i < TQ * 8; i += NT) {                         // Xw = w_q X,  dYs = e^{cs_t} dY
         const float w = s_w[i >> 3], e = s_ecs[i >> 3];
         float a[8], b[8];
         unpack8(reinterpret_cast<const uint4*>(sX)[i], a);
@@ -747,31 +802,27 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       umma::mbar_wait(bar_r, par);
       umma::tc_fence_after();
-      {   // W[t,q] = R[t,q] L[t,q] dt_q
-        const int t = row, I = t >> 5;
-        const float cs_t = s_cs[t];
-        const float e_ref = (I > 0) ? __expf(cs_t - s_cs[32 * I - 1]) : 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int J = 2 * ch + cc, s0 = 32 * J;
-          float r[32];
-          if (J <= I) {
-            umma::tmem_ld32(t_lane + (uint32_t)s0, r);
-            umma::tmem_ld_wait();
-            float l[32];
-            decay_row32(l, t, I, J, s0, cs_t, e_ref, s_cs, s_f);
+      for (int bb = 0; bb < NB; ++bb) {   // W[t,q] = R[t,q] L[t,q] dt_q   (thread = row t, 128/NCG of the 128 columns)
+        const int t = row, I = t >> 5, J = NB * cg + bb, s0 = 32 * J;
+        float r[32];
+        if (J <= I) {
+          float l[32];
+          umma::tmem_ld32(t_lane + (uint32_t)s0, r);
+          umma::tmem_ld_wait();
+          decay_row32(l, t, I, J, s0, tab);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] *= l[j] * s_dt[s0 + j];
-          } else {
+          for (int j = 0; j < 32; ++j) r[j] *= l[j] * s_dt[s0 + j];
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sW + ch * HALF + swz(t, 4 * cc + k)) = pack8(r + 8 * k);
+          for (int j = 0; j < 32; ++j) r[j] = 0.f;
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(sW + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(r + 8 * k);
       }
       umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
-      if (tid == 0) {
+      if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {                               // dC += W B
@@ -793,11 +844,13 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             umma::make_smem_desc(umma::smem_u32(sG) + kb * 32, 16, 1024), i_kk, 1u);
         umma::mma_commit(bar_m);
       }
+      if (tabber && nit < n_items) tables_for(nit, nh, tabs + ((hseq & 1) ^ 1) * TAB_FLOATS);   // while the MMAs are issued and run
       umma::mbar_wait(bar_m, par);
       umma::tc_fence_after();
-      if (tid == 0) {
-        if (h + 1 < H) load_head(it, h + 1);
-        else if (it + (int)gridDim.x < n_items) { load_cb(it + gridDim.x); load_head(it + gridDim.x, 0); }
+      __syncthreads();                                                 // the next tables are complete for everyone
+      if (issuer && nit < n_items) {
+        if (nh == 0) load_cb(nit);
+        load_head(nit, nh);
       }
     }
     // ---- write dB | dC of this chunk (bf16, like the rest of the activation gradients)
@@ -805,14 +858,14 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const int t = row;
 #pragma unroll
       for (int part = 0; part < 2; ++part) {                            // 0: dB (TMEM 256..383), 1: dC (TMEM 128..255)
-        const uint32_t tb = part == 0 ? 256u : 128u;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int bb = 0; bb < NB; ++bb) {
+          const int J = NB * cg + bb;
           float v[32];
-          umma::tmem_ld32(t_lane + tb + 64u * ch + 32u * cc, v);
+          umma::tmem_ld32(t_lane + (part == 0 ? 256u : 128u) + 32u * J, v);
           umma::tmem_ld_wait();
           if (t < qv) {
-            __nv_bfloat16* og = p.dBC + (row0 + t) * (2 * TN) + part * TN + 64 * ch + 32 * cc;
+            __nv_bfloat16* og = p.dBC + (row0 + t) * (2 * TN) + part * TN + 32 * J;
 #pragma unroll
             for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(og + 8 * k) = pack8(v + 8 * k);
           }
@@ -857,8 +910,8 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = cdiv(L, TQ);
   const int items = ndir * B * H;
   const int grid = items < sm_count() ? items : sm_count();
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-  ssd_fwd_tc_kernel<<<grid, TC_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  ssd_fwd_tc_kernel<FWD_THREADS><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
   HNB_LAUNCH_CHECK("ssd_fwd_tc");
   return HNB_OK;
 }
@@ -890,21 +943,20 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   p.dBC = (__nv_bfloat16*)dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = nc;
   p.dbg = nullptr;
-  p.mode = getenv("HNB_SSD_MODE") ? atoi(getenv("HNB_SSD_MODE")) : 0;
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
   if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, st); }
   const int sms = sm_count();
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dstate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D1_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel<BWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel<BWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
   int items = ndir * B * H;
-  ssd_bwd_dstate_tc_kernel<<<items < 2 * sms ? items : 2 * sms, TC_THREADS, D1_SMEM, st>>>(tmX, tmDY, p);
+  ssd_bwd_dstate_tc_kernel<<<items < 2 * sms ? items : 2 * sms, D1_THREADS, D1_SMEM, st>>>(tmX, tmDY, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dstate_tc");
   items = ndir * B * nc * H;
-  ssd_bwd_dx_tc_kernel<<<items < sms ? items : sms, TC_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  ssd_bwd_dx_tc_kernel<BWD_THREADS><<<items < sms ? items : sms, BWD_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dx_tc");
   items = ndir * B * nc;
-  ssd_bwd_dbc_tc_kernel<<<items < sms ? items : sms, TC_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  ssd_bwd_dbc_tc_kernel<BWD_THREADS><<<items < sms ? items : sms, BWD_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dbc_tc");
   if (debug) {
     long long h[8];
@@ -912,8 +964,8 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
     cudaMemcpy(h, p.dbg, 64, cudaMemcpyDeviceToHost);
     cudaFree(p.dbg);
     const double n = h[6] > 0 ? (double)h[6] : 1.0;
-    fprintf(stderr, "[ssd_bwd_dx CTA0] items %lld | cycles/item: tables %.0f, wait load %.0f, mma1 wait(+dot) %.0f, epiA %.0f, "
-            "mma2 wait %.0f, epiB+cumsum %.0f\n", h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n);
+    fprintf(stderr, "[ssd_bwd_dx CTA0] items %lld | cycles/item: wait load %.0f, mma1 wait (tables+dot) %.0f, epiA %.0f, "
+            "mma2 wait %.0f, epiB+cumsum %.0f\n", h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n);
   }
   return HNB_OK;
 }
