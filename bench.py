@@ -49,26 +49,46 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, 10 ms period; nvidia-smi as fallback)."""
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.stop = index, [], False
+        self.index, self.sm, self.max_mhz, self.reasons, self.stop = index, [], None, set(), False
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop:
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.reasons |= {n for bit, n in self.NAMES.items() if mask & bit}
+                time.sleep(0.01)
+        except Exception:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            while not self.stop:
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    r = [c.strip() for c in out.strip().split(",")]
+                    if len(r) >= 6 and r[0].isdigit():
+                        self.sm.append(int(r[0])); self.max_mhz = int(r[1])
+                        self.reasons |= {n for n, v in zip(names, r[2:6]) if v.lower().startswith("active")}
+                except Exception:
+                    pass
+                time.sleep(0.05)
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
@@ -76,12 +96,9 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def synth_batch(B: int, seconds: float, seed: int):
@@ -116,6 +133,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
     step, frames = cpu_reference_step_fn(1, args.seconds)
     for _ in range(max(1, min(args.warmup, 1))):
         step()
@@ -207,7 +225,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     torch.manual_seed(1)
     torch.backends.cudnn.benchmark = True           # ConvSubsampling4 is library code: let cuDNN pick its kernels
     enc = dd.DCASREncoder(**SMALL).to(dev)
@@ -222,7 +243,7 @@ def run_ours(args):
             dist.broadcast(p.data, 0)
     params = [p for p in enc.parameters()]
     from dcasr_b200.distributed import GradAllReducer
-    reducer = GradAllReducer(params) if world > 1 else None
+    reducer = GradAllReducer(params, bucket_mb=32.0, overlap=True) if world > 1 else None
     feats_h, lens_h = synth_batch(args.batch, args.seconds, 1 + rank)      # each rank its own shard of utterances
     feats_pin, lens_pin = feats_h.pin_memory(), lens_h.pin_memory()
     feats_d, lens_d = feats_h.to(dev), lens_h.to(dev)
@@ -260,6 +281,8 @@ def run_ours(args):
             out = enc.forward_hot_path(xsub_d, lsub_d)
         loss = out.features.float().pow(2).mean() + 0.03 * out.ratio_loss
         loss.backward()
+        if reducer is not None:
+            reducer()
         return loss
 
     def timed(step, steps):
@@ -313,9 +336,10 @@ def run_ours(args):
                          "what": "forward_hot_path + backward from the subsampled features (ConvSubsampling4 excluded)",
                          "gpu_launches": launches_hot},
             "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3)}
+    # the profiled step contains the gradient all-reduce when world > 1: EVERY rank must run it
+    pk, pk_src = peaks()
+    table, total = profile_step(step_resident, pk)
     if rank == 0:
-        pk, pk_src = peaks()
-        table, total = profile_step(step_resident, pk)
         top = next((r for r in table if "frac" in r), None)
         if top:
             line["roofline"] = {"kernel": "hnb_" + top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
@@ -324,6 +348,7 @@ def run_ours(args):
                                 "share_of_step": top["share"], "launches_per_step": top["launches"]}
         line["kernel_table"] = table[:12]
         if world == 1 and not args.no_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
             step, frames = cpu_reference_step_fn(1, args.seconds)
             step()
             t0 = time.perf_counter()

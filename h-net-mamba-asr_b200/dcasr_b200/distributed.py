@@ -18,13 +18,18 @@ def shard_indices(n_items: int, rank: int, world: int) -> list[int]:
 
 
 class GradAllReducer:
-    """Bucketed mean all-reduce of parameter gradients (DDP semantics) through flat buffers."""
+    """Bucketed mean all-reduce of parameter gradients (DDP semantics) through flat fp32 buffers.
 
-    def __init__(self, params, bucket_mb: float = 64.0):
+    ``overlap=True`` registers post-accumulate-grad hooks: a bucket's all-reduce is launched (async, on NCCL's own
+    stream) as soon as its last gradient has been produced, so the exchange overlaps the rest of the backward pass;
+    ``__call__`` (end of the step) launches whatever is still pending, waits, and writes the means back into ``.grad``.
+    Buckets are filled in reverse parameter order, the order in which backward produces gradients."""
+
+    def __init__(self, params, bucket_mb: float = 64.0, overlap: bool = False):
         self.params = [p for p in params if p.requires_grad]
         self.buckets, cur, size = [], [], 0
         limit = int(bucket_mb * (1 << 20))
-        for p in self.params:
+        for p in reversed(self.params):
             cur.append(p)
             size += p.numel() * 4
             if size >= limit:
@@ -34,22 +39,40 @@ class GradAllReducer:
             self.buckets.append(cur)
         self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device)
                      for b in self.buckets]
+        self.works = [None] * len(self.buckets)
+        self.pending = [len(b) for b in self.buckets]
+        self.overlap = overlap and dist.is_initialized() and dist.get_world_size() > 1
+        if self.overlap:
+            where = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(lambda q, i=where[id(p)]: self._ready(i))
+
+    def _launch(self, i: int) -> None:
+        b, flat = self.buckets[i], self.flat[i]
+        views = flat.split([p.numel() for p in b])
+        torch._foreach_copy_(list(views), [p.grad.reshape(-1).float() if p.grad is not None
+                                           else torch.zeros_like(v) for p, v in zip(b, views)])
+        self.works[i] = dist.all_reduce(flat, async_op=True)
+
+    def _ready(self, i: int) -> None:
+        self.pending[i] -= 1
+        if self.pending[i] == 0:
+            self._launch(i)
 
     def __call__(self) -> None:
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
         world = dist.get_world_size()
-        works = []
-        for b, flat in zip(self.buckets, self.flat):
-            views = flat.split([p.numel() for p in b])
-            torch._foreach_copy_(list(views), [p.grad.reshape(-1).float() if p.grad is not None
-                                               else torch.zeros_like(v) for p, v in zip(b, views)])
-            works.append(dist.all_reduce(flat, async_op=True))
-        for (b, flat), w in zip(zip(self.buckets, self.flat), works):
-            w.wait()
+        for i in range(len(self.buckets)):
+            if self.works[i] is None:
+                self._launch(i)
+        for i, (b, flat) in enumerate(zip(self.buckets, self.flat)):
+            self.works[i].wait()
             flat.div_(world)
             for p, v in zip(b, flat.split([p.numel() for p in b])):
                 if p.grad is None:
                     p.grad = v.view_as(p).to(p.dtype).clone()
                 else:
                     p.grad.copy_(v.view_as(p))
+            self.works[i] = None
+            self.pending[i] = len(b)

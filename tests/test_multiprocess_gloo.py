@@ -24,8 +24,12 @@ def _worker(rank, world, port, out):
     g = torch.Generator().manual_seed(5)
     X = torch.randn(6, 20, 64, generator=g)                     # 6 utterances in the global batch
     idx = shard_indices(6, rank, world)
-    st(X[idx]).pow(2).sum().backward()
-    red = GradAllReducer(st.parameters(), bucket_mb=0.05)       # several buckets
+    red = GradAllReducer(st.parameters(), bucket_mb=0.05, overlap=(rank >= 0))   # several buckets, hook-driven
+    st.zero_grad(set_to_none=True)
+    st(X[idx]).pow(2).sum().backward()                          # hooks launch each bucket as it completes
+    red()
+    st.zero_grad(set_to_none=True)
+    st(X[idx]).pow(2).sum().backward()                          # a second step must reuse the buckets cleanly
     red()
     torch.save({k: p.grad.clone() for k, p in st.named_parameters()}, os.path.join(out, f"g{rank}.pt"))
     dist.barrier()
