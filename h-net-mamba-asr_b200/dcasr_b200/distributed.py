@@ -69,10 +69,10 @@ class GradAllReducer:
         for i, (b, flat) in enumerate(zip(self.buckets, self.flat)):
             self.works[i].wait()
             flat.div_(world)
-            for p, v in zip(b, flat.split([p.numel() for p in b])):
+            views = flat.split([p.numel() for p in b])
+            for p, v in zip(b, views):
                 if p.grad is None:
-                    p.grad = v.view_as(p).to(p.dtype).clone()
-                else:
-                    p.grad.copy_(v.view_as(p))
+                    p.grad = torch.empty_like(p)
+            torch._foreach_copy_([p.grad for p in b], [v.view_as(p) for p, v in zip(b, views)])   # one launch per bucket
             self.works[i] = None
             self.pending[i] = len(b)

@@ -327,3 +327,44 @@ def test_encoder_bf16_autocast_vs_fp32_oracle(arch, N):
     print("worst bf16 grad rel err: tensors", max(big), " per-head scalars", max(small))
     assert max(big)[0] < 6e-2, max(big)     # medians are ~2.7e-2 (precision)
     assert max(small)[0] < 0.25, max(small)
+
+
+@pytest.mark.parametrize("d,L,lengths,dtype,tol", [
+    (384, 398, [398, 398, 250], torch.float32, 1e-3),        # Small outer dims, 16 s, fp32 (decode path, exact kernels)
+    (512, 199, [199, 120, 64], torch.bfloat16, 2e-2),        # Small main dims on the compressed sequence, bf16 (tcgen05)
+    (768, 1498, [1498, 1001], torch.bfloat16, 2e-2),         # Large main dims, 60 s utterances: 12 SSD chunks, H = 24
+])
+def test_block_at_baseline_dims_vs_oracle(d, L, lengths, dtype, tol):
+    """One bidirectional MambaBlock at the BASELINE.json model dimensions / sequence lengths against the CPU oracle."""
+    import dcasr_b200 as dd
+    from oracle.encoder_ref import MambaBlockRef
+    ref = MambaBlockRef(d)
+    fill_weights(ref, 21)
+    blk = dd.MambaBlock(d)
+    blk.load_state_dict(ref.state_dict())
+    blk = blk.to(DEV)
+    torch.manual_seed(4)
+    B = len(lengths)
+    x = torch.randn(B, L, d)
+    lens = torch.tensor(lengths)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, lens)
+    xg = x.to(DEV).requires_grad_(True)
+    if dtype == torch.bfloat16:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = blk(xg, lens.to(DEV))
+    else:
+        y = blk(xg, lens.to(DEV))
+    mask = (torch.arange(L)[None] < lens[:, None]).unsqueeze(-1)
+    e = rel_err((y.cpu() - x) * mask, (yr - x) * mask)          # error of the mixer contribution, not of x + ...
+    print(f"d={d} L={L} {dtype}: mixer-output rel err {e:.2e}")
+    assert e < tol
+    w = torch.randn(B, L, d) * mask
+    (y * w.to(DEV)).sum().backward()
+    (yr * w).sum().backward()
+    eg = rel_err(xg.grad.cpu() - w, xr.grad - w)
+    print(f"   d x (mixer part) rel err {eg:.2e}")
+    assert eg < (tol if dtype == torch.float32 else 3e-2)
+    gs, gr = dict(blk.named_parameters()), dict(ref.named_parameters())
+    for k in ("fwd.in_proj.weight", "bwd.out_proj.weight", "fwd.conv1d.weight", "norm.weight"):
+        assert rel_err(gs[k].grad, gr[k].grad) < (tol if dtype == torch.float32 else 3e-2), k
