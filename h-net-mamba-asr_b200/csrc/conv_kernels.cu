@@ -6,13 +6,12 @@
 // of scan positions; ALL of its row loads (run + 3 halo rows) are issued before any arithmetic so that each
 // thread keeps 15-25 independent vector requests in flight (the loop-carried 4-tap window would otherwise
 // serialise load -> use -> load).  Halo rows are re-read by the neighbouring tile from L2.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hnb {
 
-constexpr int CONV_TS = 16;     // scan positions per thread, forward
-constexpr int CONV_TSB = 8;     // scan positions per thread and tile, backward
-constexpr int CONV_GX = 8;      // backward: tile groups per (row, direction); each block strides over its tiles
 
 // 4 channels per thread: 16-byte vectors for fp32, 8-byte vectors for bf16 (8 channels per thread would need
 // ~250 registers for the taps, the sliding windows and the parameter-gradient accumulators: 1-2 CTAs per SM).
@@ -49,29 +48,41 @@ template <> struct V16<__nv_bfloat16> {
   }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// sigmoid: the fp32 path keeps ex2+rcp (parity 1e-3 through 20 blocks); bf16 activations take one MUFU (tanh.approx,
+// abs. error ~5e-4, below the bf16 rounding of the result)
+template <typename T> __device__ __forceinline__ float sigmoid_t(float x) { return sigmoid_f(x); }
+template <> __device__ __forceinline__ float sigmoid_t<__nv_bfloat16>(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+
+// Work decomposition shared by both kernels: a block is CONV_CT column threads (4 channels each) x CONV_SEG
+// time segments of one (direction, row); a thread walks its segment in tiles of TS scan positions, carrying the
+// 3-row window in registers, so halo rows are read once per segment instead of once per tile.
+constexpr int CONV_CT = 64;
+constexpr int CONV_SEG = 4;
+
+template <typename T, int TS, int NTILE>
+__global__ void __launch_bounds__(CONV_CT * CONV_SEG)
 conv_fwd_kernel(const T* __restrict__ zx, long long ldz, long long dstride, const int* __restrict__ lengths,
                 const float* __restrict__ conv_w, const float* __restrict__ conv_b, const float* __restrict__ dt_bias,
                 int ndir, int B, int L, int di, int N, int H, T* __restrict__ xconv, float* __restrict__ dt_out) {
   constexpr int VN = V16<T>::N;
-  const int dir = blockIdx.z, bi = blockIdx.y, s0 = blockIdx.x * CONV_TS;
+  constexpr int RUN = TS * NTILE;
+  const int ct = threadIdx.x % CONV_CT, sg = threadIdx.x / CONV_CT;
+  const int dir = blockIdx.z / B, bi = blockIdx.z % B;
   const int C = di + 2 * N;
   const long long T_ = (long long)B * L;
   const int len = lengths ? lengths[bi] : L;
   const long long xoff = (long long)dir * dstride + di;
   const long long doff = (long long)dir * dstride + di + C;
   const T* rowbase = zx + (long long)bi * L * ldz;
-  const int s1 = min(s0 + CONV_TS, L);
+  const int c = (blockIdx.x * CONV_CT + ct) * VN;
+  const int sb = (blockIdx.y * CONV_SEG + sg) * RUN;
+  const long long sbase = (long long)dir * T_ + (long long)bi * L;
 
-  for (int c = threadIdx.x * VN; c < C; c += blockDim.x * VN) {
-    typename V16<T>::raw_t raw[CONV_TS + 3];
-#pragma unroll
-    for (int k = 0; k < CONV_TS + 3; ++k) {
-      const int s = s0 - 3 + k;
-      raw[k] = (s >= 0 && s < L) ? V16<T>::ldg(rowbase + (long long)scan_to_nat(dir, s, len) * ldz + xoff + c)
-                                 : V16<T>::zero();
-    }
+  if (c < C && sb < L) {
     float w[VN][4], bias[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
@@ -79,41 +90,83 @@ conv_fwd_kernel(const T* __restrict__ zx, long long ldz, long long dstride, cons
       w[i][0] = t.x; w[i][1] = t.y; w[i][2] = t.z; w[i][3] = t.w;
       bias[i] = __ldg(conv_b + (long long)dir * C + c + i);
     }
-    float win[3][VN], cur[VN], o[VN];
-    V16<T>::unpack(raw[0], win[0]); V16<T>::unpack(raw[1], win[1]); V16<T>::unpack(raw[2], win[2]);
+    const T* src = rowbase + xoff + c;
+    typename V16<T>::raw_t h[3];
 #pragma unroll
-    for (int k = 0; k < CONV_TS; ++k) {
-      const int s = s0 + k;
-      V16<T>::unpack(raw[k + 3], cur);
+    for (int k = 0; k < 3; ++k) {
+      const int s = sb - 3 + k;
+      h[k] = s >= 0 ? V16<T>::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : V16<T>::zero();
+    }
+    float win[3][VN];
+    V16<T>::unpack(h[0], win[0]); V16<T>::unpack(h[1], win[1]); V16<T>::unpack(h[2], win[2]);
+    // the next tile's rows are requested before the current tile's arithmetic (register double buffer)
+    typename V16<T>::raw_t nxt[TS];
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        const float pre = bias[i] + w[i][0] * win[0][i] + w[i][1] * win[1][i] + w[i][2] * win[2][i] + w[i][3] * cur[i];
-        o[i] = silu_f(pre);
-        win[0][i] = win[1][i]; win[1][i] = win[2][i]; win[2][i] = cur[i];
+    for (int k = 0; k < TS; ++k)
+      nxt[k] = (sb + k < L) ? V16<T>::ldg(src + (long long)scan_to_nat(dir, sb + k, len) * ldz) : V16<T>::zero();
+#pragma unroll 2
+    for (int tile = 0; tile < NTILE; ++tile) {
+      const int s0 = sb + tile * TS;
+      if (s0 >= L) break;
+      typename V16<T>::raw_t raw[TS];
+#pragma unroll
+      for (int k = 0; k < TS; ++k) raw[k] = nxt[k];
+      if (tile + 1 < NTILE) {
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+          const int s = s0 + TS + k;
+          nxt[k] = (s < L) ? V16<T>::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : V16<T>::zero();
+        }
       }
-      if (s < s1) V16<T>::st(xconv + ((long long)dir * T_ + (long long)bi * L + s) * C + c, V16<T>::pack(o));
+#pragma unroll
+      for (int k = 0; k < TS; ++k) {
+        float cur[VN], o[VN];
+        V16<T>::unpack(raw[k], cur);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          const float pre = bias[i] + w[i][0] * win[0][i] + w[i][1] * win[1][i] + w[i][2] * win[2][i] + w[i][3] * cur[i];
+          o[i] = pre * sigmoid_t<T>(pre);
+          win[0][i] = win[1][i]; win[1][i] = win[2][i]; win[2][i] = cur[i];
+        }
+        if (s0 + k < L) V16<T>::st(xconv + (sbase + s0 + k) * C + c, V16<T>::pack(o));
+      }
     }
   }
-  for (int idx = threadIdx.x; idx < (s1 - s0) * H; idx += blockDim.x) {
-    const int s = s0 + idx / H, h = idx % H;
-    const float raw = to_f(rowbase[(long long)scan_to_nat(dir, s, len) * ldz + doff + h]);
-    dt_out[((long long)dir * T_ + (long long)bi * L + s) * H + h] = softplus_f(raw + dt_bias[dir * H + h]);
+  if (blockIdx.x == 0) {                                  // dt = softplus(raw + bias): H values per row, one column block does it
+    const int s_lo = blockIdx.y * CONV_SEG * RUN, s_hi = min(s_lo + CONV_SEG * RUN, L);
+    for (int idx = threadIdx.x; idx < (s_hi - s_lo) * H; idx += blockDim.x) {
+      const int s = s_lo + idx / H, hh = idx % H;
+      const float raw = to_f(rowbase[(long long)scan_to_nat(dir, s, len) * ldz + doff + hh]);
+      dt_out[(sbase + s) * H + hh] = softplus_f(raw + dt_bias[dir * H + hh]);
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d, bool vec) {
+  if (vec) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  } else {
+    atomicAdd(p, a); atomicAdd(p + 1, b); atomicAdd(p + 2, c); atomicAdd(p + 3, d);
   }
 }
 
 // backward.  dout[s] for channel c comes from dxc (c < di) or dBC (c >= di), both of the activation dtype; the
 // pre-activation is recomputed from zxbcdt.  d input[s'] = sum_j w[j] dpre[s'+3-j];  dw[j] = sum_s dpre[s] in[s-3+j].
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
+// A segment owns RUN = TS*NTILE - 3 positions: its last 3 tile positions recompute the dpre halo of the next segment.
+template <typename T, int TS, int NTILE, int MINB = 2>
+__global__ void __launch_bounds__(CONV_CT * CONV_SEG, MINB)
 conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long ldz, long long dstride,
                 const T* __restrict__ dBC, const float* __restrict__ ddt, const int* __restrict__ lengths,
                 const float* __restrict__ conv_w, const float* __restrict__ conv_b, const float* __restrict__ dt_bias,
                 int ndir, int B, int L, int di, int N, int H, T* __restrict__ dzx, float* __restrict__ dconv_w,
-                float* __restrict__ dconv_b, float* __restrict__ ddt_bias) {
+                float* __restrict__ dconv_b, float* __restrict__ ddt_bias, int vec_red) {
   constexpr int VN = V16<T>::N;
-  constexpr int TS = CONV_TSB;
+  constexpr int RUN = TS * NTILE - 3;
+  static_assert(VN == 4 && TS > 3, "layout");
+  __shared__ float s_red[CONV_SEG - 1][20][CONV_CT];      // parameter-gradient partials of segments 1..3
   __shared__ float s_dtb[64];
-  const int dir = blockIdx.z, bi = blockIdx.y;
+  const int ct = threadIdx.x % CONV_CT, sg = threadIdx.x / CONV_CT;
+  const int dir = blockIdx.z / B, bi = blockIdx.z % B;
   const int C = di + 2 * N;
   const long long T_ = (long long)B * L;
   const int len = lengths ? lengths[bi] : L;
@@ -122,67 +175,86 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
   const T* rowbase = zx + (long long)bi * L * ldz;
   T* drowbase = dzx + (long long)bi * L * ldz;
   const long long sbase = (long long)dir * T_ + (long long)bi * L;
-  const int ntiles = (L + TS - 1) / TS;
+  const int c = (blockIdx.x * CONV_CT + ct) * VN;
+  const int sb = (blockIdx.y * CONV_SEG + sg) * RUN;
+  const int se = min(sb + RUN, L);
   if (threadIdx.x < 64) s_dtb[threadIdx.x] = 0.f;
-  __syncthreads();
 
-  for (int c = threadIdx.x * VN; c < C; c += blockDim.x * VN) {
-    float w[VN][4], bias[VN], gw[VN][4], gb[VN];
+  float gw[VN][4], gb[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) { gw[i][0] = gw[i][1] = gw[i][2] = gw[i][3] = 0.f; gb[i] = 0.f; }
+  if (c < C && sb < L) {
+    float w[VN][4], bias[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(conv_w + ((long long)dir * C + c + i) * 4));
       w[i][0] = t.x; w[i][1] = t.y; w[i][2] = t.z; w[i][3] = t.w;
       bias[i] = __ldg(conv_b + (long long)dir * C + c + i);
-      gw[i][0] = gw[i][1] = gw[i][2] = gw[i][3] = 0.f; gb[i] = 0.f;
     }
     const bool is_x = c < di;
     const T* gsrc = is_x ? dxc + sbase * di + c : dBC + sbase * (2 * N) + (c - di);
     const long long gld = is_x ? di : 2 * N;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int s0 = tile * TS;
-      const int s1 = min(s0 + TS, L);
-      typename V16<T>::raw_t xr[TS + 6], gr[TS + 3];
+    const T* src = rowbase + xoff + c;
+    T* dst = drowbase + xoff + c;
+    typename V16<T>::raw_t h[3];
 #pragma unroll
-      for (int k = 0; k < TS + 6; ++k) {                               // inputs at s0-3 .. s0+TS+2
-        const int s = s0 - 3 + k;
-        xr[k] = (s >= 0 && s < L) ? V16<T>::ldg(rowbase + (long long)scan_to_nat(dir, s, len) * ldz + xoff + c)
-                                  : V16<T>::zero();
+    for (int k = 0; k < 3; ++k) {
+      const int s = sb - 3 + k;
+      h[k] = s >= 0 ? V16<T>::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : V16<T>::zero();
+    }
+    float win[3][VN], dp[3][VN];
+    V16<T>::unpack(h[0], win[0]); V16<T>::unpack(h[1], win[1]); V16<T>::unpack(h[2], win[2]);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { dp[0][i] = 0.f; dp[1][i] = 0.f; dp[2][i] = 0.f; }
+    typename V16<T>::raw_t xn[TS], gn[TS];                              // register double buffer (see forward)
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+      const bool ok = sb + k < L;
+      xn[k] = ok ? V16<T>::ldg(src + (long long)scan_to_nat(dir, sb + k, len) * ldz) : V16<T>::zero();
+      gn[k] = ok ? V16<T>::ldg(gsrc + (long long)(sb + k) * gld) : V16<T>::zero();
+    }
+#pragma unroll 2
+    for (int tile = 0; tile < NTILE; ++tile) {
+      const int s0 = sb + tile * TS;
+      if (s0 >= se + 3) break;
+      const bool first = tile == 0, last = tile == NTILE - 1;
+      typename V16<T>::raw_t xr[TS], gr[TS];
+#pragma unroll
+      for (int k = 0; k < TS; ++k) { xr[k] = xn[k]; gr[k] = gn[k]; }
+      if (!last) {
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+          const int s = s0 + TS + k;
+          const bool ok = s < L;
+          xn[k] = ok ? V16<T>::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : V16<T>::zero();
+          gn[k] = ok ? V16<T>::ldg(gsrc + (long long)s * gld) : V16<T>::zero();
+        }
       }
 #pragma unroll
-      for (int k = 0; k < TS + 3; ++k) {                               // upstream grads at s0 .. s0+TS+2
-        const int s = s0 + k;
-        gr[k] = (s < L) ? V16<T>::ldg(gsrc + (long long)s * gld) : V16<T>::zero();
-      }
-      float win[3][VN], dp[3][VN];
-      V16<T>::unpack(xr[0], win[0]); V16<T>::unpack(xr[1], win[1]); V16<T>::unpack(xr[2], win[2]);
-#pragma unroll
-      for (int i = 0; i < VN; ++i) { dp[0][i] = 0.f; dp[1][i] = 0.f; dp[2][i] = 0.f; }
-#pragma unroll
-      for (int k = 0; k < TS + 3; ++k) {
+      for (int k = 0; k < TS; ++k) {
         const int s = s0 + k;
         float cur[VN], g[VN], dcur[VN];
-        V16<T>::unpack(xr[k + 3], cur);
+        V16<T>::unpack(xr[k], cur);
         V16<T>::unpack(gr[k], g);
+        const bool own = !(k >= TS - 3 && last);                        // halo positions belong to the next segment
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
           const float pre = bias[i] + w[i][0] * win[0][i] + w[i][1] * win[1][i] + w[i][2] * win[2][i] + w[i][3] * cur[i];
-          const float sg = sigmoid_f(pre);
-          dcur[i] = g[i] * sg * (1.f + pre * (1.f - sg));               // g is zero beyond L
-          if (k < TS && s < s1) {                                       // parameter grads: the tile's own positions
+          const float sgm = sigmoid_t<T>(pre);
+          dcur[i] = g[i] * sgm * (1.f + pre * (1.f - sgm));             // g is zero beyond L
+          if (own) {
             gw[i][0] += dcur[i] * win[0][i]; gw[i][1] += dcur[i] * win[1][i];
             gw[i][2] += dcur[i] * win[2][i]; gw[i][3] += dcur[i] * cur[i];
             gb[i] += dcur[i];
           }
         }
-        if (k >= 3) {                                                   // d input at sp = s - 3 is complete
-          const int sp = s - 3;
-          if (sp < s1) {
-            float o[VN];
+        const int sp = s - 3;                                           // d input at sp is complete
+        if (!(k < 3 && first) && sp < se) {
+          float o[VN];
 #pragma unroll
-            for (int i = 0; i < VN; ++i)
-              o[i] = w[i][3] * dp[0][i] + w[i][2] * dp[1][i] + w[i][1] * dp[2][i] + w[i][0] * dcur[i];
-            V16<T>::st(drowbase + (long long)scan_to_nat(dir, sp, len) * ldz + xoff + c, V16<T>::pack(o));
-          }
+          for (int i = 0; i < VN; ++i)
+            o[i] = w[i][3] * dp[0][i] + w[i][2] * dp[1][i] + w[i][1] * dp[2][i] + w[i][0] * dcur[i];
+          V16<T>::st(dst + (long long)scan_to_nat(dir, sp, len) * ldz, V16<T>::pack(o));
         }
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
@@ -191,29 +263,46 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
         }
       }
     }
+  }
+  // parameter gradients: segments 1..3 -> shared memory -> segment 0 adds and issues 5 vector reductions per thread
+  if (sg > 0) {
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
-      float* gwp = dconv_w + ((long long)dir * C + c + i) * 4;
-      atomicAdd(gwp + 0, gw[i][0]); atomicAdd(gwp + 1, gw[i][1]);
-      atomicAdd(gwp + 2, gw[i][2]); atomicAdd(gwp + 3, gw[i][3]);
-      atomicAdd(dconv_b + (long long)dir * C + c + i, gb[i]);
-    }
-  }
-  // dt: d raw = ddt * sigmoid(raw + bias)
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int s0 = tile * TS;
-    const int s1 = min(s0 + TS, L);
-    for (int idx = threadIdx.x; idx < (s1 - s0) * H; idx += blockDim.x) {
-      const int s = s0 + idx / H, h = idx % H;
-      const long long nat = (long long)scan_to_nat(dir, s, len) * ldz + doff + h;
-      const float raw = to_f(rowbase[nat]);
-      const float g = ddt[(sbase + s) * H + h] * sigmoid_f(raw + dt_bias[dir * H + h]);
-      drowbase[nat] = from_f<T>(g);
-      atomicAdd(&s_dtb[h], g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_red[sg - 1][i * 4 + j][ct] = gw[i][j];
+      s_red[sg - 1][16 + i][ct] = gb[i];
     }
   }
   __syncthreads();
-  if (threadIdx.x < H) atomicAdd(ddt_bias + dir * H + threadIdx.x, s_dtb[threadIdx.x]);
+  if (sg == 0 && c < C) {
+#pragma unroll
+    for (int q = 0; q < CONV_SEG - 1; ++q) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gw[i][j] += s_red[q][i * 4 + j][ct];
+        gb[i] += s_red[q][16 + i][ct];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i)
+      red_add4(dconv_w + ((long long)dir * C + c + i) * 4, gw[i][0], gw[i][1], gw[i][2], gw[i][3], vec_red);
+    red_add4(dconv_b + (long long)dir * C + c, gb[0], gb[1], gb[2], gb[3], vec_red);
+  }
+  // dt: d raw = ddt * sigmoid(raw + bias); one column block per (row, segment group) does it
+  if (blockIdx.x == 0) {
+    const int s_lo = blockIdx.y * CONV_SEG * RUN, s_hi = min(s_lo + CONV_SEG * RUN, L);
+    for (int idx = threadIdx.x; idx < (s_hi - s_lo) * H; idx += blockDim.x) {
+      const int s = s_lo + idx / H, hh = idx % H;
+      const long long nat = (long long)scan_to_nat(dir, s, len) * ldz + doff + hh;
+      const float raw = to_f(rowbase[nat]);
+      const float g = ddt[(sbase + s) * H + hh] * sigmoid_f(raw + dt_bias[dir * H + hh]);
+      drowbase[nat] = from_f<T>(g);
+      atomicAdd(&s_dtb[hh], g);
+    }
+    __syncthreads();
+    if (threadIdx.x < H) atomicAdd(ddt_bias + dir * H + threadIdx.x, s_dtb[threadIdx.x]);
+  }
 }
 
 }  // namespace hnb
@@ -234,10 +323,8 @@ static int conv_check(const char* who, int dtype, long long ldz, long long dstri
   return HNB_OK;
 }
 
-static int conv_threads(int C, int vn) {
-  int t = (C / vn + 31) / 32 * 32;
-  return t > 256 ? 256 : (t < 32 ? 32 : t);
-}
+constexpr int CONV_F_TS = 4, CONV_F_NT = 4;      // forward: 16 positions per segment
+constexpr int CONV_B_TS = 4, CONV_B_NT = 8;      // backward: 29 positions per segment (+3 recomputed halo)
 
 extern "C" int hnb_conv_fwd(const void* zxbcdt, int dtype, long long ldz, long long dstride, const int32_t* lengths,
                             const float* conv_w, const float* conv_b, const float* dt_bias, int ndir, int B, int L,
@@ -245,15 +332,16 @@ extern "C" int hnb_conv_fwd(const void* zxbcdt, int dtype, long long ldz, long l
   HNB_CHECK_ARG(zxbcdt && conv_w && conv_b && dt_bias && xconv && dt, "conv_fwd: null pointer");
   int rc = conv_check("conv_fwd", dtype, ldz, dstride, ndir, B, L, di, N, H);
   if (rc) return rc;
-  dim3 grid(cdiv(L, CONV_TS), B, ndir);
-  cudaStream_t st = (cudaStream_t)stream;
   const int C = di + 2 * N;
+  dim3 grid(cdiv(C / 4, CONV_CT), cdiv(L, CONV_SEG * CONV_F_TS * CONV_F_NT), ndir * B);
+  cudaStream_t st = (cudaStream_t)stream;
   if (dtype == HNB_BF16)
-    conv_fwd_kernel<__nv_bfloat16><<<grid, conv_threads(C, 4), 0, st>>>((const __nv_bfloat16*)zxbcdt, ldz, dstride,
-        lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)xconv, dt);
+    conv_fwd_kernel<__nv_bfloat16, CONV_F_TS, CONV_F_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+        (const __nv_bfloat16*)zxbcdt, ldz, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H,
+        (__nv_bfloat16*)xconv, dt);
   else if (dtype == HNB_F32)
-    conv_fwd_kernel<float><<<grid, conv_threads(C, 4), 0, st>>>((const float*)zxbcdt, ldz, dstride, lengths, conv_w,
-        conv_b, dt_bias, ndir, B, L, di, N, H, (float*)xconv, dt);
+    conv_fwd_kernel<float, CONV_F_TS, CONV_F_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt, ldz, dstride,
+        lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (float*)xconv, dt);
   else { set_error("conv_fwd: unsupported dtype"); return HNB_ERR_INVALID_ARG; }
   HNB_LAUNCH_CHECK("conv_fwd");
   return HNB_OK;
@@ -267,18 +355,23 @@ extern "C" int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long
                 "conv_bwd: null pointer");
   int rc = conv_check("conv_bwd", dtype, ldz, dstride, ndir, B, L, di, N, H);
   if (rc) return rc;
-  const int ntiles = cdiv(L, CONV_TSB);
-  dim3 grid(ntiles < CONV_GX ? ntiles : CONV_GX, B, ndir);
-  cudaStream_t st = (cudaStream_t)stream;
   const int C = di + 2 * N;
-  if (dtype == HNB_BF16)
-    conv_bwd_kernel<__nv_bfloat16><<<grid, conv_threads(C, 4), 0, st>>>((const __nv_bfloat16*)zxbcdt,
-        (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths, conv_w, conv_b, dt_bias, ndir,
-        B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias);
+  dim3 grid(cdiv(C / 4, CONV_CT), cdiv(L, CONV_SEG * (CONV_B_TS * CONV_B_NT - 3)), ndir * B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vec = ((reinterpret_cast<uintptr_t>(dconv_w) | reinterpret_cast<uintptr_t>(dconv_b)) & 15) == 0;
+  static const int variant = getenv("HNB_CONV_BWD_VARIANT") ? atoi(getenv("HNB_CONV_BWD_VARIANT")) : 0;   // tuning knob
+  if (dtype == HNB_BF16 && variant == 1)
+    conv_bwd_kernel<__nv_bfloat16, 8, 4, 2><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+        (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
+        conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
+  else if (dtype == HNB_BF16)
+    conv_bwd_kernel<__nv_bfloat16, CONV_B_TS, CONV_B_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+        (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
+        conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
   else if (dtype == HNB_F32)
-    conv_bwd_kernel<float><<<grid, conv_threads(C, 4), 0, st>>>((const float*)zxbcdt, (const float*)dxc, ldz, dstride,
-        (const float*)dBC, ddt, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (float*)dzxbcdt, dconv_w,
-        dconv_b, ddt_bias);
+    conv_bwd_kernel<float, CONV_B_TS, CONV_B_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt,
+        (const float*)dxc, ldz, dstride, (const float*)dBC, ddt, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H,
+        (float*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
   else { set_error("conv_bwd: unsupported dtype"); return HNB_ERR_INVALID_ARG; }
   HNB_LAUNCH_CHECK("conv_bwd");
   return HNB_OK;

@@ -1,11 +1,22 @@
 // LayerNorm (pre-norm / final norm of MambaBlock / MambaStack) and the mixer's gated RMSNorm.
 // One warp per row; rows are short (d_model 384..768, d_inner 768..1536) so a row lives in L1 and is
 // re-read for the second moment instead of being held in a variable-size register array.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace hnb {
 
 constexpr int NORM_WARPS = 8;
+
+// sigmoid of the gate: fp32 activations keep ex2 + rcp; bf16 activations take one MUFU (tanh.approx, abs. error
+// ~5e-4, below the bf16 rounding of the values it multiplies)
+template <typename T> __device__ __forceinline__ float sigmoid_t(float x) { return sigmoid_f(x); }
+template <> __device__ __forceinline__ float sigmoid_t<__nv_bfloat16>(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm forward
@@ -144,7 +155,7 @@ gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long lo
     float a[VN], z[VN];
     ldv<T, VN>(yr + c, a); ldv<T, VN>(zr + c, z);
 #pragma unroll
-    for (int i = 0; i < VN; ++i) { const float g = a[i] * silu_f(z[i]); q += g * g; }
+    for (int i = 0; i < VN; ++i) { const float g = a[i] * z[i] * sigmoid_t<T>(z[i]); q += g * g; }
   }
   const float rs = rsqrtf(warp_sum(q) / di + eps);
   if (lane == 0) rstd_out[(long long)dir * T_ + tok] = rs;
@@ -154,7 +165,7 @@ gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long lo
     float a[VN], z[VN], ww[VN];
     ldv<T, VN>(yr + c, a); ldv<T, VN>(zr + c, z); ldv<float, VN>(wr + c, ww);
 #pragma unroll
-    for (int i = 0; i < VN; ++i) a[i] = a[i] * silu_f(z[i]) * rs * ww[i];
+    for (int i = 0; i < VN; ++i) a[i] = a[i] * z[i] * sigmoid_t<T>(z[i]) * rs * ww[i];
     stv<T, VN>(o + c, a);
   }
 }
@@ -194,7 +205,7 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
         float yv[VN], zv[VN], go[VN], ww[VN];
         ldv<T, VN>(y + yoff + c, yv); ldv<T, VN>(zr + c, zv); ldv<T, VN>(gr + c, go); ldv<float, VN>(wr + c, ww);
 #pragma unroll
-        for (int i = 0; i < VN; ++i) s2 += go[i] * ww[i] * yv[i] * silu_f(zv[i]) * rs;
+        for (int i = 0; i < VN; ++i) s2 += go[i] * ww[i] * yv[i] * zv[i] * sigmoid_t<T>(zv[i]) * rs;
       }
     }
     s2 = warp_sum(s2) / di;
@@ -206,7 +217,7 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
         ldv<T, VN>(y + yoff + c, yv); ldv<T, VN>(zr + c, zv); ldv<T, VN>(gr + c, go); ldv<float, VN>(wr + c, ww);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          const float sg = sigmoid_f(zv[i]);
+          const float sg = sigmoid_t<T>(zv[i]);
           const float gh = yv[i] * zv[i] * sg * rs;                  // normalised gated value
           aw[k][i] += go[i] * gh;
           const float dg = rs * (go[i] * ww[i] - gh * s2);
@@ -300,9 +311,15 @@ extern "C" int hnb_layernorm_fwd(const void* x, int x_dtype, const float* gamma,
   return HNB_OK;
 }
 
-static int norm_grid(long long rows) {
-  int g = cdiv(rows, NORM_WARPS);
-  return g < 148 * 4 ? g : 148 * 4;                                 // 4 resident CTAs per SM, grid-stride over rows
+// grid-stride kernels: exactly one wave of resident CTAs (a partial second wave would cost a full one)
+template <typename K>
+static int norm_grid(K kernel, long long rows, size_t smem) {
+  int dev = 0, sms = 148, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NORM_WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 2;
+  const int g = cdiv(rows, NORM_WARPS), cap = sms * occ;
+  return g < cap ? g : cap;
 }
 
 extern "C" int hnb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
@@ -311,15 +328,14 @@ extern "C" int hnb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, in
   HNB_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0 && d > 0,
                 "layernorm_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = norm_grid(rows);
   const bool v4 = d % 4 == 0 && al(x, 4 * esz(x_dtype)) && al(dy, 4 * esz(dy_dtype)) && al(dx, 4 * esz(dx_dtype)) &&
                   (!dres || al(dres, 4 * esz(dx_dtype))) && al(gamma, 16);
   const int vn = v4 ? 4 : 1;
   const int nv = cdiv(d, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "layernorm_bwd: d=%d too large", d);
   const size_t smem = 2 * (size_t)d * sizeof(float);
-#define RUN2(A, Bx, C, VN, NV) layernorm_bwd_kernel<A, Bx, C, VN, NV><<<grid, NORM_WARPS * 32, smem, st>>>( \
-      (const A*)dy, (const Bx*)x, gamma, mean, rstd, (const C*)dres, rows, d, (C*)dx, dgamma, dbeta)
+#define RUN2(A, Bx, C, VN, NV) layernorm_bwd_kernel<A, Bx, C, VN, NV><<<norm_grid(layernorm_bwd_kernel<A, Bx, C, VN, NV>, rows, smem), \
+      NORM_WARPS * 32, smem, st>>>((const A*)dy, (const Bx*)x, gamma, mean, rstd, (const C*)dres, rows, d, (C*)dx, dgamma, dbeta)
 #define RUN(A, Bx, C, VN)                                                                  \
   do {                                                                                     \
     if (nv <= 2) RUN2(A, Bx, C, VN, 2); else if (nv <= 3) RUN2(A, Bx, C, VN, 3);           \
@@ -363,9 +379,6 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
   HNB_CHECK_ARG(ndir >= 1 && ndir <= 2 && B > 0 && L > 0 && di > 0, "gated_norm_bwd: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)B * L;
-  int gx = norm_grid(rows) / ndir;
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, ndir);
   const bool v4 = di % 4 == 0 && ldz % 4 == 0 && dstride % 4 == 0 && al(y, 4 * esz(dtype)) && al(zxbcdt, 4 * esz(dtype)) &&
                   al(dout, 4 * esz(dtype)) && al(dy, 4 * esz(dtype)) && al(dzxbcdt, 4 * esz(dtype)) && al(norm_w, 16);
   const bool v8 = dtype == HNB_BF16 && di % 8 == 0 && ldz % 8 == 0 && dstride % 8 == 0 && al(y, 16) && al(zxbcdt, 16) &&
@@ -374,8 +387,8 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
   const int nv = cdiv(di, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "gated_norm_bwd: d_inner=%d too large", di);
   const size_t smem = (size_t)di * sizeof(float);
-#define RUN2(T, VN, NV) gated_norm_bwd_kernel<T, VN, NV><<<grid, NORM_WARPS * 32, smem, st>>>( \
-      (const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w)
+#define RUN2(T, VN, NV) gated_norm_bwd_kernel<T, VN, NV><<<dim3(std::max(1, norm_grid(gated_norm_bwd_kernel<T, VN, NV>, rows * ndir, smem) / ndir), ndir), \
+      NORM_WARPS * 32, smem, st>>>((const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w)
 #define RUN(T, VN)                                                             \
   do {                                                                         \
     if (nv <= 1) RUN2(T, VN, 1); else if (nv <= 2) RUN2(T, VN, 2);             \

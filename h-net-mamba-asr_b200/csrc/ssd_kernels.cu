@@ -546,11 +546,14 @@ static size_t ssd_states_floats(int ndir, int B, int L, int H) {
 
 extern "C" int hnb_ssd_chunk(void) { return SQ; }
 
+long long hnb_ssd_tc_ws_bytes(int ndir, int B, int L, int H);
+
 extern "C" long long hnb_ssd_ws_bytes(int ndir, int B, int L, int di, int N, int H) {
   (void)di; (void)N;
   const int nc = cdiv(L, SQ);
   const size_t fl = ssd_states_floats(ndir, B, L, H) + (size_t)ndir * B * H * nc + 2 * (size_t)ndir * B * L * H + 64;
-  return (long long)(fl * sizeof(float));
+  const long long exact = (long long)(fl * sizeof(float)), tc = hnb_ssd_tc_ws_bytes(ndir, B, L, H);
+  return exact > tc ? exact : tc;                       // one size serves both implementations
 }
 
 static int ssd_check(const char* who, int ndir, int B, int L, int di, int N, int H) {

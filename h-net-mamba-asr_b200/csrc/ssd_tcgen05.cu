@@ -40,7 +40,7 @@ constexpr int BWD_THREADS = 512;          // dx / dbc
 constexpr int HALF = TQ * 128;          // bytes of one [128 rows x 128 B] swizzled block (16 KB)
 constexpr int TAB_FLOATS = 9 * TQ + 8;  // cs, dt, w, ecs, eq [128 each] | f[4][128] | warp totals
 constexpr int TAB_BYTES = TAB_FLOATS * 4;
-constexpr int EXTRA_FLOATS = 2 * TQ + 8;
+constexpr int EXTRA_FLOATS = 12 * TQ + 3 * 16 + 8;   // dx kernel: per-column-group partial sums (no shared-memory atomics)
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk16) {          // byte offset inside a [rows x 128 B] SW128 block
   return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
@@ -102,6 +102,21 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int 
   named_sync(1, nt);
 }
 
+// The tables of every (row, head, chunk), built ONCE per forward and kept in the workspace: the forward and the three
+// backward kernels fetch them with one 1-D bulk copy next to their TMA tile loads, so no scan / exp / barrier for
+// them sits on a kernel's critical path any more.
+__global__ void __launch_bounds__(TQ)
+ssd_tables_kernel(const float* __restrict__ dt, const float* __restrict__ A_log, float* __restrict__ tables, int B, int L,
+                  int H, int nc) {
+  __shared__ float tab[TAB_FLOATS];
+  const int item = blockIdx.x;                                        // ((db * H) + h) * nc + c
+  const int c = item % nc, h = (item / nc) % H, db = item / (nc * H), dir = db / B;
+  const int q0 = c * TQ;
+  build_tables(dt + ((long long)db * L + q0) * H + h, H, min(TQ, L - q0), -__expf(A_log[dir * H + h]), tab, TQ);
+  float* out = tables + (long long)item * TAB_FLOATS;
+  for (int i = threadIdx.x; i < 9 * TQ; i += TQ) out[i] = tab[i];
+}
+
 // decay factors l[j] = L[t, s0+j] (j < 32) of row t (row block I) against column block J <= I.  The case split is
 // warp-uniform and sits OUTSIDE the element loop.
 __device__ __forceinline__ void decay_row32(float* l, int t, int I, int J, int s0, const float* tab) {
@@ -136,6 +151,7 @@ struct FwdParams {
   const float* Dskip;     // [ndir, H]
   __nv_bfloat16* y;       // [ndir*B*L, di]
   __nv_bfloat16* states;  // [ndir*B, H, nc, 128(n), 64(p)]  state ENTERING each chunk
+  const float* tables;    // [ndir*B, H, nc, TAB_FLOATS]
   int ndirB, B, L, H, di, nc;
 };
 
@@ -144,7 +160,7 @@ __global__ void __launch_bounds__(NT, 1)
 ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   constexpr int NCG = NT / 128;           // column groups: warp w -> TMEM lane quarter w%4, column group w/4
   constexpr int NB = 4 / NCG;             // 32-column blocks (of 128) and 16-column blocks (of 64) per thread
-  constexpr int NTAB = NT - 32;           // table builders: every warp but the last, which issues the MMAs
+  constexpr int NTAB = NT - 32;           // lane 0 of the last warp issues TMA and MMAs
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* base = smem_raw;                               // (no integer round trip: keeps the .shared address space)
   uint8_t* sC = base + OFF_C; uint8_t* sB = base + OFF_B; uint8_t* sX = base + OFF_X; uint8_t* sXw = base + OFF_XW;
@@ -159,7 +175,6 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   const int lq = warp & 3, cg = warp >> 2;
   const int row = lq * 32 + lane;
   const bool issuer = tid == NTAB;                   // lane 0 of the last warp: TMA + MMA issue
-  const bool tabber = tid < NTAB;
 
   if (tid == 0) {
     umma::prefetch_tmap(&tmX);
@@ -181,25 +196,17 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
 
   auto issue_load = [&](int item, int c, int buf) {                 // issuer only
     const int db = item / H, h = item % H;
-    umma::mbar_expect_tx(bar_load, 5 * HALF);
+    umma::mbar_expect_tx(bar_load, 5 * HALF + TAB_BYTES);
+    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(item * nc + c) * TAB_FLOATS, TAB_BYTES, bar_load);
     umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
     umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
     umma::tma_load_3d(sB, &tmX, bar_load, di, c * TQ, db);
     umma::tma_load_3d(sB + HALF, &tmX, bar_load, di + 64, c * TQ, db);
     umma::tma_load_3d(sX + buf * HALF, &tmX, bar_load, h * TP, c * TQ, db);
   };
-  auto tables_for = [&](int item, int c, float* tab) {              // tabber threads
-    const int db = item / H, h = item % H, dir = db / p.B;
-    const int q0 = c * TQ;
-    build_tables(p.dt + ((long long)db * L + q0) * H + h, H, min(TQ, L - q0), -__expf(p.A_log[dir * H + h]), tab, NTAB);
-  };
 
   uint32_t seq = 0;                                                   // (item, chunk) sequence number of this CTA
-  if (blockIdx.x < n_items) {
-    if (issuer) issue_load(blockIdx.x, 0, 0);
-    if (tabber) tables_for(blockIdx.x, 0, tabs);
-  }
-  __syncthreads();
+  if (blockIdx.x < n_items && issuer) issue_load(blockIdx.x, 0, 0);
 
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int db = it / H, h = it % H, dir = db / p.B;
@@ -215,6 +222,8 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       const float* tab = tabs + buf * TAB_FLOATS;
       const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
       const int q0 = c * TQ, qv = min(TQ, L - q0);
+      const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;           // 32-row blocks / 16-row k-steps holding valid frames
+      const bool last_chunk = c == nc - 1;                             // nothing consumes the state leaving it
       const long long row0 = (long long)db * L + q0;
       int nit = it, ncn = c + 1;                                       // the step after this one
       if (ncn == nc) { nit = it + gridDim.x; ncn = 0; }
@@ -235,7 +244,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
         umma::mma_commit(bar_g);
       }
       // Xw = w_s * X (same swizzled positions: the swizzle permutes 16-byte chunks inside a row only)
-      for (int i = tid; i < TQ * 8; i += NT) {
+      if (!last_chunk) for (int i = tid; i < TQ * 8; i += NT) {
         const float w = s_w[i >> 3];
         float v[8];
         unpack8(reinterpret_cast<const uint4*>(sX + buf * HALF)[i], v);
@@ -249,6 +258,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {
         const int t = row, I = t >> 5, J = NB * cg + bb, s0 = 32 * J;
+        if (I >= nblk) break;                                          // padding rows: their M rows only feed unused y rows
         float g[32];
         if (J <= I) {
           umma::tmem_ld32(t_lane + (uint32_t)s0, g);
@@ -271,10 +281,11 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {                               // Yd = M X
+        for (int kb = 0; kb < 8; ++kb) {                               // Yd = M X   (k = time: valid frames only)
           const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
-          umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sM) + o, 16, 1024),
-                            umma::make_smem_desc(umma::smem_u32(sX + buf * HALF) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
+          if (kb < nkb)
+            umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sM) + o, 16, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sX + buf * HALF) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
         }
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {                               // Yo = C S_in
@@ -282,14 +293,16 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
           umma::mma_bf16_ss(tmem + 192, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
                             umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
         }
+        if (!last_chunk) {
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {                               // dS = B^T (w o X)
-          umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024),
-                            umma::make_smem_desc(umma::smem_u32(sXw) + kb * 2048, 1024, 1024), idesc_s, kb > 0);
+          for (int kb = 0; kb < 8; ++kb) {                             // dS = B^T (w o X)
+            if (kb < nkb)
+              umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024),
+                                umma::make_smem_desc(umma::smem_u32(sXw) + kb * 2048, 1024, 1024), idesc_s, kb > 0);
+          }
         }
         umma::mma_commit(bar_y);
       }
-      if (tabber && nit < n_items) tables_for(nit, ncn, tabs + (buf ^ 1) * TAB_FLOATS);   // while the MMAs are issued and run
       umma::mbar_wait(bar_y, par);
       umma::tc_fence_after();
       if (issuer && nit < n_items) issue_load(nit, ncn, buf ^ 1);      // C, B and the other X buffer are free
@@ -297,6 +310,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {
         const int t = row, c16 = NB * cg + bb;                         // 16-column block of the 64
+        if ((t >> 5) >= nblk) break;
         float yd[16], yo[16];
         umma::tmem_ld16(t_lane + 128u + 16u * c16, yd);
         umma::tmem_ld16(t_lane + 192u + 16u * c16, yo);
@@ -315,7 +329,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
         }
       }
       // ---- epilogue 3: S = e^{cs_last} S + dS  (thread = state row n)
-      {
+      if (!last_chunk) {
         const float decay = s_ecs[TQ - 1];
 #pragma unroll
         for (int bb = 0; bb < NB; ++bb) {
@@ -344,6 +358,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
 // ===================================================================================================
 struct BwdParams {
   const float* dt; const float* A_log; const float* Dskip;
+  const float* tables;           // [ndir*B, H, nc, TAB_FLOATS]  (built by the forward)
   __nv_bfloat16* gstates;        // [ndir*B, H, nc, 128, 64]
   __nv_bfloat16* dxc;            // [ndir*B*L, di]
   __nv_bfloat16* dBC;            // [ndir*B*L, 2N]
@@ -356,7 +371,7 @@ struct BwdParams {
 // ---- 1. dstate (256 threads, 2 CTAs per SM) -----------------------------------------------------------
 constexpr int D1_THREADS = 256;
 constexpr int D1_OFF_C = 0, D1_OFF_DY = 2 * HALF, D1_OFF_DYS = 3 * HALF, D1_OFF_TAB = 4 * HALF;
-constexpr int D1_OFF_BAR = D1_OFF_TAB + TAB_BYTES;
+constexpr int D1_OFF_BAR = D1_OFF_TAB + 2 * TAB_BYTES;
 constexpr int D1_SMEM = D1_OFF_BAR + 64 + 1024;
 
 __global__ void __launch_bounds__(D1_THREADS, 2)
@@ -365,8 +380,7 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   uint8_t* sC = base + D1_OFF_C; uint8_t* sdY = base + D1_OFF_DY; uint8_t* sdYs = base + D1_OFF_DYS;
-  float* tab = reinterpret_cast<float*>(base + D1_OFF_TAB);
-  const float* s_ecs = tab + 3 * TQ;
+  float* tabs = reinterpret_cast<float*>(base + D1_OFF_TAB);
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + D1_OFF_BAR);
   uint64_t* bar_m = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
@@ -383,26 +397,27 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
   const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * H;
   constexpr uint32_t idesc = umma::make_idesc_bf16(128, 64, 1, 1);
-  auto issue_load = [&](int item, int c) {
+  auto issue_load = [&](int item, int c, int buf) {
     const int db = item / H, h = item % H;
-    umma::mbar_expect_tx(bar_load, 3 * HALF);
+    umma::mbar_expect_tx(bar_load, 3 * HALF + TAB_BYTES);
+    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(item * nc + c) * TAB_FLOATS, TAB_BYTES, bar_load);
     umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
     umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
     umma::tma_load_3d(sdY, &tmDY, bar_load, h * TP, c * TQ, db);
   };
   uint32_t seq = 0;
-  if (blockIdx.x < n_items && tid == 0) issue_load(blockIdx.x, nc - 1);
+  // chunk 0 needs no step of its own: the gradient w.r.t. the (zero) state entering it is never used
+  if (blockIdx.x < n_items && tid == 0 && nc > 1) issue_load(blockIdx.x, nc - 1, 0);
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int db = it / H, h = it % H, dir = db / p.B;
-    const float A = -__expf(p.A_log[dir * H + h]);
+    const int db = it / H, h = it % H;
     float Grun[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) Grun[j] = 0.f;
-    for (int c = nc - 1; c >= 0; --c, ++seq) {
+    for (int c = nc - 1; c >= 1; --c, ++seq) {
       const uint32_t par = seq & 1;
+      const float* s_ecs = tabs + (seq & 1) * TAB_FLOATS + 3 * TQ;
       const int q0 = c * TQ, qv = min(TQ, L - q0);
-      const long long row0 = (long long)db * L + q0;
-      build_tables(p.dt + row0 * H + h, H, qv, A, tab, D1_THREADS);
+      const int nkb = (qv + 15) >> 4;
       {   // gradient w.r.t. the state LEAVING this chunk
         __nv_bfloat16* gg = p.gstates + ((((long long)db * H + h) * nc + c) * TN + row) * TP + 32 * ch;
 #pragma unroll
@@ -421,17 +436,18 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       if (tid == 0) {
         umma::tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb)
-          umma::mma_bf16_ss(tmem, umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024),
-                            umma::make_smem_desc(umma::smem_u32(sdYs) + kb * 2048, 1024, 1024), idesc, kb > 0);
+        for (int kb = 0; kb < 8; ++kb)                                 // k = time: valid frames only
+          if (kb < nkb)
+            umma::mma_bf16_ss(tmem, umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sdYs) + kb * 2048, 1024, 1024), idesc, kb > 0);
         umma::mma_commit(bar_m);
       }
       umma::mbar_wait(bar_m, par);
       umma::tc_fence_after();
       if (tid == 0) {
         int nit = it, ncn = c - 1;
-        if (ncn < 0) { nit = it + gridDim.x; ncn = nc - 1; }
-        if (nit < n_items) issue_load(nit, ncn);
+        if (ncn < 1) { nit = it + gridDim.x; ncn = nc - 1; }
+        if (nit < n_items) issue_load(nit, ncn, (seq & 1) ^ 1);
       }
       float ds[32];
       umma::tmem_ld32(t_lane + 32u * ch, ds);
@@ -440,6 +456,11 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll
       for (int j = 0; j < 32; ++j) Grun[j] = decay * Grun[j] + ds[j];
       umma::tc_fence_before(); __syncthreads();
+    }
+    {   // gradient w.r.t. the state leaving chunk 0
+      __nv_bfloat16* gg = p.gstates + ((((long long)db * H + h) * nc) * TN + row) * TP + 32 * ch;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(gg + 8 * k) = pack8(Grun + 8 * k);
     }
   }
   umma::tc_fence_before(); __syncthreads();
@@ -465,16 +486,22 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint8_t* sdY = base + D2_OFF_DY; uint8_t* sS = base + D2_OFF_S; uint8_t* sG = base + D2_OFF_G;
   uint8_t* sK = base + D2_OFF_K;
   float* tabs = reinterpret_cast<float*>(base + D2_OFF_TAB);
-  float* s_dcs = reinterpret_cast<float*>(base + D2_OFF_EXTRA);    // [128]  d loss / d cs_t
-  float* s_ddtx = s_dcs + TQ;                                       // [128]  <du_q, x_q>
-  float* s_sc = s_ddtx + TQ;                                        // [0] extra d cs_last, [1] dD, [4..7] warp totals
+  // partial sums, one slot per (column group, row) or per warp: shared-memory float atomics are CAS loops
+  float* s_dcsA = reinterpret_cast<float*>(base + D2_OFF_EXTRA);   // [4][128]  d cs_t, row terms (epilogue A)
+  float* s_dcsB = s_dcsA + 4 * TQ;                                  // [4][128]  d cs_q, column terms (epilogue B)
+  float* s_ddtx = s_dcsB + 4 * TQ;                                  // [4][128]  <du_q, x_q>
+  float* s_wdot = s_ddtx + 4 * TQ;                                  // [16] per warp: <Gst, S_in>
+  float* s_wsc = s_wdot + 16;                                       // [16] per warp: d cs_last from the chunk state
+  float* s_wdd = s_wsc + 16;                                        // [16] per warp: dD
+  float* s_tot = s_wdd + 16;                                        // [8]  warp totals of the reverse cumsum
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + D2_OFF_BAR);
   uint64_t* bar1 = bar_load + 1;
   uint64_t* bar2 = bar_load + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
-  const bool issuer = tid == NTAB, tabber = tid < NTAB;
+  const bool issuer = tid == NTAB;
+  static_assert(NCG <= 4 && NT / 32 <= 16, "partial-sum slots");
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
     umma::mbar_init(bar_load, 1); umma::mbar_init(bar1, 1); umma::mbar_init(bar2, 1);
@@ -488,10 +515,11 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr uint32_t idesc_kk128 = umma::make_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t idesc_km64 = umma::make_idesc_bf16(128, 64, 0, 1);
   constexpr uint32_t idesc_mm64 = umma::make_idesc_bf16(128, 64, 1, 1);
-  auto issue_load = [&](int item) {
+  auto issue_load = [&](int item, int buf) {
     const int h = item % H, c = (item / H) % nc, db = item / (H * nc);
     const int srow = (((db * H + h) * nc) + c) * TN;
-    umma::mbar_expect_tx(bar_load, 8 * HALF);
+    umma::mbar_expect_tx(bar_load, 8 * HALF + TAB_BYTES);
+    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(srow / TN) * TAB_FLOATS, TAB_BYTES, bar_load);
     umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
     umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
     umma::tma_load_3d(sB, &tmX, bar_load, di, c * TQ, db);
@@ -501,16 +529,10 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     umma::tma_load_2d(sS, &tmS, bar_load, 0, srow);
     umma::tma_load_2d(sG, &tmG, bar_load, 0, srow);
   };
-  auto tables_for = [&](int item, float* tab) {
-    const int h = item % H, c = (item / H) % nc, db = item / (H * nc), dir = db / p.B;
-    const int q0 = c * TQ;
-    build_tables(p.dt + ((long long)db * L + q0) * H + h, H, min(TQ, L - q0), -__expf(p.A_log[dir * H + h]), tab, NTAB);
-  };
   uint32_t seq = 0;
-  if (blockIdx.x < n_items) {
-    if (issuer) issue_load(blockIdx.x);
-    if (tabber) tables_for(blockIdx.x, tabs);
-  }
+  for (int i = tid; i < 2 * HALF / 16; i += NT) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);   // finite padding rows
+  umma::fence_async_smem();
+  if (blockIdx.x < n_items && issuer) issue_load(blockIdx.x, 0);
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++seq) {
     const uint32_t par = seq & 1;
     const float* tab = tabs + (seq & 1) * TAB_FLOATS;
@@ -519,12 +541,10 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const float A = -__expf(p.A_log[dir * H + h]);
     const float Dh = p.Dskip[dir * H + h];
     const int q0 = c * TQ, qv = min(TQ, L - q0);
+    const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;             // row blocks / k-steps that hold valid frames
     const long long row0 = (long long)db * L + q0;
     const int nit = it + gridDim.x;
     long long tk0 = clock64();
-    if (tid < TQ) { s_dcs[tid] = 0.f; s_ddtx[tid] = 0.f; }
-    if (tid < 2) s_sc[tid] = 0.f;
-    __syncthreads();                                                   // zeroing (and the first tables) visible
     umma::mbar_wait(bar_load, par);
     long long tk1 = clock64();
     if (issuer) {
@@ -547,8 +567,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
       umma::mma_commit(bar1);
     }
-    // while the MMAs are issued and run: tables of the next item, and the decay term e^{cs_last} <Gst, S_in>
-    if (tabber && nit < n_items) tables_for(nit, tabs + ((seq & 1) ^ 1) * TAB_FLOATS);
+    // while the MMAs run: the decay term e^{cs_last} <Gst, S_in>
     {
       float dot = 0.f;
       for (int i = tid; i < TQ * 8; i += NT) {                         // same swizzle on both tiles: elementwise product
@@ -559,14 +578,16 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int k = 0; k < 8; ++k) dot += a[k] * b[k];
       }
       dot = warp_sum(dot);
-      if (lane == 0) atomicAdd(&s_sc[0], s_ecs[TQ - 1] * dot);
+      if (lane == 0) s_wdot[warp] = s_ecs[TQ - 1] * dot;
     }
     umma::mbar_wait(bar1, par);
     umma::tc_fence_after();
     long long tk2 = clock64();
     // ---- epilogue A (thread = row t, 128/NCG of the 128 columns): K = G o L -> smem;
     //      d cs_t += sum_q W G  +  e^{cs_t} <dY_t, Yo_t>
-    {
+    if ((row >> 5) >= nblk) {
+      s_dcsA[cg * TQ + row] = 0.f;                                     // padding rows: K rows stay finite, see the k-trimmed MMA
+    } else {
       const int t = row, I = t >> 5;
       float acc = 0.f;
 #pragma unroll
@@ -609,16 +630,17 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           for (int e = 0; e < 8; ++e) yd += d[e] * yo[8 * k + e];
         }
       }
-      atomicAdd(&s_dcs[t], acc + s_ecs[t] * yd);
+      s_dcsA[cg * TQ + t] = acc + s_ecs[t] * yd;
     }
     umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
     long long tk3 = clock64();
     if (issuer) {
       umma::tc_fence_after();
 #pragma unroll
-      for (int kb = 0; kb < 8; ++kb)                                   // du1 = K^T dY
-        umma::mma_bf16_ss(tmem + 320, umma::make_smem_desc(umma::smem_u32(sK) + kb * 2048, HALF, 1024),
-                          umma::make_smem_desc(umma::smem_u32(sdY) + kb * 2048, 1024, 1024), idesc_mm64, kb > 0);
+      for (int kb = 0; kb < 8; ++kb)                                   // du1 = K^T dY   (k = time: valid frames only)
+        if (kb < nkb)
+          umma::mma_bf16_ss(tmem + 320, umma::make_smem_desc(umma::smem_u32(sK) + kb * 2048, HALF, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sdY) + kb * 2048, 1024, 1024), idesc_mm64, kb > 0);
 #pragma unroll
       for (int kb = 0; kb < 8; ++kb) {                                 // du2 = B Gst
         const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
@@ -639,9 +661,12 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     umma::tc_fence_after();
     long long tk4 = clock64();
     __syncthreads();                                                   // every smem operand has been consumed
-    if (issuer && nit < n_items) issue_load(nit);
+    if (issuer && nit < n_items) issue_load(nit, (seq & 1) ^ 1);
     // ---- epilogue B (thread = row q, 64/NCG of the 64 columns): dx, and the remaining d cs terms
-    {
+    if ((q >> 5) >= nblk) {
+      s_dcsB[cg * TQ + q] = 0.f; s_ddtx[cg * TQ + q] = 0.f;
+      if (lane == 0) { s_wsc[warp] = 0.f; s_wdd[warp] = 0.f; }
+    } else {
       const float eq = s_eq[q], dtq = s_dt[q];
       float col = 0.f, sc = 0.f, dux = 0.f, dd = 0.f;
 #pragma unroll
@@ -668,29 +693,40 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
       col *= dtq; sc *= dtq * eq;
-      atomicAdd(&s_dcs[q], -(col + sc));
-      atomicAdd(&s_ddtx[q], dux);
+      s_dcsB[cg * TQ + q] = -(col + sc);
+      s_ddtx[cg * TQ + q] = dux;
       sc = warp_sum(sc); dd = warp_sum(dd);
-      if (lane == 0) { atomicAdd(&s_sc[0], sc); atomicAdd(&s_sc[1], dd); }
+      if (lane == 0) { s_wsc[warp] = sc; s_wdd[warp] = dd; }
     }
     __syncthreads();
     // ---- reverse inclusive cumsum of d cs over the chunk -> ddt, dA_log
-    float v = 0.f;
+    float v = 0.f, ddx = 0.f;
     if (tid < TQ) {
-      v = s_dcs[TQ - 1 - tid] + (tid == 0 ? s_sc[0] : 0.f);           // tid 0 holds the latest time
+      const int t = TQ - 1 - tid;                                      // tid 0 holds the latest time
+#pragma unroll
+      for (int g = 0; g < NCG; ++g) { v += s_dcsA[g * TQ + t] + s_dcsB[g * TQ + t]; ddx += s_ddtx[g * TQ + t]; }
+      if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) v += s_wdot[w] + s_wsc[w];
+      }
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-      if (lane == 31) s_sc[4 + warp] = v;
+      if (lane == 31) s_tot[warp] = v;
     }
     __syncthreads();
     if (tid < TQ) {
-      for (int w = 0; w < warp; ++w) v += s_sc[4 + w];
+      for (int w = 0; w < warp; ++w) v += s_tot[w];
       const int t = TQ - 1 - tid;
       float accA = v * s_dt[t];
-      if (t < qv) p.ddt[(row0 + t) * H + h] = v * A + s_ddtx[t];
+      if (t < qv) p.ddt[(row0 + t) * H + h] = v * A + ddx;
       accA = warp_sum(accA);
       if (lane == 0) atomicAdd(p.dA_log + dir * H + h, accA * A);
-      if (tid == 0) atomicAdd(p.dD + dir * H + h, s_sc[1]);
+      if (tid == 0) {
+        float dd = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) dd += s_wdd[w];
+        atomicAdd(p.dD + dir * H + h, dd);
+      }
     }
     umma::tc_fence_before(); __syncthreads();
     if (p.dbg && blockIdx.x == 0 && tid == 0) {
@@ -728,7 +764,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_cb + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
-  const bool issuer = tid == NTAB, tabber = tid < NTAB;
+  const bool issuer = tid == NTAB;
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
     umma::mbar_init(bar_cb, 1); umma::mbar_init(bar_h, 1); umma::mbar_init(bar_r, 1); umma::mbar_init(bar_m, 1);
@@ -750,29 +786,24 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     umma::tma_load_3d(sB, &tmX, bar_cb, di, c * TQ, db);
     umma::tma_load_3d(sB + HALF, &tmX, bar_cb, di + 64, c * TQ, db);
   };
-  auto load_head = [&](int item, int h) {
+  auto load_head = [&](int item, int h, int buf) {
     const int c = item % nc, db = item / nc;
     const int srow = (((db * H + h) * nc) + c) * TN;
-    umma::mbar_expect_tx(bar_h, 4 * HALF);
+    umma::mbar_expect_tx(bar_h, 4 * HALF + TAB_BYTES);
+    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(srow / TN) * TAB_FLOATS, TAB_BYTES, bar_h);
     umma::tma_load_3d(sX, &tmX, bar_h, h * TP, c * TQ, db);
     umma::tma_load_3d(sdY, &tmDY, bar_h, h * TP, c * TQ, db);
     umma::tma_load_2d(sS, &tmS, bar_h, 0, srow);
     umma::tma_load_2d(sG, &tmG, bar_h, 0, srow);
   };
-  auto tables_for = [&](int item, int h, float* tab) {
-    const int c = item % nc, db = item / nc, dir = db / p.B;
-    const int q0 = c * TQ;
-    build_tables(p.dt + ((long long)db * L + q0) * H + h, H, min(TQ, L - q0), -__expf(p.A_log[dir * H + h]), tab, NTAB);
-  };
   uint32_t iseq = 0, hseq = 0;
-  if (blockIdx.x < n_items) {
-    if (issuer) { load_cb(blockIdx.x); load_head(blockIdx.x, 0); }
-    if (tabber) tables_for(blockIdx.x, 0, tabs);
-  }
-  __syncthreads();
+  for (int i = tid; i < 2 * HALF / 16; i += NT) reinterpret_cast<uint4*>(sW)[i] = make_uint4(0, 0, 0, 0);   // finite padding rows
+  umma::fence_async_smem();
+  if (blockIdx.x < n_items && issuer) { load_cb(blockIdx.x); load_head(blockIdx.x, 0, 0); }
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
     const int c = it % nc, db = it / nc;
     const int q0 = c * TQ, qv = min(TQ, L - q0);
+    const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;             // row blocks / k-steps that hold valid frames
     const long long row0 = (long long)db * L + q0;
     for (int h = 0; h < H; ++h, ++hseq) {
       const uint32_t par = hseq & 1;
@@ -805,6 +836,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {   // W[t,q] = R[t,q] L[t,q] dt_q   (thread = row t, 128/NCG of the 128 columns)
         const int t = row, I = t >> 5, J = NB * cg + bb, s0 = 32 * J;
+        if (I >= nblk) break;                                          // padding rows are never read (k-trimmed MMAs)
         float r[32];
         if (J <= I) {
           float l[32];
@@ -825,32 +857,33 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {                               // dC += W B
+        for (int kb = 0; kb < 8; ++kb) {                               // dC += W B        (k = time q: valid frames only)
           const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
-          umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sW) + o, 16, 1024),
-                            umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024), i_km, (h > 0 || kb > 0));
+          if (kb < nkb)
+            umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sW) + o, 16, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024), i_km, (h > 0 || kb > 0));
         }
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)                                 // dC += (e^{cs} dY) S_in^T
           umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sdYs) + kb * 32, 16, 1024),
                             umma::make_smem_desc(umma::smem_u32(sS) + kb * 32, 16, 1024), i_kk, 1u);
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb)                                 // dB += W^T C
-          umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sW) + kb * 2048, HALF, 1024),
-                            umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024), i_mm, (h > 0 || kb > 0));
+        for (int kb = 0; kb < 8; ++kb)                                 // dB += W^T C      (k = time t: valid frames only)
+          if (kb < nkb)
+            umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sW) + kb * 2048, HALF, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024), i_mm, (h > 0 || kb > 0));
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)                                 // dB += (w X) Gst^T
           umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sXw) + kb * 32, 16, 1024),
                             umma::make_smem_desc(umma::smem_u32(sG) + kb * 32, 16, 1024), i_kk, 1u);
         umma::mma_commit(bar_m);
       }
-      if (tabber && nit < n_items) tables_for(nit, nh, tabs + ((hseq & 1) ^ 1) * TAB_FLOATS);   // while the MMAs are issued and run
       umma::mbar_wait(bar_m, par);
       umma::tc_fence_after();
-      __syncthreads();                                                 // the next tables are complete for everyone
+      __syncthreads();                                                 // every thread is done with this head's tables
       if (issuer && nit < n_items) {
         if (nh == 0) load_cb(nit);
-        load_head(nit, nh);
+        load_head(nit, nh, (hseq & 1) ^ 1);
       }
     }
     // ---- write dB | dC of this chunk (bf16, like the rest of the activation gradients)
@@ -894,6 +927,15 @@ static int sm_count() {
   return n;
 }
 
+// workspace of the tcgen05 path: bf16 states [ndir*B, H, nc, 128, 64] followed (128-byte aligned) by the fp32 tables
+static size_t tc_tables_offset(int ndir, int B, int L, int H) {
+  const size_t st = (size_t)ndir * B * H * cdiv(L, TQ) * TN * TP * sizeof(__nv_bfloat16);
+  return (st + 127) / 128 * 128;
+}
+long long hnb_ssd_tc_ws_bytes(int ndir, int B, int L, int H) {
+  return (long long)(tc_tables_offset(ndir, B, L, H) + (size_t)ndir * B * H * cdiv(L, TQ) * TAB_BYTES + 128);
+}
+
 int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B, int L,
                    int di, int N, int H, void* y, void* states, void* stream) {
   HNB_CHECK_ARG(N == TN && di == H * TP, "ssd_fwd(tcgen05): built for d_state=128, headdim=64");
@@ -908,7 +950,11 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip;
   p.y = (__nv_bfloat16*)y; p.states = (__nv_bfloat16*)states;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = cdiv(L, TQ);
+  float* tables = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
+  p.tables = tables;
   const int items = ndir * B * H;
+  ssd_tables_kernel<<<items * p.nc, TQ, 0, (cudaStream_t)stream>>>(dt, A_log, tables, B, L, H, p.nc);
+  HNB_LAUNCH_CHECK("ssd_tables");
   const int grid = items < sm_count() ? items : sm_count();
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   ssd_fwd_tc_kernel<FWD_THREADS><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
@@ -942,6 +988,7 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.gstates = (__nv_bfloat16*)ws2; p.dxc = (__nv_bfloat16*)dxc;
   p.dBC = (__nv_bfloat16*)dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = nc;
+  p.tables = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.dbg = nullptr;
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
   if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, st); }

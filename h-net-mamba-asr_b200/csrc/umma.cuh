@@ -78,6 +78,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------
 // one full warp calls alloc/dealloc; ncols is a power of two in [32, 512]
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {

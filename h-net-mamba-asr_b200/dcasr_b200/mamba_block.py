@@ -111,10 +111,11 @@ def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, ln_a
     if dstride != dip:
         dzx.view(-1, ndir, dstride)[:, :, dip:] = 0                      # pad columns feed the GEMMs below
     # one zero-filled buffer for every accumulated parameter gradient of the block (one fill instead of ten)
-    sizes = [ndir * di, ndir * H, ndir * H, ndir * C * 4, ndir * C, ndir * H, 2 * ln_acc_d]
+    # (conv accumulators first: C % 4 == 0 keeps them 16-byte aligned for the kernel's vector reductions)
+    sizes = [ndir * C * 4, ndir * C, ndir * di, ndir * H, ndir * H, ndir * H, 2 * ln_acc_d]
     accs = torch.zeros(sum(sizes), dtype=torch.float32, device=zx.device).split(sizes)
-    a_nw, a_dA, a_dD = accs[0].view(ndir, di), accs[1].view(ndir, H), accs[2].view(ndir, H)
-    a_cw, a_cb, a_dtb = accs[3].view(ndir, C, 4), accs[4].view(ndir, C), accs[5].view(ndir, H)
+    a_cw, a_cb, a_nw = accs[0].view(ndir, C, 4), accs[1].view(ndir, C), accs[2].view(ndir, di)
+    a_dA, a_dD, a_dtb = accs[3].view(ndir, H), accs[4].view(ndir, H), accs[5].view(ndir, H)
     dy, dnorm_w = ops.gated_norm_bwd(dyn, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx, acc=a_nw)
     dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, acc=(a_dA, a_dD))
     dconv_w, dconv_b, ddt_bias = ops.conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias,
