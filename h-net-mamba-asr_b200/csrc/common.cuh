@@ -59,6 +59,17 @@ void count_launch(int n = 1);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Division by a run-time constant as one multiply-high: exact while n * d < 2^32 (item counts and head / chunk /
+// batch counts here are far below that).  The kernels decode an item index per loop iteration in every thread; the
+// hardware has no integer divide and the emulation costs ~40 instructions per division.
+struct FastDiv {
+  uint32_t d, m;
+  FastDiv() : d(1), m(0) {}
+  explicit FastDiv(int div) : d((uint32_t)div), m(div > 1 ? (uint32_t)((0x100000000ULL + (uint32_t)div - 1) / (uint32_t)div) : 0u) {}
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)__umulhi((uint32_t)n, m); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * (int)d; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // scalar conversions
 // ---------------------------------------------------------------------------------------------

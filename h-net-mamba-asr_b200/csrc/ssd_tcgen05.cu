@@ -153,6 +153,8 @@ struct FwdParams {
   __nv_bfloat16* states;  // [ndir*B, H, nc, 128(n), 64(p)]  state ENTERING each chunk
   const float* tables;    // [ndir*B, H, nc, TAB_FLOATS]
   int ndirB, B, L, H, di, nc;
+  FastDiv dH, dB, dnc;
+  long long* dbg;         // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
 };
 
 template <int NT>
@@ -195,7 +197,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   constexpr uint32_t idesc_s = umma::make_idesc_bf16(128, 64, 1, 1);
 
   auto issue_load = [&](int item, int c, int buf) {                 // issuer only
-    const int db = item / H, h = item % H;
+    int db, h; p.dH.divmod(item, db, h);
     umma::mbar_expect_tx(bar_load, 5 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(item * nc + c) * TAB_FLOATS, TAB_BYTES, bar_load);
     umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
@@ -209,7 +211,8 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   if (blockIdx.x < n_items && issuer) issue_load(blockIdx.x, 0, 0);
 
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int db = it / H, h = it % H, dir = db / p.B;
+    int db, h; p.dH.divmod(it, db, h);
+    const int dir = p.dB.div(db);
     const float Dh = p.Dskip[dir * H + h];
     float Sreg[16 * NB];
 #pragma unroll
@@ -232,7 +235,9 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
 #pragma unroll
         for (int k = 0; k < 2 * NB; ++k) *reinterpret_cast<uint4*>(sg + 8 * k) = pack8(Sreg + 8 * k);
       }
+      const long long tk0 = clock64();
       umma::mbar_wait(bar_load, par);
+      const long long tk1 = clock64();
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
@@ -254,6 +259,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       }
       umma::mbar_wait(bar_g, par);
       umma::tc_fence_after();
+      const long long tk2 = clock64();
       // ---- epilogue 1: M[t,s] = G[t,s] e^{cs_t - cs_s} dt_s (s <= t), bf16, K-major swizzled
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {
@@ -278,6 +284,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       umma::fence_async_smem();
       umma::tc_fence_before();
       __syncthreads();
+      const long long tk3 = clock64();
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
@@ -305,6 +312,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       }
       umma::mbar_wait(bar_y, par);
       umma::tc_fence_after();
+      const long long tk4 = clock64();
       if (issuer && nit < n_items) issue_load(nit, ncn, buf ^ 1);      // C, B and the other X buffer are free
       // ---- epilogue 2: y = Yd + e^{cs_t} Yo + D x          (thread = row t, 64/NCG of the 64 columns)
 #pragma unroll
@@ -346,6 +354,11 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       umma::fence_async_smem();
       umma::tc_fence_before();
       __syncthreads();
+      if (p.dbg && blockIdx.x == 0 && tid == 0) {
+        const long long tk5 = clock64();
+        p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
+        p.dbg[4] += tk5 - tk4; p.dbg[6] += 1;
+      }
     }
   }
   umma::tc_fence_before();
@@ -365,6 +378,7 @@ struct BwdParams {
   float* ddt;                    // [ndir*B*L, H]
   float* dA_log; float* dD;      // [ndir, H]
   int ndirB, B, L, H, di, nc;
+  FastDiv dH, dB, dnc;
   long long* dbg;                // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
 };
 
@@ -398,7 +412,7 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * H;
   constexpr uint32_t idesc = umma::make_idesc_bf16(128, 64, 1, 1);
   auto issue_load = [&](int item, int c, int buf) {
-    const int db = item / H, h = item % H;
+    int db, h; p.dH.divmod(item, db, h);
     umma::mbar_expect_tx(bar_load, 3 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(item * nc + c) * TAB_FLOATS, TAB_BYTES, bar_load);
     umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
@@ -409,7 +423,7 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   // chunk 0 needs no step of its own: the gradient w.r.t. the (zero) state entering it is never used
   if (blockIdx.x < n_items && tid == 0 && nc > 1) issue_load(blockIdx.x, nc - 1, 0);
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int db = it / H, h = it % H;
+    int db, h; p.dH.divmod(it, db, h);
     float Grun[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) Grun[j] = 0.f;
@@ -516,7 +530,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr uint32_t idesc_km64 = umma::make_idesc_bf16(128, 64, 0, 1);
   constexpr uint32_t idesc_mm64 = umma::make_idesc_bf16(128, 64, 1, 1);
   auto issue_load = [&](int item, int buf) {
-    const int h = item % H, c = (item / H) % nc, db = item / (H * nc);
+    int t1, h, db, c; p.dH.divmod(item, t1, h); p.dnc.divmod(t1, db, c);
     const int srow = (((db * H + h) * nc) + c) * TN;
     umma::mbar_expect_tx(bar_load, 8 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(srow / TN) * TAB_FLOATS, TAB_BYTES, bar_load);
@@ -537,7 +551,8 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t par = seq & 1;
     const float* tab = tabs + (seq & 1) * TAB_FLOATS;
     const float* s_dt = tab + TQ; const float* s_ecs = tab + 3 * TQ; const float* s_eq = tab + 4 * TQ;
-    const int h = it % H, c = (it / H) % nc, db = it / (H * nc), dir = db / p.B;
+    int t1, h, db, c; p.dH.divmod(it, t1, h); p.dnc.divmod(t1, db, c);
+    const int dir = p.dB.div(db);
     const float A = -__expf(p.A_log[dir * H + h]);
     const float Dh = p.Dskip[dir * H + h];
     const int q0 = c * TQ, qv = min(TQ, L - q0);
@@ -779,7 +794,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   constexpr uint32_t i_km = umma::make_idesc_bf16(128, 128, 0, 1);
   constexpr uint32_t i_mm = umma::make_idesc_bf16(128, 128, 1, 1);
   auto load_cb = [&](int item) {
-    const int c = item % nc, db = item / nc;
+    int db, c; p.dnc.divmod(item, db, c);
     umma::mbar_expect_tx(bar_cb, 4 * HALF);
     umma::tma_load_3d(sC, &tmX, bar_cb, di + TN, c * TQ, db);
     umma::tma_load_3d(sC + HALF, &tmX, bar_cb, di + TN + 64, c * TQ, db);
@@ -787,7 +802,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     umma::tma_load_3d(sB + HALF, &tmX, bar_cb, di + 64, c * TQ, db);
   };
   auto load_head = [&](int item, int h, int buf) {
-    const int c = item % nc, db = item / nc;
+    int db, c; p.dnc.divmod(item, db, c);
     const int srow = (((db * H + h) * nc) + c) * TN;
     umma::mbar_expect_tx(bar_h, 4 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(srow / TN) * TAB_FLOATS, TAB_BYTES, bar_h);
@@ -801,7 +816,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   umma::fence_async_smem();
   if (blockIdx.x < n_items && issuer) { load_cb(blockIdx.x); load_head(blockIdx.x, 0, 0); }
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
-    const int c = it % nc, db = it / nc;
+    int db, c; p.dnc.divmod(it, db, c);
     const int q0 = c * TQ, qv = min(TQ, L - q0);
     const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;             // row blocks / k-steps that hold valid frames
     const long long row0 = (long long)db * L + q0;
@@ -811,8 +826,10 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
       int nit = it, nh = h + 1;                                        // the head-step after this one
       if (nh == H) { nit = it + gridDim.x; nh = 0; }
+      const long long tk0 = clock64();
       if (h == 0) umma::mbar_wait(bar_cb, iseq & 1);
       umma::mbar_wait(bar_h, par);
+      const long long tk1 = clock64();
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
@@ -833,6 +850,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       umma::mbar_wait(bar_r, par);
       umma::tc_fence_after();
+      const long long tk2 = clock64();
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {   // W[t,q] = R[t,q] L[t,q] dt_q   (thread = row t, 128/NCG of the 128 columns)
         const int t = row, I = t >> 5, J = NB * cg + bb, s0 = 32 * J;
@@ -854,6 +872,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           *reinterpret_cast<uint4*>(sW + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(r + 8 * k);
       }
       umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
+      const long long tk3 = clock64();
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
@@ -884,6 +903,10 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (issuer && nit < n_items) {
         if (nh == 0) load_cb(nit);
         load_head(nit, nh, (hseq & 1) ^ 1);
+      }
+      if (p.dbg && blockIdx.x == 0 && tid == 0) {
+        const long long tk4 = clock64();
+        p.dbg[8] += tk1 - tk0; p.dbg[9] += tk2 - tk1; p.dbg[10] += tk3 - tk2; p.dbg[11] += tk4 - tk3; p.dbg[14] += 1;
       }
     }
     // ---- write dB | dC of this chunk (bf16, like the rest of the activation gradients)
@@ -950,15 +973,29 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip;
   p.y = (__nv_bfloat16*)y; p.states = (__nv_bfloat16*)states;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = cdiv(L, TQ);
+  p.dH = FastDiv(H); p.dB = FastDiv(B); p.dnc = FastDiv(p.nc);
+  HNB_CHECK_ARG((long long)ndir * B * H * p.nc * (H > B ? H : B) < (1LL << 31), "ssd_fwd(tcgen05): problem too large");
   float* tables = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.tables = tables;
   const int items = ndir * B * H;
   ssd_tables_kernel<<<items * p.nc, TQ, 0, (cudaStream_t)stream>>>(dt, A_log, tables, B, L, H, p.nc);
   HNB_LAUNCH_CHECK("ssd_tables");
   const int grid = items < sm_count() ? items : sm_count();
+  p.dbg = nullptr;
+  const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
+  if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, (cudaStream_t)stream); }
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   ssd_fwd_tc_kernel<FWD_THREADS><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
   HNB_LAUNCH_CHECK("ssd_fwd_tc");
+  if (debug) {
+    long long h[8];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, p.dbg, 64, cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    const double n = h[6] > 0 ? (double)h[6] : 1.0;
+    fprintf(stderr, "[ssd_fwd CTA0] steps %lld | cycles/step: wait load %.0f, G mma wait (+Xw) %.0f, epi1 %.0f, "
+            "mma2 wait %.0f, epi2+3 %.0f\n", h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n);
+  }
   return HNB_OK;
 }
 
@@ -988,10 +1025,12 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.gstates = (__nv_bfloat16*)ws2; p.dxc = (__nv_bfloat16*)dxc;
   p.dBC = (__nv_bfloat16*)dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = nc;
+  p.dH = FastDiv(H); p.dB = FastDiv(B); p.dnc = FastDiv(nc);
+  HNB_CHECK_ARG((long long)ndir * B * H * nc * (H > B ? H : B) < (1LL << 31), "ssd_bwd(tcgen05): problem too large");
   p.tables = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.dbg = nullptr;
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
-  if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, st); }
+  if (debug) { cudaMalloc(&p.dbg, 128); cudaMemsetAsync(p.dbg, 0, 128, st); }
   const int sms = sm_count();
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dstate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D1_SMEM));
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel<BWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
@@ -1006,10 +1045,13 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   ssd_bwd_dbc_tc_kernel<BWD_THREADS><<<items < sms ? items : sms, BWD_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dbc_tc");
   if (debug) {
-    long long h[8];
+    long long h[16];
     cudaStreamSynchronize(st);
-    cudaMemcpy(h, p.dbg, 64, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, p.dbg, 128, cudaMemcpyDeviceToHost);
     cudaFree(p.dbg);
+    const double m = h[14] > 0 ? (double)h[14] : 1.0;
+    fprintf(stderr, "[ssd_bwd_dbc CTA0] head-steps %lld | cycles/step: wait load %.0f, R mma wait (+Xw,dYs) %.0f, W epilogue %.0f, "
+            "mma2 wait %.0f\n", h[14], h[8] / m, h[9] / m, h[10] / m, h[11] / m);
     const double n = h[6] > 0 ? (double)h[6] : 1.0;
     fprintf(stderr, "[ssd_bwd_dx CTA0] items %lld | cycles/item: wait load %.0f, mma1 wait (tables+dot) %.0f, epiA %.0f, "
             "mma2 wait %.0f, epiB+cumsum %.0f\n", h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n);
