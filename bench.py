@@ -156,32 +156,38 @@ def run_reference(args):
 # roofline of the dominant kernel from a profiled step
 # ---------------------------------------------------------------------------------------------------
 def algorithmic_work(name: str, a: tuple):
-    """(bound, work per launch) — flops for tensor-bound entry points, compulsory bytes for HBM-bound ones.
-    `a` holds the scalar arguments of the C call in declaration order (see include/hnet_b200.h)."""
+    """(flops, bytes) of ONE launch of a C-ABI entry point: flops in the reference's convention, bytes = every input
+    read once + every output written once (saved-for-backward by-products such as the SSD chunk
+    states are NOT counted).  `a` holds the scalar arguments of the C call in declaration order (include/hnet_b200.h).
+    Which roofline binds is decided from these two numbers and the measured peaks, not asserted per kernel."""
     if name == "gemm_bf16":       # lda, transA, ldb, transB, M, N, K, ldr, ldc, c_dtype, splitk
         M, N, K = a[4], a[5], a[6]
-        return "tensor", 2.0 * M * N * K
+        csz = 4 if a[9] == 0 else 2
+        return 2.0 * M * N * K, 2.0 * (M * K + N * K) + csz * M * N
     if name in ("ssd_fwd", "ssd_bwd"):   # dtype, ndir, B, L, di, N, H, impl
-        ndir, B, L, di, N = a[1], a[2], a[3], a[4], a[5]
-        f = 4.0 * di * N * ndir * B * L          # reference convention: linear recurrence (efficiency.py:135)
-        return "tensor", f * (1.0 if name == "ssd_fwd" else 2.5)
+        ndir, B, L, di, N, H = a[1], a[2], a[3], a[4], a[5], a[6]
+        T, C = ndir * B * L, di + 2 * N
+        f = 4.0 * di * N * T                     # linear recurrence, reference convention (eval/efficiency.py:135)
+        if name == "ssd_fwd":
+            return f, T * (C * 2 + di * 2 + H * 4)                    # xconv, dt -> y
+        return 2.5 * f, T * (di * 2 + C * 2 + H * 4 + di * 2 + 2 * N * 2 + H * 4)   # dy, xconv, dt -> dxc, dBC, ddt
     if name == "conv_fwd":        # dtype, ldz, dstride, ndir, B, L, di, N, H
         ndir, B, L, di, N, H = a[3:9]
-        return "hbm", ndir * B * L * ((di + 2 * N) * 4 + H * 6)
+        return None, ndir * B * L * ((di + 2 * N) * 4 + H * 6)
     if name == "conv_bwd":
         ndir, B, L, di, N, H = a[3:9]
-        return "hbm", ndir * B * L * ((di + 2 * N) * 4 + di * 2 + 2 * N * 4 + H * 10)
+        return None, ndir * B * L * ((di + 2 * N) * 4 + di * 2 + 2 * N * 4 + H * 10)
     if name == "gated_norm_fwd":  # dtype, ldz, dstride, ndir, B, L, di, eps
         ndir, B, L, di = a[3:7]
-        return "hbm", ndir * B * L * di * 6
+        return None, ndir * B * L * di * 6
     if name == "gated_norm_bwd":
         ndir, B, L, di = a[3:7]
-        return "hbm", ndir * B * L * di * 10
+        return None, ndir * B * L * di * 10
     if name == "layernorm_fwd":   # x_dtype, rows, d, eps, y_dtype
-        return "hbm", a[1] * a[2] * 6
+        return None, a[1] * a[2] * 6
     if name == "layernorm_bwd":   # dy_dtype, x_dtype, rows, d, dx_dtype
-        return "hbm", a[2] * a[3] * 12
-    return "hbm", None
+        return None, a[2] * a[3] * 12
+    return None, None
 
 
 def profile_step(step, pk):
@@ -190,26 +196,28 @@ def profile_step(step, pk):
     step()
     rec = _lib.profile_stop()
     agg = {}
+    pf, pb = pk["bf16_tflops_sustained"] * 1e12, pk["hbm_gbs"] * 1e9
     for name, a, ms in rec:
-        key = name
-        e = agg.setdefault(key, {"ms": 0.0, "n": 0, "work": 0.0, "bound": "hbm", "ok": True})
-        bound, w = algorithmic_work(name, a)
-        e["ms"] += ms; e["n"] += 1; e["bound"] = bound
-        if w is None:
+        e = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0, "ok": True})
+        f, by = algorithmic_work(name, a)
+        e["ms"] += ms; e["n"] += 1
+        if by is None:
             e["ok"] = False
         else:
-            e["work"] += w
+            e["flops"] += f or 0.0; e["bytes"] += by
     total = sum(e["ms"] for e in agg.values())
     table = []
     for k, e in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-        row = {"kernel": k, "launches": e["n"], "ms": round(e["ms"], 3), "share": round(e["ms"] / total, 4), "bound": e["bound"]}
+        row = {"kernel": k, "launches": e["n"], "ms": round(e["ms"], 3), "share": round(e["ms"] / total, 4)}
         if e["ok"] and e["ms"] > 0:
-            if e["bound"] == "tensor":
-                ach, peak = e["work"] / (e["ms"] * 1e-3) / 1e12, pk["bf16_tflops_sustained"]
-                row.update(achieved=round(ach, 2), peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4))
+            sec = e["ms"] * 1e-3
+            t_f, t_b = e["flops"] / pf, e["bytes"] / pb          # time each roofline alone would allow
+            if t_f > t_b:
+                ach, peak = e["flops"] / sec / 1e12, pk["bf16_tflops_sustained"]
+                row.update(bound="tensor", achieved=round(ach, 2), peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4))
             else:
-                ach, peak = e["work"] / (e["ms"] * 1e-3) / 1e9, pk["hbm_gbs"]
-                row.update(achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4))
+                ach, peak = e["bytes"] / sec / 1e9, pk["hbm_gbs"]
+                row.update(bound="hbm", achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4))
         table.append(row)
     return table, total
 

@@ -10,6 +10,8 @@
 // drain the other accumulator (TMEM lane quarter = warp % 4), so the epilogue of tile i overlaps the main loop of
 // tile i+1.  The projections of this model have K = 384..512 (6-8 k-blocks per tile): without that overlap the
 // prologue/epilogue, not the tensor pipe, sets the pace.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -58,7 +60,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_STAGE_FLOATS = 32 * 33;                     // per-warp [32 rows][33] fp32 transpose buffer
 template <int BN> struct GemmCfg {
   static constexpr int B_STAGE = BN * BK * 2;                 // 16 / 32 KB
-  static constexpr int STAGES = BN == 256 ? 3 : 4;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;          // as many bytes in flight as 227 KB allows
   static constexpr int RING = STAGES * (A_STAGE + B_STAGE);
   static constexpr int SMEM = RING + EPI_WARPS * EPI_STAGE_FLOATS * 4 + 256 + 1024;
 };
@@ -66,6 +68,7 @@ template <int BN> struct GemmCfg {
 struct GemmParams {
   int M, N, K;
   int tiles_m, tiles_n, splitk, kblocks_per_split, total_kb;
+  int groups_m;               // tiles_m / cluster size (rounded up): one work item = CL vertically adjacent tiles
   const float* bias;
   const void* R;
   long long ldr;
@@ -79,7 +82,12 @@ struct GemmParams {
 //   TMA warp  -> smem ring (full/empty mbarriers)
 //   MMA warp  -> tcgen05.mma 128 x BN x 16 into one of TWO TMEM accumulators (tmem_full/tmem_empty mbarriers)
 //   8 epilogue warps drain accumulator i while the MMA warp already fills accumulator i^1.
-template <int TA, int TB, int BN>
+//
+// CL = 2: the two CTAs of a cluster take vertically adjacent tiles of the same column block, so they need the same B
+// tile.  Each loads HALF of it and multicasts that half into both CTAs' shared memory: 32 KB instead of 48 KB of L2
+// reads per CTA and k-block (these K = 384..512 GEMMs are paced by L2 -> SM bandwidth, not by the tensor pipe).  The
+// MMAs stay 1-SM; a stage is refilled only when BOTH CTAs' MMAs have released it (multicast commit, empty count 2).
+template <int TA, int TB, int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -95,26 +103,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.tiles_m * p.tiles_n * p.splitk;
+  const int n_items = p.groups_m * p.tiles_n * p.splitk;
+  const int crank = CL > 1 ? (int)umma::cluster_ctarank() : 0;
+  const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     umma::prefetch_tmap(&tmA);
     umma::prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], CL); }
     for (int a = 0; a < 2; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], EPI_WARPS); }
     umma::fence_barrier_init();
   }
   if (warp == 1) umma::tmem_alloc(tmem_slot, 2 * BN);
   umma::tc_fence_before();
   __syncthreads();
+  if (CL > 1) umma::cluster_sync_all();        // the peer's barriers are initialised before anything is multicast into them
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
-    const int tm = item % p.tiles_m;
-    const int r = item / p.tiles_m;
+    const int tm = item % p.groups_m;
+    const int r = item / p.groups_m;
     const int tn = r % p.tiles_n, ks = r / p.tiles_n;
-    m0 = tm * BM; n0 = tn * BN;
+    m0 = (tm * CL + crank) * BM; n0 = tn * BN;          // may start beyond M for the odd last tile: loads zero-fill
     kb0 = ks * p.kblocks_per_split;
     nkb = min(p.kblocks_per_split, p.total_kb - kb0);
   };
@@ -123,7 +134,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = first_item; item < n_items; item += item_stride) {
         int m0, n0, kb0, nkb;
         decode(item, m0, n0, kb0, nkb);
         for (int i = 0; i < nkb; ++i, ++it) {
@@ -140,11 +151,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma::tma_load_2d(a, &tmA, &full[s], m0, k0);                  // boxes {64 m, 64 k}
             umma::tma_load_2d(a + 8192, &tmA, &full[s], m0 + 64, k0);
           }
-          if (TB == 0) {
-            umma::tma_load_2d(b, &tmB, &full[s], k0, n0);                  // box {64 k, BN n}
-          } else {
+          if (CL == 1) {
+            if (TB == 0) {
+              umma::tma_load_2d(b, &tmB, &full[s], k0, n0);                // box {64 k, BN n}
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) umma::tma_load_2d(b + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);
+              for (int j = 0; j < BN / 64; ++j) umma::tma_load_2d(b + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);
+            }
+          } else {                                                         // this CTA's half of B, into both CTAs
+            if (TB == 0) {
+              umma::tma_load_2d_mc(b + crank * (B_STAGE / 2), &tmB, &full[s], k0, n0 + crank * (BN / 2), 0x3);   // box {64 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = crank * (BN / 128) + j;
+                umma::tma_load_2d_mc(b + jj * 8192, &tmB, &full[s], n0 + 64 * jj, k0, 0x3);
+              }
+            }
           }
         }
       }
@@ -154,7 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma::make_idesc_bf16(BM, BN, TA, TB);
       uint32_t it = 0, li = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+      for (int item = first_item; item < n_items; item += item_stride, ++li) {
         int m0, n0, kb0, nkb;
         decode(item, m0, n0, kb0, nkb);
         const uint32_t acc = li & 1, aph = (li >> 1) & 1;
@@ -176,7 +199,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                           : umma::make_smem_desc(b + k * 2048, 8192, 1024);
             umma::mma_bf16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          umma::mma_commit(&empty[s]);                                     // frees the smem slot when the MMAs retire
+          if (CL == 1) umma::mma_commit(&empty[s]);                        // frees the smem slot when the MMAs retire
+          else umma::mma_commit_mc(&empty[s], 0x3);                        // ... in both CTAs: either may refill it
         }
         umma::mma_commit(&tmem_full[acc]);
       }
@@ -187,7 +211,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int lq = warp & 3;                      // TMEM lane quarter this warp may read
     const int chalf = ew >> 2;                    // column half of the tile
     uint32_t li = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+    for (int item = first_item; item < n_items; item += item_stride, ++li) {
       int m0, n0, kb0, nkb;
       decode(item, m0, n0, kb0, nkb);
       const uint32_t acc = li & 1, aph = (li >> 1) & 1;
@@ -274,6 +298,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   umma::tc_fence_before();
   __syncthreads();
+  if (CL > 1) umma::cluster_sync_all();        // no CTA leaves while its peer can still signal or fill its shared memory
   if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * BN);
 }
 
@@ -322,6 +347,8 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   // tile width: 256 columns unless that would waste more than ~10 % of the MMA work on the ragged last tile
   const int waste256 = cdiv(N, 256) * 256 - N;
   const int BN = (N >= 256 && waste256 * 10 <= N) ? 256 : 128;
+  static const int cl_env = getenv("HNB_GEMM_CLUSTER") ? atoi(getenv("HNB_GEMM_CLUSTER")) : 1;   // tuning knob
+  const int CL = (cl_env == 2 && cdiv(M, BM) >= 4) ? 2 : 1;
   CUtensorMap tmA, tmB;
   int rc;
   {
@@ -331,7 +358,7 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
     else         { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
     st[0] = (uint64_t)lda * 2;
     if ((rc = make_tmap_bf16(&tmA, A, 2, dims, st, box))) return rc;
-    if (!transB) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)BN; }
+    if (!transB) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)(BN / CL); }
     else         { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
     st[0] = (uint64_t)ldb * 2;
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, st, box))) return rc;
@@ -344,21 +371,33 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   p.kblocks_per_split = cdiv(total_kb, splitk);
   p.splitk = cdiv(total_kb, p.kblocks_per_split);
   p.tiles_m = cdiv(M, BM); p.tiles_n = cdiv(N, BN);
+  p.groups_m = cdiv(p.tiles_m, CL);
   p.bias = bias; p.R = R; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.c_is_f32 = (c_dtype == HNB_F32);
   p.atomic = p.splitk > 1;
-  const int n_items = p.tiles_m * p.tiles_n * p.splitk;
+  const int n_items = p.groups_m * p.tiles_n * p.splitk;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const int grid = n_items < sms ? n_items : sms;
+  const int grid = CL * (n_items < sms / CL ? n_items : sms / CL);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(TA, TB, BN_)                                                                                          \
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+#define LAUNCH(TA, TB, BN_, CL_)                                                                                     \
   do {                                                                                                               \
-    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_kernel<TA, TB, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_kernel<TA, TB, BN_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        GemmCfg<BN_>::SMEM));                                                         \
-    gemm_bf16_kernel<TA, TB, BN_><<<grid, GEMM_THREADS, GemmCfg<BN_>::SMEM, st>>>(tmA, tmB, p);                       \
+    cfg.dynamicSmemBytes = GemmCfg<BN_>::SMEM;                                                                       \
+    HNB_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<TA, TB, BN_, CL_>, tmA, tmB, p));                         \
   } while (0)
-#define LAUNCH_BN(TA, TB) do { if (BN == 256) LAUNCH(TA, TB, 256); else LAUNCH(TA, TB, 128); } while (0)
+#define LAUNCH_BN(TA, TB)                                                                                            \
+  do {                                                                                                               \
+    if (BN == 256) { if (CL == 2) LAUNCH(TA, TB, 256, 2); else LAUNCH(TA, TB, 256, 1); }                              \
+    else           { if (CL == 2) LAUNCH(TA, TB, 128, 2); else LAUNCH(TA, TB, 128, 1); }                              \
+  } while (0)
   if (!transA && !transB) LAUNCH_BN(0, 0);
   else if (!transA && transB) LAUNCH_BN(0, 1);
   else if (transA && !transB) LAUNCH_BN(1, 0);
@@ -369,30 +408,33 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   return HNB_OK;
 }
 
-// Runs the four operand-major combinations (with ragged M, N, K tails, a bias/residual epilogue and a split-K
-// case) against a naive kernel.  Allocates scratch with cudaMalloc: diagnostic entry point, not a hot-path call.
+// Runs the four operand-major combinations (with ragged M, N, K tails) plus a split-K case against a naive kernel, once
+// with 3 row tiles (single-CTA path) and once with 5 (2-CTA multicast path, odd tile count: the last cluster's second
+// CTA owns no rows).  Allocates scratch with cudaMalloc: diagnostic entry point, not a hot-path call.
 extern "C" int hnb_umma_selftest(float* max_abs_err_host, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const int M = 328, N = 200, K = 424;                         // tails in every dimension
-  const long long lda = 432, ldb = 432;                        // covers both [M,K] (K=424) and [K,M] (M=328) storage
+  const int N = 200, K = 424, LD = 608;                        // LD covers [M,K], [K,M], [N,K], [K,N] storage
   __nv_bfloat16 *A, *B;
   float *C, *Cref, *err;
-  HNB_CUDA_CALL(cudaMalloc(&A, sizeof(__nv_bfloat16) * 432 * 432));
-  HNB_CUDA_CALL(cudaMalloc(&B, sizeof(__nv_bfloat16) * 432 * 432));
-  HNB_CUDA_CALL(cudaMalloc(&C, sizeof(float) * M * N));
-  HNB_CUDA_CALL(cudaMalloc(&Cref, sizeof(float) * M * N));
+  HNB_CUDA_CALL(cudaMalloc(&A, sizeof(__nv_bfloat16) * LD * LD));
+  HNB_CUDA_CALL(cudaMalloc(&B, sizeof(__nv_bfloat16) * LD * LD));
+  HNB_CUDA_CALL(cudaMalloc(&C, sizeof(float) * LD * N));
+  HNB_CUDA_CALL(cudaMalloc(&Cref, sizeof(float) * LD * N));
   HNB_CUDA_CALL(cudaMalloc(&err, sizeof(float) * 8));
   HNB_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(float) * 8, st));
-  fill_kernel<<<cdiv(432 * 432, 256), 256, 0, st>>>(A, 432 * 432, 1u);
-  fill_kernel<<<cdiv(432 * 432, 256), 256, 0, st>>>(B, 432 * 432, 7u);
+  fill_kernel<<<cdiv(LD * LD, 256), 256, 0, st>>>(A, LD * LD, 1u);
+  fill_kernel<<<cdiv(LD * LD, 256), 256, 0, st>>>(B, LD * LD, 7u);
   int rc = HNB_OK;
-  for (int combo = 0; combo < 5 && rc == HNB_OK; ++combo) {
-    const int ta = combo & 1, tb = (combo >> 1) & 1;
-    const int splitk = combo == 4 ? 3 : 1;
-    HNB_CUDA_CALL(cudaMemsetAsync(C, 0, sizeof(float) * M * N, st));
-    ref_gemm_kernel<<<dim3(cdiv(N, 128), M), 128, 0, st>>>(A, lda, ta, B, ldb, tb, M, N, K, Cref);
-    rc = hnb_gemm_bf16(A, lda, ta, B, ldb, tb, M, N, K, nullptr, nullptr, 0, C, N, HNB_F32, splitk, stream);
-    if (rc == HNB_OK) maxdiff_kernel<<<cdiv((long long)M * N, 256), 256, 0, st>>>(C, Cref, (long long)M * N, err + combo);
+  for (int pass = 0; pass < 2 && rc == HNB_OK; ++pass) {
+    const int M = pass == 0 ? 328 : 600;
+    for (int combo = 0; combo < 5 && rc == HNB_OK; ++combo) {
+      const int ta = combo & 1, tb = (combo >> 1) & 1;
+      const int splitk = combo == 4 ? 3 : 1;
+      HNB_CUDA_CALL(cudaMemsetAsync(C, 0, sizeof(float) * M * N, st));
+      ref_gemm_kernel<<<dim3(cdiv(N, 128), M), 128, 0, st>>>(A, LD, ta, B, LD, tb, M, N, K, Cref);
+      rc = hnb_gemm_bf16(A, LD, ta, B, LD, tb, M, N, K, nullptr, nullptr, 0, C, N, HNB_F32, splitk, stream);
+      if (rc == HNB_OK) maxdiff_kernel<<<cdiv((long long)M * N, 256), 256, 0, st>>>(C, Cref, (long long)M * N, err + combo);
+    }
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == HNB_OK && e != cudaSuccess) { set_error("umma_selftest: %s", cudaGetErrorString(e)); rc = HNB_ERR_CUDA; }

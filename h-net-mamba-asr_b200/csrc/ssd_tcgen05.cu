@@ -124,12 +124,29 @@ __device__ __forceinline__ void decay_row32(float* l, int t, int I, int J, int s
   const float cs_t = s_cs[t];
   if (J < I) {
     const float e_ref = __expf(cs_t - s_cs[32 * I - 1]);
+    const float4* f4 = reinterpret_cast<const float4*>(s_f + I * TQ + s0);   // warp-uniform address: 8 broadcast LDS.128
 #pragma unroll
-    for (int j = 0; j < 32; ++j) l[j] = e_ref * s_f[I * TQ + s0 + j];
+    for (int j = 0; j < 8; ++j) {
+      const float4 f = f4[j];
+      l[4 * j] = e_ref * f.x; l[4 * j + 1] = e_ref * f.y; l[4 * j + 2] = e_ref * f.z; l[4 * j + 3] = e_ref * f.w;
+    }
   } else {
+    const float4* c4 = reinterpret_cast<const float4*>(s_cs + s0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) l[j] = (s0 + j <= t) ? __expf(cs_t - s_cs[s0 + j]) : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float4 c = c4[j];
+      l[4 * j] = (s0 + 4 * j <= t) ? __expf(cs_t - c.x) : 0.f;
+      l[4 * j + 1] = (s0 + 4 * j + 1 <= t) ? __expf(cs_t - c.y) : 0.f;
+      l[4 * j + 2] = (s0 + 4 * j + 2 <= t) ? __expf(cs_t - c.z) : 0.f;
+      l[4 * j + 3] = (s0 + 4 * j + 3 <= t) ? __expf(cs_t - c.w) : 0.f;
+    }
   }
+}
+// 32 consecutive table entries (warp-uniform address) as 8 broadcast LDS.128
+__device__ __forceinline__ void load32(float* v, const float* src) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float4 f = s4[j]; v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w; }
 }
 
 // ===================================================================================================
@@ -171,16 +188,20 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + OFF_BAR);
   uint64_t* bar_g = bar_load + 1;
   uint64_t* bar_y = bar_load + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+  uint64_t* bar_free = bar_load + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2;
   const int row = lq * 32 + lane;
-  const bool issuer = tid == NTAB;                   // lane 0 of the last warp: TMA + MMA issue
+  const bool issuer = tid == NTAB;                   // lane 0 of the last warp: MMA issue
+  // TMA issue: lane 0 of the warp that owns the top-right 32x32 block of the score matrix (all zeros: the warp with
+  // the least epilogue work), so waiting for the operands to be released costs nobody else time
+  const bool loader = tid == 128 * (NCG - 1);
 
   if (tid == 0) {
     umma::prefetch_tmap(&tmX);
-    umma::mbar_init(bar_load, 1); umma::mbar_init(bar_g, 1); umma::mbar_init(bar_y, 1);
+    umma::mbar_init(bar_load, 1); umma::mbar_init(bar_g, 1); umma::mbar_init(bar_y, 1); umma::mbar_init(bar_free, 1);
     umma::fence_barrier_init();
   }
   if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
@@ -196,7 +217,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   constexpr uint32_t idesc_y = umma::make_idesc_bf16(128, 64, 0, 1);
   constexpr uint32_t idesc_s = umma::make_idesc_bf16(128, 64, 1, 1);
 
-  auto issue_load = [&](int item, int c, int buf) {                 // issuer only
+  auto issue_load = [&](int item, int c, int buf) {                 // loader only
     int db, h; p.dH.divmod(item, db, h);
     umma::mbar_expect_tx(bar_load, 5 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(item * nc + c) * TAB_FLOATS, TAB_BYTES, bar_load);
@@ -208,7 +229,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   };
 
   uint32_t seq = 0;                                                   // (item, chunk) sequence number of this CTA
-  if (blockIdx.x < n_items && issuer) issue_load(blockIdx.x, 0, 0);
+  if (blockIdx.x < n_items && loader) issue_load(blockIdx.x, 0, 0);
 
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
     int db, h; p.dH.divmod(it, db, h);
@@ -257,6 +278,31 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
         for (int e = 0; e < 8; ++e) v[e] *= w;
         reinterpret_cast<uint4*>(sXw)[i] = pack8(v);
       }
+      umma::fence_async_smem();
+      umma::tc_fence_before();
+      __syncthreads();                                                 // Xw (and the state in smem) visible to the tensor core
+      if (issuer) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {                               // Yo = C S_in
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + 192, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
+        }
+        if (!last_chunk) {
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {                             // dS = B^T (w o X)   (k = time: valid frames only)
+            if (kb < nkb)
+              umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024),
+                                umma::make_smem_desc(umma::smem_u32(sXw) + kb * 2048, 1024, 1024), idesc_s, kb > 0);
+          }
+        }
+        umma::mma_commit(bar_free);                                    // C, B, Xw, S_in released when these retire
+      }
+      if (loader && nit < n_items) {                                   // next step's tiles land during this step's epilogues
+        umma::mbar_wait(bar_free, par);
+        issue_load(nit, ncn, buf ^ 1);
+      }
       umma::mbar_wait(bar_g, par);
       umma::tc_fence_after();
       const long long tk2 = clock64();
@@ -269,10 +315,11 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
         if (J <= I) {
           umma::tmem_ld32(t_lane + (uint32_t)s0, g);
           umma::tmem_ld_wait();
-          float l[32];
+          float l[32], d32[32];
           decay_row32(l, t, I, J, s0, tab);
+          load32(d32, s_dt + s0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] *= l[j] * s_dt[s0 + j];
+          for (int j = 0; j < 32; ++j) g[j] *= l[j] * d32[j];
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) g[j] = 0.f;
@@ -294,26 +341,11 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
             umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sM) + o, 16, 1024),
                               umma::make_smem_desc(umma::smem_u32(sX + buf * HALF) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
         }
-#pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {                               // Yo = C S_in
-          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
-          umma::mma_bf16_ss(tmem + 192, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
-                            umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
-        }
-        if (!last_chunk) {
-#pragma unroll
-          for (int kb = 0; kb < 8; ++kb) {                             // dS = B^T (w o X)
-            if (kb < nkb)
-              umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024),
-                                umma::make_smem_desc(umma::smem_u32(sXw) + kb * 2048, 1024, 1024), idesc_s, kb > 0);
-          }
-        }
         umma::mma_commit(bar_y);
       }
       umma::mbar_wait(bar_y, par);
       umma::tc_fence_after();
       const long long tk4 = clock64();
-      if (issuer && nit < n_items) issue_load(nit, ncn, buf ^ 1);      // C, B and the other X buffer are free
       // ---- epilogue 2: y = Yd + e^{cs_t} Yo + D x          (thread = row t, 64/NCG of the 64 columns)
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {
@@ -485,7 +517,7 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 constexpr int D2_OFF_C = 0, D2_OFF_B = 2 * HALF, D2_OFF_X = 4 * HALF, D2_OFF_DY = 5 * HALF, D2_OFF_S = 6 * HALF,
               D2_OFF_G = 7 * HALF, D2_OFF_K = 8 * HALF, D2_OFF_TAB = 10 * HALF;
 constexpr int D2_OFF_EXTRA = D2_OFF_TAB + 2 * TAB_BYTES;
-constexpr int D2_OFF_BAR = D2_OFF_EXTRA + EXTRA_FLOATS * 4;
+constexpr int D2_OFF_BAR = D2_OFF_EXTRA + 2 * EXTRA_FLOATS * 4;     // partial sums double-buffered by item parity
 constexpr int D2_SMEM = D2_OFF_BAR + 64 + 1024;
 
 template <int NT>
@@ -500,25 +532,19 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint8_t* sdY = base + D2_OFF_DY; uint8_t* sS = base + D2_OFF_S; uint8_t* sG = base + D2_OFF_G;
   uint8_t* sK = base + D2_OFF_K;
   float* tabs = reinterpret_cast<float*>(base + D2_OFF_TAB);
-  // partial sums, one slot per (column group, row) or per warp: shared-memory float atomics are CAS loops
-  float* s_dcsA = reinterpret_cast<float*>(base + D2_OFF_EXTRA);   // [4][128]  d cs_t, row terms (epilogue A)
-  float* s_dcsB = s_dcsA + 4 * TQ;                                  // [4][128]  d cs_q, column terms (epilogue B)
-  float* s_ddtx = s_dcsB + 4 * TQ;                                  // [4][128]  <du_q, x_q>
-  float* s_wdot = s_ddtx + 4 * TQ;                                  // [16] per warp: <Gst, S_in>
-  float* s_wsc = s_wdot + 16;                                       // [16] per warp: d cs_last from the chunk state
-  float* s_wdd = s_wsc + 16;                                        // [16] per warp: dD
-  float* s_tot = s_wdd + 16;                                        // [8]  warp totals of the reverse cumsum
+  float* xtra = reinterpret_cast<float*>(base + D2_OFF_EXTRA);
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + D2_OFF_BAR);
   uint64_t* bar1 = bar_load + 1;
   uint64_t* bar2 = bar_load + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+  uint64_t* bar1b = bar_load + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
   const bool issuer = tid == NTAB;
   static_assert(NCG <= 4 && NT / 32 <= 16, "partial-sum slots");
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
-    umma::mbar_init(bar_load, 1); umma::mbar_init(bar1, 1); umma::mbar_init(bar2, 1);
+    umma::mbar_init(bar_load, 1); umma::mbar_init(bar1, 1); umma::mbar_init(bar2, 1); umma::mbar_init(bar1b, 1);
     umma::fence_barrier_init();
   }
   if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
@@ -551,6 +577,14 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t par = seq & 1;
     const float* tab = tabs + (seq & 1) * TAB_FLOATS;
     const float* s_dt = tab + TQ; const float* s_ecs = tab + 3 * TQ; const float* s_eq = tab + 4 * TQ;
+    // partial sums of this item, one slot per (column group, row) or per warp (shared-memory float atomics are CAS
+    // loops); double-buffered by item parity so that warp 0 can finish item i while the others start item i+1
+    float* s_dcsA = xtra + (seq & 1) * EXTRA_FLOATS;                  // [4][128]  d cs_t, row terms (epilogue A)
+    float* s_dcsB = s_dcsA + 4 * TQ;                                  // [4][128]  d cs_q, column terms (epilogue B)
+    float* s_ddtx = s_dcsB + 4 * TQ;                                  // [4][128]  <du_q, x_q>
+    float* s_wdot = s_ddtx + 4 * TQ;                                  // [16] per warp: <Gst, S_in>
+    float* s_wsc = s_wdot + 16;                                       // [16] per warp: d cs_last from the chunk state
+    float* s_wdd = s_wsc + 16;                                        // [16] per warp: dD
     int t1, h, db, c; p.dH.divmod(it, t1, h); p.dnc.divmod(t1, db, c);
     const int dir = p.dB.div(db);
     const float A = -__expf(p.A_log[dir * H + h]);
@@ -574,13 +608,20 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       for (int kb = 0; kb < 4; ++kb)                                   // R = dY X^T
         umma::mma_bf16_ss(tmem + 128, umma::make_smem_desc(umma::smem_u32(sdY) + kb * 32, 16, 1024),
                           umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), idesc_kk128, kb > 0);
+      umma::mma_commit(bar1);                                          // epilogue A starts on G and R ...
 #pragma unroll
       for (int kb = 0; kb < 8; ++kb) {                                 // Yo = C S_in (unscaled)
         const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
         umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
                           umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), idesc_km64, kb > 0);
       }
-      umma::mma_commit(bar1);
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {                                 // du2 = B Gst (independent of epilogue A)
+        const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+        umma::mma_bf16_ss(tmem + 384, umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024),
+                          umma::make_smem_desc(umma::smem_u32(sG) + kb * 2048, 1024, 1024), idesc_km64, kb > 0);
+      }
+      umma::mma_commit(bar1b);                                         // ... while these two still run
     }
     // while the MMAs run: the decay term e^{cs_last} <Gst, S_in>
     {
@@ -615,12 +656,14 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           umma::tmem_ld32(t_lane + 128u + (uint32_t)s0, r);
           umma::tmem_ld_wait();
           decay_row32(l, t, I, J, s0, tab);
+          float d32[32];
+          load32(d32, s_dt + s0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             g[j] *= l[j];
             // the row sums must use K exactly as the tensor core will see it (bf16): the column sums come out of
             // du1 = K^T dY, and the two cancel in the cumulative sum -- any rounding asymmetry would survive
-            acc += r[j] * s_dt[s0 + j] * __bfloat162float(__float2bfloat16_rn(g[j]));
+            acc += r[j] * d32[j] * __bfloat162float(__float2bfloat16_rn(g[j]));
           }
         } else {
 #pragma unroll
@@ -631,6 +674,8 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           *reinterpret_cast<uint4*>(sK + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(g + 8 * k);
       }
       float yd = 0.f;
+      umma::mbar_wait(bar1b, par);
+      umma::tc_fence_after();
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {
         const int c16 = NB * cg + bb;
@@ -656,12 +701,6 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (kb < nkb)
           umma::mma_bf16_ss(tmem + 320, umma::make_smem_desc(umma::smem_u32(sK) + kb * 2048, HALF, 1024),
                             umma::make_smem_desc(umma::smem_u32(sdY) + kb * 2048, 1024, 1024), idesc_mm64, kb > 0);
-#pragma unroll
-      for (int kb = 0; kb < 8; ++kb) {                                 // du2 = B Gst
-        const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
-        umma::mma_bf16_ss(tmem + 384, umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024),
-                          umma::make_smem_desc(umma::smem_u32(sG) + kb * 2048, 1024, 1024), idesc_km64, kb > 0);
-      }
       umma::mma_commit(bar2);
     }
     // operands of epilogue B that live in TMA-owned buffers: fetch them now so the buffers can be refilled
@@ -713,38 +752,42 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       sc = warp_sum(sc); dd = warp_sum(dd);
       if (lane == 0) { s_wsc[warp] = sc; s_wdd[warp] = dd; }
     }
-    __syncthreads();
-    // ---- reverse inclusive cumsum of d cs over the chunk -> ddt, dA_log
-    float v = 0.f, ddx = 0.f;
-    if (tid < TQ) {
-      const int t = TQ - 1 - tid;                                      // tid 0 holds the latest time
+    umma::tc_fence_before(); __syncthreads();                          // partial sums complete; du1 / du2 consumed
+    // ---- reverse inclusive cumsum of d cs over the chunk -> ddt, dA_log: ONE warp (lane l owns frames 4l..4l+3);
+    //      every other warp goes on to the next item
+    if (warp == 4 * (NCG - 1)) {                                       // the warp whose epilogue-A block is all zeros
+      float v[4] = {0.f, 0.f, 0.f, 0.f}, ddx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int g = 0; g < NCG; ++g) { v += s_dcsA[g * TQ + t] + s_dcsB[g * TQ + t]; ddx += s_ddtx[g * TQ + t]; }
-      if (tid == 0) {
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) v += s_wdot[w] + s_wsc[w];
+      for (int g = 0; g < NCG; ++g) {
+        const float4 a = *reinterpret_cast<const float4*>(s_dcsA + g * TQ + 4 * lane);
+        const float4 b = *reinterpret_cast<const float4*>(s_dcsB + g * TQ + 4 * lane);
+        const float4 d = *reinterpret_cast<const float4*>(s_ddtx + g * TQ + 4 * lane);
+        v[0] += a.x + b.x; v[1] += a.y + b.y; v[2] += a.z + b.z; v[3] += a.w + b.w;
+        ddx[0] += d.x; ddx[1] += d.y; ddx[2] += d.z; ddx[3] += d.w;
       }
+      float extra = lane < NT / 32 ? s_wdot[lane] + s_wsc[lane] : 0.f;
+      float dd = lane < NT / 32 ? s_wdd[lane] : 0.f;
+      extra = warp_sum(extra); dd = warp_sum(dd);
+      if (lane == 31) v[3] += extra;                                   // d cs of the chunk's last frame
+      v[2] += v[3]; v[1] += v[2]; v[0] += v[1];                        // suffix sums inside the lane
+      float suf = v[0];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-      if (lane == 31) s_tot[warp] = v;
-    }
-    __syncthreads();
-    if (tid < TQ) {
-      for (int w = 0; w < warp; ++w) v += s_tot[w];
-      const int t = TQ - 1 - tid;
-      float accA = v * s_dt[t];
-      if (t < qv) p.ddt[(row0 + t) * H + h] = v * A + ddx;
+      for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += u; }
+      const float later = suf - v[0];                                  // everything after this lane's frames
+      const float4 dt4 = *reinterpret_cast<const float4*>(s_dt + 4 * lane);
+      const float dtv[4] = {dt4.x, dt4.y, dt4.z, dt4.w};
+      float accA = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = 4 * lane + k;
+        const float sv = v[k] + later;
+        accA += sv * dtv[k];
+        if (t < qv) p.ddt[(row0 + t) * H + h] = sv * A + ddx[k];
+      }
       accA = warp_sum(accA);
-      if (lane == 0) atomicAdd(p.dA_log + dir * H + h, accA * A);
-      if (tid == 0) {
-        float dd = 0.f;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) dd += s_wdd[w];
-        atomicAdd(p.dD + dir * H + h, dd);
-      }
+      if (lane == 0) { atomicAdd(p.dA_log + dir * H + h, accA * A); atomicAdd(p.dD + dir * H + h, dd); }
     }
-    umma::tc_fence_before(); __syncthreads();
-    if (p.dbg && blockIdx.x == 0 && tid == 0) {
+    if (p.dbg && blockIdx.x == 0 && tid == 160) {                      // a warp that does not run the tail
       const long long tk5 = clock64();
       p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
       p.dbg[4] += tk5 - tk4; p.dbg[6] += 1;
@@ -773,16 +816,18 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint8_t* sS = base + D3_OFF_S; uint8_t* sG = base + D3_OFF_G; uint8_t* sW = base + D3_OFF_W;
   float* tabs = reinterpret_cast<float*>(base + D3_OFF_TAB);
   uint64_t* bar_cb = reinterpret_cast<uint64_t*>(base + D3_OFF_BAR);
-  uint64_t* bar_h = bar_cb + 1;
+  uint64_t* bar_xd = bar_cb + 1;
   uint64_t* bar_r = bar_cb + 2;
   uint64_t* bar_m = bar_cb + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_cb + 4);
+  uint64_t* bar_sg = bar_cb + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_cb + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
   const bool issuer = tid == NTAB;
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
-    umma::mbar_init(bar_cb, 1); umma::mbar_init(bar_h, 1); umma::mbar_init(bar_r, 1); umma::mbar_init(bar_m, 1);
+    umma::mbar_init(bar_cb, 1); umma::mbar_init(bar_xd, 1); umma::mbar_init(bar_r, 1); umma::mbar_init(bar_m, 1);
+    umma::mbar_init(bar_sg, 1);
     umma::fence_barrier_init();
   }
   if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
@@ -801,20 +846,40 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     umma::tma_load_3d(sB, &tmX, bar_cb, di, c * TQ, db);
     umma::tma_load_3d(sB + HALF, &tmX, bar_cb, di + 64, c * TQ, db);
   };
-  auto load_head = [&](int item, int h, int buf) {
+  // Per head-step two load groups: X | dY | tables (free again as soon as R and the scaled copies are made) and
+  // S_in | Gst (free when the second MMA group retires), so the first group of the NEXT step is in flight, and its
+  // R = dY X^T already queued on the tensor pipe, while this step's second MMA group runs.
+  auto load_xd = [&](int item, int h, int buf) {
+    int db, c; p.dnc.divmod(item, db, c);
+    const int srow = ((db * H + h) * nc) + c;
+    umma::mbar_expect_tx(bar_xd, 2 * HALF + TAB_BYTES);
+    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)srow * TAB_FLOATS, TAB_BYTES, bar_xd);
+    umma::tma_load_3d(sX, &tmX, bar_xd, h * TP, c * TQ, db);
+    umma::tma_load_3d(sdY, &tmDY, bar_xd, h * TP, c * TQ, db);
+  };
+  auto load_sg = [&](int item, int h) {
     int db, c; p.dnc.divmod(item, db, c);
     const int srow = (((db * H + h) * nc) + c) * TN;
-    umma::mbar_expect_tx(bar_h, 4 * HALF + TAB_BYTES);
-    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(srow / TN) * TAB_FLOATS, TAB_BYTES, bar_h);
-    umma::tma_load_3d(sX, &tmX, bar_h, h * TP, c * TQ, db);
-    umma::tma_load_3d(sdY, &tmDY, bar_h, h * TP, c * TQ, db);
-    umma::tma_load_2d(sS, &tmS, bar_h, 0, srow);
-    umma::tma_load_2d(sG, &tmG, bar_h, 0, srow);
+    umma::mbar_expect_tx(bar_sg, 2 * HALF);
+    umma::tma_load_2d(sS, &tmS, bar_sg, 0, srow);
+    umma::tma_load_2d(sG, &tmG, bar_sg, 0, srow);
+  };
+  auto issue_r = [&]() {                                                // R = dY X^T -> TMEM columns 0..127
+    umma::tc_fence_after();
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+      umma::mma_bf16_ss(tmem + 0, umma::make_smem_desc(umma::smem_u32(sdY) + kb * 32, 16, 1024),
+                        umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), i_kk, kb > 0);
+    umma::mma_commit(bar_r);
   };
   uint32_t iseq = 0, hseq = 0;
   for (int i = tid; i < 2 * HALF / 16; i += NT) reinterpret_cast<uint4*>(sW)[i] = make_uint4(0, 0, 0, 0);   // finite padding rows
   umma::fence_async_smem();
-  if (blockIdx.x < n_items && issuer) { load_cb(blockIdx.x); load_head(blockIdx.x, 0, 0); }
+  if (blockIdx.x < n_items && issuer) {
+    load_cb(blockIdx.x); load_xd(blockIdx.x, 0, 0); load_sg(blockIdx.x, 0);
+    umma::mbar_wait(bar_xd, 0);
+    issue_r();
+  }
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
     int db, c; p.dnc.divmod(it, db, c);
     const int q0 = c * TQ, qv = min(TQ, L - q0);
@@ -827,17 +892,8 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       int nit = it, nh = h + 1;                                        // the head-step after this one
       if (nh == H) { nit = it + gridDim.x; nh = 0; }
       const long long tk0 = clock64();
-      if (h == 0) umma::mbar_wait(bar_cb, iseq & 1);
-      umma::mbar_wait(bar_h, par);
+      umma::mbar_wait(bar_xd, par);
       const long long tk1 = clock64();
-      if (issuer) {
-        umma::tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)                                 // R = dY X^T
-          umma::mma_bf16_ss(tmem + 0, umma::make_smem_desc(umma::smem_u32(sdY) + kb * 32, 16, 1024),
-                            umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), i_kk, kb > 0);
-        umma::mma_commit(bar_r);
-      }
       for (int i = tid; i < TQ * 8; i += NT) {                         // Xw = w_q X,  dYs = e^{cs_t} dY
         const float w = s_w[i >> 3], e = s_ecs[i >> 3];
         float a[8], b[8];
@@ -861,8 +917,10 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           umma::tmem_ld32(t_lane + (uint32_t)s0, r);
           umma::tmem_ld_wait();
           decay_row32(l, t, I, J, s0, tab);
+          float d32[32];
+          load32(d32, s_dt + s0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] *= l[j] * s_dt[s0 + j];
+          for (int j = 0; j < 32; ++j) r[j] *= l[j] * d32[j];
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0.f;
@@ -871,9 +929,14 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int k = 0; k < 4; ++k)
           *reinterpret_cast<uint4*>(sW + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(r + 8 * k);
       }
-      umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
+      umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();   // W, Xw, dYs written; R, X, dY, tables consumed
       const long long tk3 = clock64();
       if (issuer) {
+        // next step's first load group goes out BEFORE this step's MMAs: the issuing thread stalls on the tensor-core
+        // queue while it feeds 24 MMAs, and a TMA request placed behind them would start ~1.5k cycles late
+        if (nit < n_items) load_xd(nit, nh, (hseq & 1) ^ 1);
+        if (h == 0) umma::mbar_wait(bar_cb, iseq & 1);
+        umma::mbar_wait(bar_sg, par);
         umma::tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {                               // dC += W B        (k = time q: valid frames only)
@@ -896,13 +959,16 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           umma::mma_bf16_ss(tmem + 256, umma::make_smem_desc(umma::smem_u32(sXw) + kb * 32, 16, 1024),
                             umma::make_smem_desc(umma::smem_u32(sG) + kb * 32, 16, 1024), i_kk, 1u);
         umma::mma_commit(bar_m);
+        if (nit < n_items) {                                           // next step's R, queued behind this step's MMAs
+          umma::mbar_wait(bar_xd, par ^ 1);
+          issue_r();
+        }
       }
       umma::mbar_wait(bar_m, par);
       umma::tc_fence_after();
-      __syncthreads();                                                 // every thread is done with this head's tables
-      if (issuer && nit < n_items) {
+      if (issuer && nit < n_items) {                                   // S, G (and C, B after the last head) are free
         if (nh == 0) load_cb(nit);
-        load_head(nit, nh, (hseq & 1) ^ 1);
+        load_sg(nit, nh);
       }
       if (p.dbg && blockIdx.x == 0 && tid == 0) {
         const long long tk4 = clock64();

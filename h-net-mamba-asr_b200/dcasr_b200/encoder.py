@@ -59,7 +59,15 @@ class ConvSubsampling4(nn.Module):
         self.proj = nn.Linear(d_model * (((n_mels - 1) // 2 - 1) // 2), d_model)
 
     def forward(self, feats: torch.Tensor, lengths: torch.Tensor):
-        x = self.conv(feats.unsqueeze(1))
+        x = feats.unsqueeze(1)
+        if x.is_cuda:
+            # NHWC end to end: cuDNN's tensor-core kernels are NHWC, and the default NCHW tensors made it transpose the
+            # 0.96 GB conv1 output twice per step (measured: 12.2 -> 11.4 ms fwd+bwd at 40 x 16 s).  Shapes, values and
+            # state_dict layout are unchanged; only the strides of the conv weights and intermediates differ.
+            if not self.conv[2].weight.is_contiguous(memory_format=torch.channels_last):
+                self.conv.to(memory_format=torch.channels_last)
+            x = x.contiguous(memory_format=torch.channels_last)
+        x = self.conv(x)
         B, C, T, F = x.shape
         return self.proj(x.transpose(1, 2).reshape(B, T, C * F)), _subsampled_length(lengths)
 
