@@ -40,7 +40,7 @@ constexpr int BWD_THREADS = 512;          // dx / dbc
 constexpr int HALF = TQ * 128;          // bytes of one [128 rows x 128 B] swizzled block (16 KB)
 constexpr int TAB_FLOATS = 9 * TQ + 8;  // cs, dt, w, ecs, eq [128 each] | f[4][128] | warp totals
 constexpr int TAB_BYTES = TAB_FLOATS * 4;
-constexpr int EXTRA_FLOATS = 12 * TQ + 3 * 16 + 8;   // dx kernel: per-column-group partial sums (no shared-memory atomics)
+constexpr int EXTRA_FLOATS = 12 * TQ + 3 * BWD_THREADS + 8;   // dx kernel: per-column-group / per-thread partial sums
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk16) {          // byte offset inside a [rows x 128 B] SW128 block
   return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
@@ -117,36 +117,28 @@ ssd_tables_kernel(const float* __restrict__ dt, const float* __restrict__ A_log,
   for (int i = threadIdx.x; i < 9 * TQ; i += TQ) out[i] = tab[i];
 }
 
-// decay factors l[j] = L[t, s0+j] (j < 32) of row t (row block I) against column block J <= I.  The case split is
-// warp-uniform and sits OUTSIDE the element loop.
-__device__ __forceinline__ void decay_row32(float* l, int t, int I, int J, int s0, const float* tab) {
-  const float* s_cs = tab; const float* s_f = tab + 5 * TQ;
-  const float cs_t = s_cs[t];
-  if (J < I) {
-    const float e_ref = __expf(cs_t - s_cs[32 * I - 1]);
-    const float4* f4 = reinterpret_cast<const float4*>(s_f + I * TQ + s0);   // warp-uniform address: 8 broadcast LDS.128
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 f = f4[j];
-      l[4 * j] = e_ref * f.x; l[4 * j + 1] = e_ref * f.y; l[4 * j + 2] = e_ref * f.z; l[4 * j + 3] = e_ref * f.w;
-    }
+// Balanced split of the lower-triangular 128 x 128 score tile over the 16 epilogue warps: warp (lq, cg) owns, in
+// each of the four 32-column blocks k, the 8 columns 32k + 8cg .. +7 of rows 32lq .. +31.  Every warp of a row
+// block then carries the same load (k < lq: one multiply per element through the block factor table; k == lq: one
+// exp per element; k > lq: zeros) instead of one warp doing the whole exp-heavy diagonal block while others idle.
+// l[j] = L[t, s0 + j], j < 8, for column block k (warp-uniform case split).
+__device__ __forceinline__ void decay8(float* l, int t, int I, int k, int s0, float cs_t, float e_ref, const float* tab) {
+  if (k < I) {
+    const float4 a = *reinterpret_cast<const float4*>(tab + 5 * TQ + I * TQ + s0);
+    const float4 b = *reinterpret_cast<const float4*>(tab + 5 * TQ + I * TQ + s0 + 4);
+    l[0] = e_ref * a.x; l[1] = e_ref * a.y; l[2] = e_ref * a.z; l[3] = e_ref * a.w;
+    l[4] = e_ref * b.x; l[5] = e_ref * b.y; l[6] = e_ref * b.z; l[7] = e_ref * b.w;
   } else {
-    const float4* c4 = reinterpret_cast<const float4*>(s_cs + s0);
+    const float4 a = *reinterpret_cast<const float4*>(tab + s0);
+    const float4 b = *reinterpret_cast<const float4*>(tab + s0 + 4);
+    const float c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 c = c4[j];
-      l[4 * j] = (s0 + 4 * j <= t) ? __expf(cs_t - c.x) : 0.f;
-      l[4 * j + 1] = (s0 + 4 * j + 1 <= t) ? __expf(cs_t - c.y) : 0.f;
-      l[4 * j + 2] = (s0 + 4 * j + 2 <= t) ? __expf(cs_t - c.z) : 0.f;
-      l[4 * j + 3] = (s0 + 4 * j + 3 <= t) ? __expf(cs_t - c.w) : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) l[j] = (s0 + j <= t) ? __expf(cs_t - c[j]) : 0.f;
   }
 }
-// 32 consecutive table entries (warp-uniform address) as 8 broadcast LDS.128
-__device__ __forceinline__ void load32(float* v, const float* src) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { const float4 f = s4[j]; v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w; }
+__device__ __forceinline__ void load8(float* v, const float* src) {
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 // ===================================================================================================
@@ -178,6 +170,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   constexpr int NCG = NT / 128;           // column groups: warp w -> TMEM lane quarter w%4, column group w/4
+  static_assert(NCG == 4, "the balanced score-tile split assumes 16 warps");
   constexpr int NB = 4 / NCG;             // 32-column blocks (of 128) and 16-column blocks (of 64) per thread
   constexpr int NTAB = NT - 32;           // lane 0 of the last warp issues TMA and MMAs
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -307,26 +300,29 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       umma::tc_fence_after();
       const long long tk2 = clock64();
       // ---- epilogue 1: M[t,s] = G[t,s] e^{cs_t - cs_s} dt_s (s <= t), bf16, K-major swizzled
-#pragma unroll
-      for (int bb = 0; bb < NB; ++bb) {
-        const int t = row, I = t >> 5, J = NB * cg + bb, s0 = 32 * J;
-        if (I >= nblk) break;                                          // padding rows: their M rows only feed unused y rows
-        float g[32];
-        if (J <= I) {
-          umma::tmem_ld32(t_lane + (uint32_t)s0, g);
-          umma::tmem_ld_wait();
-          float l[32], d32[32];
-          decay_row32(l, t, I, J, s0, tab);
-          load32(d32, s_dt + s0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] *= l[j] * d32[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] = 0.f;
-        }
+      if ((row >> 5) < nblk) {                                         // padding rows: their M rows only feed unused y rows
+        const int t = row, I = t >> 5;
+        const float cs_t = tab[t], e_ref = I > 0 ? __expf(cs_t - tab[32 * I - 1]) : 0.f;
+        float g[4][8];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<uint4*>(sM + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(g + 8 * k);
+          if (k <= I) umma::tmem_ld8(t_lane + (uint32_t)(32 * k + 8 * cg), g[k]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int s0 = 32 * k + 8 * cg;
+          if (k <= I) {
+            float l[8], d8[8];
+            decay8(l, t, I, k, s0, cs_t, e_ref, tab);
+            load8(d8, s_dt + s0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[k][j] *= l[j] * d8[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[k][j] = 0.f;
+          }
+          *reinterpret_cast<uint4*>(sM + (k >> 1) * HALF + swz(t, 4 * (k & 1) + cg)) = pack8(g[k]);
+        }
       }
       umma::fence_async_smem();
       umma::tc_fence_before();
@@ -526,6 +522,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                      const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
                      const BwdParams p) {
   constexpr int NCG = NT / 128, NB = 4 / NCG, NTAB = NT - 32;
+  static_assert(NCG == 4, "the balanced score-tile split assumes 16 warps");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   uint8_t* sC = base + D2_OFF_C; uint8_t* sB = base + D2_OFF_B; uint8_t* sX = base + D2_OFF_X;
@@ -541,7 +538,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
   const bool issuer = tid == NTAB;
-  static_assert(NCG <= 4 && NT / 32 <= 16, "partial-sum slots");
+  static_assert(NCG <= 4 && NT <= BWD_THREADS, "partial-sum slots");
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
     umma::mbar_init(bar_load, 1); umma::mbar_init(bar1, 1); umma::mbar_init(bar2, 1); umma::mbar_init(bar1b, 1);
@@ -582,9 +579,10 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     float* s_dcsA = xtra + (seq & 1) * EXTRA_FLOATS;                  // [4][128]  d cs_t, row terms (epilogue A)
     float* s_dcsB = s_dcsA + 4 * TQ;                                  // [4][128]  d cs_q, column terms (epilogue B)
     float* s_ddtx = s_dcsB + 4 * TQ;                                  // [4][128]  <du_q, x_q>
-    float* s_wdot = s_ddtx + 4 * TQ;                                  // [16] per warp: <Gst, S_in>
-    float* s_wsc = s_wdot + 16;                                       // [16] per warp: d cs_last from the chunk state
-    float* s_wdd = s_wsc + 16;                                        // [16] per warp: dD
+    // per THREAD (summed by the tail warp: a warp reduction here is a 5-deep shuffle chain on every warp's critical path)
+    float* s_pdot = s_ddtx + 4 * TQ;                                  // [NT] <Gst, S_in>
+    float* s_psc = s_pdot + NT;                                       // [NT] d cs_last from the chunk state
+    float* s_pdd = s_psc + NT;                                        // [NT] dD
     int t1, h, db, c; p.dH.divmod(it, t1, h); p.dnc.divmod(t1, db, c);
     const int dir = p.dB.div(db);
     const float A = -__expf(p.A_log[dir * H + h]);
@@ -633,8 +631,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
         for (int k = 0; k < 8; ++k) dot += a[k] * b[k];
       }
-      dot = warp_sum(dot);
-      if (lane == 0) s_wdot[warp] = s_ecs[TQ - 1] * dot;
+      s_pdot[tid] = dot;                                               // scaled by e^{cs_last} in the tail
     }
     umma::mbar_wait(bar1, par);
     umma::tc_fence_after();
@@ -646,32 +643,36 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     } else {
       const int t = row, I = t >> 5;
       float acc = 0.f;
-#pragma unroll
-      for (int bb = 0; bb < NB; ++bb) {
-        const int J = NB * cg + bb, s0 = 32 * J;
-        float g[32];
-        if (J <= I) {
-          float r[32], l[32];
-          umma::tmem_ld32(t_lane + (uint32_t)s0, g);
-          umma::tmem_ld32(t_lane + 128u + (uint32_t)s0, r);
-          umma::tmem_ld_wait();
-          decay_row32(l, t, I, J, s0, tab);
-          float d32[32];
-          load32(d32, s_dt + s0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            g[j] *= l[j];
-            // the row sums must use K exactly as the tensor core will see it (bf16): the column sums come out of
-            // du1 = K^T dY, and the two cancel in the cumulative sum -- any rounding asymmetry would survive
-            acc += r[j] * d32[j] * __bfloat162float(__float2bfloat16_rn(g[j]));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] = 0.f;
-        }
+      {
+        const float cs_t = tab[t], e_ref = I > 0 ? __expf(cs_t - tab[32 * I - 1]) : 0.f;
+        float g[4][8], r[4][8];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<uint4*>(sK + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(g + 8 * k);
+          if (k <= I) {
+            umma::tmem_ld8(t_lane + (uint32_t)(32 * k + 8 * cg), g[k]);
+            umma::tmem_ld8(t_lane + 128u + (uint32_t)(32 * k + 8 * cg), r[k]);
+          }
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int s0 = 32 * k + 8 * cg;
+          if (k <= I) {
+            float l[8], d8[8];
+            decay8(l, t, I, k, s0, cs_t, e_ref, tab);
+            load8(d8, s_dt + s0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              g[k][j] *= l[j];
+              // the row sums must use K exactly as the tensor core will see it (bf16): the column sums come out of
+              // du1 = K^T dY, and the two cancel in the cumulative sum -- any rounding asymmetry would survive
+              acc += r[k][j] * d8[j] * __bfloat162float(__float2bfloat16_rn(g[k][j]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[k][j] = 0.f;
+          }
+          *reinterpret_cast<uint4*>(sK + (k >> 1) * HALF + swz(t, 4 * (k & 1) + cg)) = pack8(g[k]);
+        }
       }
       float yd = 0.f;
       umma::mbar_wait(bar1b, par);
@@ -719,7 +720,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ---- epilogue B (thread = row q, 64/NCG of the 64 columns): dx, and the remaining d cs terms
     if ((q >> 5) >= nblk) {
       s_dcsB[cg * TQ + q] = 0.f; s_ddtx[cg * TQ + q] = 0.f;
-      if (lane == 0) { s_wsc[warp] = 0.f; s_wdd[warp] = 0.f; }
+      s_psc[tid] = 0.f; s_pdd[tid] = 0.f;
     } else {
       const float eq = s_eq[q], dtq = s_dt[q];
       float col = 0.f, sc = 0.f, dux = 0.f, dd = 0.f;
@@ -749,8 +750,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       col *= dtq; sc *= dtq * eq;
       s_dcsB[cg * TQ + q] = -(col + sc);
       s_ddtx[cg * TQ + q] = dux;
-      sc = warp_sum(sc); dd = warp_sum(dd);
-      if (lane == 0) { s_wsc[warp] = sc; s_wdd[warp] = dd; }
+      s_psc[tid] = sc; s_pdd[tid] = dd;
     }
     umma::tc_fence_before(); __syncthreads();                          // partial sums complete; du1 / du2 consumed
     // ---- reverse inclusive cumsum of d cs over the chunk -> ddt, dA_log: ONE warp (lane l owns frames 4l..4l+3);
@@ -765,8 +765,18 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         v[0] += a.x + b.x; v[1] += a.y + b.y; v[2] += a.z + b.z; v[3] += a.w + b.w;
         ddx[0] += d.x; ddx[1] += d.y; ddx[2] += d.z; ddx[3] += d.w;
       }
-      float extra = lane < NT / 32 ? s_wdot[lane] + s_wsc[lane] : 0.f;
-      float dd = lane < NT / 32 ? s_wdd[lane] : 0.f;
+      float extra = 0.f, dd = 0.f;
+      {
+        const float ecl = s_ecs[TQ - 1];
+#pragma unroll
+        for (int k = 0; k < NT / 128; ++k) {
+          const float4 a = *reinterpret_cast<const float4*>(s_pdot + 128 * k + 4 * lane);
+          const float4 b = *reinterpret_cast<const float4*>(s_psc + 128 * k + 4 * lane);
+          const float4 c4 = *reinterpret_cast<const float4*>(s_pdd + 128 * k + 4 * lane);
+          extra += ecl * (a.x + a.y + a.z + a.w) + (b.x + b.y + b.z + b.w);
+          dd += c4.x + c4.y + c4.z + c4.w;
+        }
+      }
       extra = warp_sum(extra); dd = warp_sum(dd);
       if (lane == 31) v[3] += extra;                                   // d cs of the chunk's last frame
       v[2] += v[3]; v[1] += v[2]; v[0] += v[1];                        // suffix sums inside the lane
@@ -809,6 +819,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                       const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
                       const BwdParams p) {
   constexpr int NCG = NT / 128, NB = 4 / NCG, NTAB = NT - 32;
+  static_assert(NCG == 4, "the balanced score-tile split assumes 16 warps");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   uint8_t* sC = base + D3_OFF_C; uint8_t* sB = base + D3_OFF_B; uint8_t* sX = base + D3_OFF_X;
@@ -907,27 +918,29 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       umma::mbar_wait(bar_r, par);
       umma::tc_fence_after();
       const long long tk2 = clock64();
-#pragma unroll
-      for (int bb = 0; bb < NB; ++bb) {   // W[t,q] = R[t,q] L[t,q] dt_q   (thread = row t, 128/NCG of the 128 columns)
-        const int t = row, I = t >> 5, J = NB * cg + bb, s0 = 32 * J;
-        if (I >= nblk) break;                                          // padding rows are never read (k-trimmed MMAs)
-        float r[32];
-        if (J <= I) {
-          float l[32];
-          umma::tmem_ld32(t_lane + (uint32_t)s0, r);
-          umma::tmem_ld_wait();
-          decay_row32(l, t, I, J, s0, tab);
-          float d32[32];
-          load32(d32, s_dt + s0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] *= l[j] * d32[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0.f;
-        }
+      if ((row >> 5) < nblk) {            // W[t,q] = R[t,q] L[t,q] dt_q; padding rows are never read (k-trimmed MMAs)
+        const int t = row, I = t >> 5;
+        const float cs_t = tab[t], e_ref = I > 0 ? __expf(cs_t - tab[32 * I - 1]) : 0.f;
+        float r[4][8];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<uint4*>(sW + (J >> 1) * HALF + swz(t, 4 * (J & 1) + k)) = pack8(r + 8 * k);
+          if (k <= I) umma::tmem_ld8(t_lane + (uint32_t)(32 * k + 8 * cg), r[k]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int s0 = 32 * k + 8 * cg;
+          if (k <= I) {
+            float l[8], d8[8];
+            decay8(l, t, I, k, s0, cs_t, e_ref, tab);
+            load8(d8, s_dt + s0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[k][j] *= l[j] * d8[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[k][j] = 0.f;
+          }
+          *reinterpret_cast<uint4*>(sW + (k >> 1) * HALF + swz(t, 4 * (k & 1) + cg)) = pack8(r[k]);
+        }
       }
       umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();   // W, Xw, dYs written; R, X, dY, tables consumed
       const long long tk3 = clock64();
