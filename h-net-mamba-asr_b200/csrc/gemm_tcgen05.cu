@@ -57,13 +57,23 @@ constexpr int A_STAGE = BM * BK * 2;                          // 16 KB
 constexpr int GEMM_THREADS = 64 + 256;                        // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr int EPI_WARPS = 8;
 
-constexpr int EPI_STAGE_FLOATS = 32 * 33;                     // per-warp [32 rows][33] fp32 transpose buffer
 template <int BN> struct GemmCfg {
   static constexpr int B_STAGE = BN * BK * 2;                 // 16 / 32 KB
-  static constexpr int STAGES = BN == 256 ? 4 : 6;          // as many bytes in flight as 227 KB allows
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 7);   // as many bytes in flight as 227 KB allows
+  static constexpr int TMEM_COLS = BN == 192 ? 512 : 2 * BN;           // two accumulators; a power of two
   static constexpr int RING = STAGES * (A_STAGE + B_STAGE);
-  static constexpr int SMEM = RING + EPI_WARPS * EPI_STAGE_FLOATS * 4 + 256 + 1024;
+  static constexpr int SMEM = RING + 256 + 1024;
 };
+
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 
 struct GemmParams {
   int M, N, K;
@@ -95,8 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE;
-  float* sEpi = reinterpret_cast<float*>(smem + Cfg::RING);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING + EPI_WARPS * EPI_STAGE_FLOATS * 4);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;                       // [2]
   uint64_t* tmem_empty = tmem_full + 2;                       // [2]
@@ -114,7 +123,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int a = 0; a < 2; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], EPI_WARPS); }
     umma::fence_barrier_init();
   }
-  if (warp == 1) umma::tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) umma::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   umma::tc_fence_before();
   __syncthreads();
   if (CL > 1) umma::cluster_sync_all();        // the peer's barriers are initialised before anything is multicast into them
@@ -218,8 +227,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       umma::mbar_wait(&tmem_full[acc], aph);
       umma::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16);
-      float* st = sEpi + ew * EPI_STAGE_FLOATS;
-      const int rsub = lane >> 2, cgrp = lane & 3;          // after the transpose: lane -> (row within 8, 8-column group)
+      // TMEM hands each lane one ROW: 32 consecutive columns = 64 B (bf16) / 128 B (fp32) of that row.  They leave as
+      // 256-bit stores, one full 32-byte sector per lane and instruction -- no shared-memory transpose (the first
+      // version spent 12 k warp-instructions per tile in one: the K = 384 projections were epilogue-bound).
+      const int row = m0 + lq * 32 + lane;
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         const int col0 = n0 + c0;
@@ -227,69 +238,75 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
         umma::tmem_ld32(t_addr + (uint32_t)c0, v);
         umma::tmem_ld_wait();
-        // TMEM hands each lane one ROW; a direct store would touch 32 different lines per instruction.  Transpose
-        // through a padded per-warp buffer so that 4 lanes cover 32 consecutive columns of one row.
+        if (row < p.M) {
+        if (p.bias) {
+          if (col0 + 32 <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = v[j];
-        __syncwarp();
-        const int col = col0 + cgrp * 8;
-        const bool full8 = col + 8 <= p.N;
-        float bias8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bias8[e] = (p.bias && col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rl = i * 8 + rsub;
-          const int row = m0 + lq * 32 + rl;
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = st[rl * 33 + cgrp * 8 + e] + bias8[e];
-          if (row < p.M && col < p.N) {
-            if (p.atomic) {
-              float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
-              if (full8 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (col + e < p.N) atomicAdd(c + e, o[e]);
-              }
-            } else if (p.c_is_f32) {
-              float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
-              const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col : nullptr;
-              if (full8 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
-                if (r) {
-                  float t[8];
-                  ldv<float, 8>(r, t);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] += t[e];
-                }
-                *reinterpret_cast<float4*>(c) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(c + 4) = make_float4(o[4], o[5], o[6], o[7]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (col + e < p.N) c[e] = o[e] + (r ? r[e] : 0.f);
-              }
-            } else {
-              __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col;
-              const __nv_bfloat16* r = p.R ? reinterpret_cast<const __nv_bfloat16*>(p.R) + (long long)row * p.ldr + col : nullptr;
-              if (full8 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
-                if (r) {
-                  float t[8];
-                  ldv<__nv_bfloat16, 8>(r, t);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] += t[e];
-                }
-                stv<__nv_bfloat16, 8>(c, o);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (col + e < p.N) c[e] = __float2bfloat16_rn(o[e] + (r ? __bfloat162float(r[e]) : 0.f));
-              }
-            }
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);       // warp-uniform addresses: broadcast
+          } else {
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
           }
         }
-        __syncwarp();
+        if (p.atomic) {
+          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+          } else {
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(c + j, v[j]);
+          }
+        } else if (p.c_is_f32) {
+          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+          const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 31) == 0)) {
+            if (r) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8];
+                ldg256(r + j, reinterpret_cast<uint32_t*>(t));
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j + e] += t[e];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) stg256(c + j, reinterpret_cast<const uint32_t*>(v + j));
+          } else {
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) c[j] = v[j] + (r ? r[j] : 0.f);
+          }
+        } else {
+          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+          const __nv_bfloat16* r = p.R ? reinterpret_cast<const __nv_bfloat16*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 31) == 0)) {
+            if (r) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 16) {
+                uint32_t t[8];
+                ldg256(r + j, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t[e]));
+                  v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 16) {
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                o[e] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              stg256(c + j, o);
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) c[j] = __float2bfloat16_rn(v[j] + (r ? __bfloat162float(r[j]) : 0.f));
+          }
+        }
+        }
+        __syncwarp();                                       // tcgen05.ld is warp-collective: reconverge before the next one
       }
       umma::tc_fence_before();
       __syncwarp();
@@ -299,7 +316,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   umma::tc_fence_before();
   __syncthreads();
   if (CL > 1) umma::cluster_sync_all();        // no CTA leaves while its peer can still signal or fill its shared memory
-  if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 1) umma::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // naive reference for the self test
@@ -334,6 +351,40 @@ __global__ void maxdiff_kernel(const float* a, const float* b, long long n, floa
 
 using namespace hnb;
 
+// tile width: the widest of 256 / 192 / 128 columns that wastes at most ~10 % of the MMA work on the ragged last tile
+// (128-wide MMAs read 8 KB of operands per 64 cycles -- the shared-memory limit -- so wider is better when it fits)
+static int gemm_tile_n(int N) {
+  int best = 128, best_waste = cdiv(N, 128) * 128 - N;
+  const int cand[2] = {256, 192};
+  for (int i = 0; i < 2; ++i) {
+    const int w = cdiv(N, cand[i]) * cand[i] - N;
+    if (N >= cand[i] && w * 10 <= N) return cand[i];
+    if (N >= cand[i] && w < best_waste) { best = cand[i]; best_waste = w; }
+  }
+  return best;
+}
+
+static int gemm_sm_count() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+
+// Split-K factor for a weight-gradient GEMM (K = tokens): the one that minimises  waves x (k-blocks per item + fixed
+// per-item cost)  for the tile grid hnb_gemm_bf16 will actually use.  The caller zero-fills C when the answer is > 1.
+extern "C" int hnb_gemm_splitk_hint(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 1;
+  const int tiles = cdiv(M, 128) * cdiv(N, gemm_tile_n(N)), kb = cdiv(K, 64), sms = gemm_sm_count();
+  int best = 1;
+  double best_cost = 1e30;
+  for (int sk = 1; sk <= 32 && sk * 4 <= kb; ++sk) {
+    const int per = cdiv(kb, sk), eff_sk = cdiv(kb, per);
+    const double cost = (double)cdiv((long long)tiles * eff_sk, sms) * (per + 8.0) + 0.5 * eff_sk;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = eff_sk; }
+  }
+  return best;
+}
+
 extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const void* B, long long ldb, int transB, int M,
                              int N, int K, const float* bias, const void* R, long long ldr, void* C, long long ldc,
                              int c_dtype, int splitk, void* stream) {
@@ -344,11 +395,9 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   HNB_CHECK_ARG(c_dtype == HNB_F32 || c_dtype == HNB_BF16, "gemm_bf16: bad output dtype");
   if (splitk < 1) splitk = 1;
   HNB_CHECK_ARG(splitk == 1 || (c_dtype == HNB_F32 && !bias && !R), "gemm_bf16: split-K needs fp32 C and no bias/residual");
-  // tile width: 256 columns unless that would waste more than ~10 % of the MMA work on the ragged last tile
-  const int waste256 = cdiv(N, 256) * 256 - N;
-  const int BN = (N >= 256 && waste256 * 10 <= N) ? 256 : 128;
+  const int BN = gemm_tile_n(N);
   static const int cl_env = getenv("HNB_GEMM_CLUSTER") ? atoi(getenv("HNB_GEMM_CLUSTER")) : 1;   // tuning knob
-  const int CL = (cl_env == 2 && cdiv(M, BM) >= 4) ? 2 : 1;
+  const int CL = (cl_env == 2 && cdiv(M, BM) >= 4 && BN != 192) ? 2 : 1;
   CUtensorMap tmA, tmB;
   int rc;
   {
@@ -376,8 +425,7 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   p.c_is_f32 = (c_dtype == HNB_F32);
   p.atomic = p.splitk > 1;
   const int n_items = p.groups_m * p.tiles_n * p.splitk;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int sms = gemm_sm_count();
   const int grid = CL * (n_items < sms / CL ? n_items : sms / CL);
   cudaStream_t st = (cudaStream_t)stream;
   cudaLaunchConfig_t cfg = {};
@@ -395,8 +443,9 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   } while (0)
 #define LAUNCH_BN(TA, TB)                                                                                            \
   do {                                                                                                               \
-    if (BN == 256) { if (CL == 2) LAUNCH(TA, TB, 256, 2); else LAUNCH(TA, TB, 256, 1); }                              \
-    else           { if (CL == 2) LAUNCH(TA, TB, 128, 2); else LAUNCH(TA, TB, 128, 1); }                              \
+    if (BN == 256)      { if (CL == 2) LAUNCH(TA, TB, 256, 2); else LAUNCH(TA, TB, 256, 1); }                         \
+    else if (BN == 192) { LAUNCH(TA, TB, 192, 1); }                                                                  \
+    else                { if (CL == 2) LAUNCH(TA, TB, 128, 2); else LAUNCH(TA, TB, 128, 1); }                         \
   } while (0)
   if (!transA && !transB) LAUNCH_BN(0, 0);
   else if (!transA && transB) LAUNCH_BN(0, 1);

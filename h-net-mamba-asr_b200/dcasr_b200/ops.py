@@ -63,10 +63,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
 
 
 def wgrad_splitk(k_tokens: int, m: int, n: int) -> int:
-    """split-K factor for weight gradients (K = tokens): enough CTAs to cover 148 SMs x 2."""
-    tiles = ((m + 127) // 128) * ((n + 127) // 128)
-    kb = (k_tokens + 63) // 64
-    return max(1, min(kb, (296 + tiles - 1) // tiles))
+    """split-K factor for weight gradients (K = tokens), chosen by the library for the tile grid it will use."""
+    return max(1, int(lib().raw("gemm_splitk_hint")(int(m), int(n), int(k_tokens))))
 
 
 # ------------------------------------------------------------------------------------------------

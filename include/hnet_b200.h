@@ -193,6 +193,11 @@ int hnb_pack_mixer_params(const float* in_w, const float* out_w, const float* co
 int hnb_gemm_bf16(const void* A, long long lda, int transA, const void* B, long long ldb, int transB,
                   int M, int N, int K, const float* bias, const void* R, long long ldr,
                   void* C, long long ldc, int c_dtype, int splitk, void* stream);
+
+/* Recommended split-K factor for hnb_gemm_bf16 on this (M, N, K): fills whole waves of the tile grid the library will
+ * use.  > 1 means: zero-fill an fp32 C and pass the value as `splitk`.  (Weight gradients of the reference's
+ * nn.Linear layers, src/dcasr/models/mamba_block.py:45-47 via mamba_ssm; K = tokens.) */
+int hnb_gemm_splitk_hint(int M, int N, int K);
 /* exact fp32 GEMM on CUDA cores (decode / fp32 parity path), same operand conventions */
 int hnb_gemm_f32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
                  int M, int N, int K, const float* bias, const float* R, long long ldr,

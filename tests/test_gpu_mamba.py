@@ -28,6 +28,21 @@ def test_umma_selftest():
     assert max(errs) < 2e-3, errs          # K=424 bf16 products, fp32 accumulation order differences only
 
 
+def test_umma_selftest_cluster_path():
+    """The optional 2-CTA multicast path of the GEMM (HNB_GEMM_CLUSTER=2, read once per process) against the naive kernel."""
+    import subprocess
+    import sys
+    code = ("import sys, ctypes; sys.path[:0] = %r; from dcasr_b200._lib import lib, stream; import torch; "
+            "err = (ctypes.c_float * 8)(); rc = lib().raw('umma_selftest')(ctypes.cast(err, ctypes.c_void_p), stream()); "
+            "torch.cuda.synchronize(); print('ERRS', rc, max(err[i] for i in range(5)))") % (sys.path,)
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "HNB_GEMM_CLUSTER": "2"}, capture_output=True,
+                         text=True, timeout=300)
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("ERRS")]
+    assert line, out.stdout + out.stderr
+    _, rc, e = line[0].split()
+    assert int(rc) == 0 and float(e) < 2e-3, line
+
+
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(15920, 3616, 384), (776, 520, 1032), (384, 1808, 15920)])
 def test_gemm_bf16_vs_torch(ta, tb, M, N, K):
