@@ -1,0 +1,190 @@
+// ConvSubsampling4 front end (reference src/dcasr/models/encoder.py:55-70): the first Conv2d(1 -> C, k3, s2) + ReLU,
+// forward and backward.  The layer has ONE input channel: 9 MACs per output, but a [B, C, T1, F1] result of
+// 0.96 GB (bf16, 40 x 16 s).  Through cuDNN + ATen the step paid for that tensor eight times (fp32->bf16 casts, a
+// separate ReLU forward/backward, NCHW<->NHWC transposes, an fp32 SGEMM-style conv); here it is written once (forward,
+// straight into the NHWC layout cuDNN's tensor-core kernels of the second convolution want) and read once (backward:
+// the ReLU mask is recomputed from the input, dW1 / db1 are reduced on the fly).
+//
+// Work decomposition: a block owns RB consecutive (b, t) output rows; a thread owns CPT consecutive channels of one
+// of PX pixel lanes and keeps its 9*CPT taps in registers; the three input rows a (b, t) row needs are staged in shared
+// memory.  NHWC stores/loads are 16 bytes (forward, 8 channels) / 8 bytes (backward, 4 channels) per thread, contiguous
+// across the threads of a pixel.
+#include "common.cuh"
+
+namespace hnb {
+
+constexpr int SUB_RB = 8;            // (b, t) rows per block
+
+template <int CPT>
+__global__ void __launch_bounds__(256)
+sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B, int T,
+                     int F, int C, int T1, int F1, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float s_in[];                       // [3][F]
+  const int CG = C / CPT;                               // threads per pixel
+  const int cgp = threadIdx.x % CG, pl = threadIdx.x / CG, PX = blockDim.x / CG;
+  const int c0 = cgp * CPT;
+  float wt[CPT][9], bs[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wt[i][k] = __ldg(w + (long long)(c0 + i) * 9 + k);
+    bs[i] = __ldg(bias + c0 + i);
+  }
+  const long long rows = (long long)B * T1;
+  for (long long r = (long long)blockIdx.x * SUB_RB; r < min(rows, (long long)(blockIdx.x + 1) * SUB_RB); ++r) {
+    const int b = (int)(r / T1), t = (int)(r % T1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) s_in[i] = x[((long long)b * T + 2 * t + i / F) * F + i % F];
+    __syncthreads();
+    for (int f = pl; f < F1; f += PX) {
+      float xin[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
+      float o[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        float a = bs[i];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a = fmaf(wt[i][k], xin[k], a);
+        o[i] = fmaxf(a, 0.f);
+      }
+      stv<__nv_bfloat16, CPT>(out + ((r * F1 + f) * C + c0), o);
+    }
+  }
+}
+
+// backward: dA1 (NHWC, bf16) -> dW1 [C, 9], db1 [C] (fp32, accumulated).  The input needs no gradient.
+template <int CPT>
+__global__ void __launch_bounds__(256)
+sub_conv1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     const __nv_bfloat16* __restrict__ dout, int B, int T, int F, int C, int T1, int F1, int rows_per_block,
+                     float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float s_in[];                       // [3][F], then reused for the block reduction
+  const int CG = C / CPT;
+  const int cgp = threadIdx.x % CG, pl = threadIdx.x / CG, PX = blockDim.x / CG;
+  const int c0 = cgp * CPT;
+  float wt[CPT][9], bs[CPT], gw[CPT][9], gb[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { wt[i][k] = __ldg(w + (long long)(c0 + i) * 9 + k); gw[i][k] = 0.f; }
+    bs[i] = __ldg(bias + c0 + i); gb[i] = 0.f;
+  }
+  const long long rows = (long long)B * T1;
+  const long long r_end = min(rows, (long long)(blockIdx.x + 1) * rows_per_block);
+  for (long long r = (long long)blockIdx.x * rows_per_block; r < r_end; ++r) {
+    const int b = (int)(r / T1), t = (int)(r % T1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) s_in[i] = x[((long long)b * T + 2 * t + i / F) * F + i % F];
+    __syncthreads();
+    for (int f0 = pl; f0 < F1; f0 += 4 * PX) {          // four gradient vectors in flight per thread
+      float g4[4][CPT];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = f0 + u * PX;
+        if (f < F1) ldv<__nv_bfloat16, CPT>(dout + ((r * F1 + f) * C + c0), g4[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = f0 + u * PX;
+        if (f >= F1) break;
+        float xin[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          float a = bs[i];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a = fmaf(wt[i][k], xin[k], a);
+          const float gi = a > 0.f ? g4[u][i] : 0.f;       // ReLU mask recomputed, not stored
+          gb[i] += gi;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) gw[i][k] = fmaf(gi, xin[k], gw[i][k]);
+        }
+      }
+    }
+  }
+  // pixel lanes -> shared memory -> lane 0 of each channel group -> one global atomic per value and block
+  __syncthreads();
+  float* red = s_in;                                     // [PX-1][CG][10*CPT]  (the launch sizes shared memory for it)
+  if (pl > 0) {
+    float* dst = red + ((long long)(pl - 1) * CG + cgp) * (10 * CPT);
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dst[i * 10 + k] = gw[i][k];
+      dst[i * 10 + 9] = gb[i];
+    }
+  }
+  __syncthreads();
+  if (pl == 0) {
+    for (int q = 0; q < PX - 1; ++q) {
+      const float* src = red + ((long long)q * CG + cgp) * (10 * CPT);
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gw[i][k] += src[i * 10 + k];
+        gb[i] += src[i * 10 + 9];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(dw + (long long)(c0 + i) * 9 + k, gw[i][k]);
+      atomicAdd(db + c0 + i, gb[i]);
+    }
+  }
+}
+
+}  // namespace hnb
+
+using namespace hnb;
+
+static int sub_check(const char* who, int B, int T, int F, int C) {
+  if (!(B > 0 && T >= 3 && F >= 3 && C > 0)) { set_error("%s: bad sizes", who); return HNB_ERR_INVALID_ARG; }
+  if (C % 8 || C > 1024) {
+    set_error("%s: channels must be a multiple of 8, at most 1024 (got %d)", who, C);
+    return HNB_ERR_UNSUPPORTED;
+  }
+  return HNB_OK;
+}
+
+extern "C" int hnb_subsample_conv1_fwd(const float* feats, const float* w, const float* bias, int B, int T, int F, int C,
+                                       void* out, void* stream) {
+  HNB_CHECK_ARG(feats && w && bias && out, "subsample_conv1_fwd: null pointer");
+  int rc = sub_check("subsample_conv1_fwd", B, T, F, C);
+  if (rc) return rc;
+  const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
+  const long long rows = (long long)B * T1;
+  const int CG = C / 8, PX = 256 / CG > 0 ? 256 / CG : 1;
+  sub_conv1_fwd_kernel<8><<<cdiv(rows, SUB_RB), CG * PX, 3 * F * sizeof(float), (cudaStream_t)stream>>>(
+      feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
+  HNB_LAUNCH_CHECK("subsample_conv1_fwd");
+  return HNB_OK;
+}
+
+extern "C" int hnb_subsample_conv1_bwd(const float* feats, const float* w, const float* bias, const void* dout, int B,
+                                       int T, int F, int C, float* dw, float* db, void* stream) {
+  HNB_CHECK_ARG(feats && w && bias && dout && dw && db, "subsample_conv1_bwd: null pointer");
+  int rc = sub_check("subsample_conv1_bwd", B, T, F, C);
+  if (rc) return rc;
+  const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
+  const long long rows = (long long)B * T1;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int CG = C / 4, PX = 256 / CG > 0 ? 256 / CG : 1;
+  int blocks = sms * 4;                                  // few blocks: each ends in 10*C global atomics
+  if (blocks > rows) blocks = (int)rows;
+  const int rpb = cdiv(rows, blocks);
+  blocks = cdiv(rows, rpb);
+  size_t smem = 3 * (size_t)F * sizeof(float);
+  const size_t red = (size_t)(PX > 1 ? PX - 1 : 0) * CG * 40 * sizeof(float);
+  if (red > smem) smem = red;
+  HNB_CUDA_CALL(cudaFuncSetAttribute(sub_conv1_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sub_conv1_bwd_kernel<4><<<blocks, CG * PX, smem, (cudaStream_t)stream>>>(feats, w, bias, (const __nv_bfloat16*)dout, B, T,
+                                                                     F, C, T1, F1, rpb, dw, db);
+  HNB_LAUNCH_CHECK("subsample_conv1_bwd");
+  return HNB_OK;
+}

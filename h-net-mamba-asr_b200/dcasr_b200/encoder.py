@@ -48,8 +48,34 @@ def _subsampled_length(lengths: torch.Tensor) -> torch.Tensor:
     return (((lengths - 1) // 2 - 1) // 2).clamp_min(0)
 
 
+class _Conv1ReluFn(torch.autograd.Function):
+    """relu(Conv2d(1 -> C, k3, s2)(x)) of ConvSubsampling4 as ONE kernel each way (csrc/subsample_kernels.cu): bf16 result
+    written once, directly in the NHWC layout the tensor-core kernels of the second convolution read; the backward
+    recomputes the ReLU mask from the input and reduces dW / db on the fly.  The input features need no gradient."""
+
+    @staticmethod
+    def forward(ctx, feats, w, b):
+        f32 = feats.float().contiguous()
+        wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
+        ctx.save_for_backward(f32, wf, bf)
+        ctx.meta = (w.dtype, b.dtype)
+        return ops.subsample_conv1_fwd(f32, wf, bf)
+
+    @staticmethod
+    def backward(ctx, dout):
+        f32, wf, bf = ctx.saved_tensors
+        d = dout if dout.dtype == torch.bfloat16 else dout.to(torch.bfloat16)
+        d = d.contiguous(memory_format=torch.channels_last)
+        dw, db = ops.subsample_conv1_bwd(f32, wf, bf, d)
+        return None, dw.to(ctx.meta[0]), db.to(ctx.meta[1])
+
+
 class ConvSubsampling4(nn.Module):
-    """x4 time downsample (two Conv2d k3 s2 + ReLU, then Linear).  Library kernels; outside the hot path."""
+    """x4 time downsample (two Conv2d k3 s2 + ReLU, then Linear) -- reference encoder.py:55-70; same module tree and
+    state_dict.  Under CUDA bf16 autocast (the training configuration) the one-input-channel first convolution + ReLU
+    runs as the fused kernels above and everything downstream stays NHWC; the second convolution (803 GFLOP of
+    implicit GEMM per step) and the Linear are library kernels (cuDNN / cuBLAS).  Any other setting (fp32 decode, CPU)
+    takes the reference's own op sequence."""
 
     def __init__(self, n_mels: int, d_model: int):
         super().__init__()
@@ -57,18 +83,26 @@ class ConvSubsampling4(nn.Module):
             nn.Conv2d(1, d_model, kernel_size=3, stride=2), nn.ReLU(),
             nn.Conv2d(d_model, d_model, kernel_size=3, stride=2), nn.ReLU())
         self.proj = nn.Linear(d_model * (((n_mels - 1) // 2 - 1) // 2), d_model)
+        self.fused_front_end = True          # False: always the reference op sequence (parity tests)
 
     def forward(self, feats: torch.Tensor, lengths: torch.Tensor):
-        x = feats.unsqueeze(1)
-        if x.is_cuda:
-            # NHWC end to end: cuDNN's tensor-core kernels are NHWC, and the default NCHW tensors made it transpose the
-            # 0.96 GB conv1 output twice per step (measured: 12.2 -> 11.4 ms fwd+bwd at 40 x 16 s).  Shapes, values and
-            # state_dict layout are unchanged; only the strides of the conv weights and intermediates differ.
-            if not self.conv[2].weight.is_contiguous(memory_format=torch.channels_last):
-                self.conv.to(memory_format=torch.channels_last)
-            x = x.contiguous(memory_format=torch.channels_last)
-        x = self.conv(x)
+        c1, c2 = self.conv[0], self.conv[2]
+        fused = (self.fused_front_end and feats.is_cuda and _autocast_dtype() == torch.bfloat16 and feats.shape[1] >= 3 and feats.shape[2] >= 3
+                 and not feats.requires_grad and ops.subsample_conv1_supported(c1.out_channels))
+        if fused:
+            a1 = _Conv1ReluFn.apply(feats, c1.weight, c1.bias)             # bf16, channels_last
+            w2 = c2.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            x = torch.relu(torch.nn.functional.conv2d(a1, w2, c2.bias.to(torch.bfloat16), stride=2))
+        else:
+            x = self.conv(feats.unsqueeze(1))
         B, C, T, F = x.shape
+        if fused and x.is_contiguous(memory_format=torch.channels_last):
+            # NHWC memory is already [B, T, F, C]: flatten it as it lies and permute the (2.8 M element) weight's
+            # columns instead of copying the (116 M element) activation into channel-major order, forward and backward
+            O = self.proj.out_features
+            w3 = self.proj.weight.view(O, C, F).transpose(1, 2).reshape(O, F * C)
+            y = torch.nn.functional.linear(x.permute(0, 2, 3, 1).reshape(B, T, F * C), w3, self.proj.bias)
+            return y, _subsampled_length(lengths)
         return self.proj(x.transpose(1, 2).reshape(B, T, C * F)), _subsampled_length(lengths)
 
 

@@ -274,3 +274,31 @@ def pack_mixer_params(params, ndir, d, di, N, H, dstride, w_dtype, device):
                 dtype_code(w_dtype), conv_w, conv_b, dt_bias, A_log, Dk, norm_w, stream())
     return (Win, Wout, conv_w.view(ndir, C, 4), conv_b.view(ndir, C), dt_bias.view(ndir, H), A_log.view(ndir, H),
             Dk.view(ndir, H), norm_w.view(ndir, di))
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvSubsampling4 front end
+# ------------------------------------------------------------------------------------------------
+def subsample_conv1_supported(C: int) -> bool:
+    return C % 8 == 0 and C <= 1024
+
+
+def subsample_conv1_fwd(feats, w, b):
+    """feats [B, T, F] fp32, w [C, 1, 3, 3] fp32, b [C] -> relu(conv) as bf16 [B, C, T1, F1] in channels_last memory."""
+    B, T, F = feats.shape
+    C = w.shape[0]
+    T1, F1 = (T - 3) // 2 + 1, (F - 3) // 2 + 1
+    out = torch.empty((B, T1, F1, C), dtype=torch.bfloat16, device=feats.device)       # NHWC storage
+    lib().call("subsample_conv1_fwd", feats, w, b, B, T, F, C, out, stream())
+    return out.permute(0, 3, 1, 2)                                                      # logical NCHW, channels_last strides
+
+
+def subsample_conv1_bwd(feats, w, b, dout):
+    """dout: bf16 [B, C, T1, F1] channels_last -> (dw [C, 1, 3, 3], db [C]) fp32."""
+    B, T, F = feats.shape
+    C = w.shape[0]
+    acc = torch.zeros(C * 10, dtype=torch.float32, device=feats.device)
+    dw, db = acc[:C * 9], acc[C * 9:]
+    lib().call("subsample_conv1_bwd", feats, w, b, dout.permute(0, 2, 3, 1), B, T, F, C, dw, db, stream())
+    return dw.view(C, 1, 3, 3), db
+

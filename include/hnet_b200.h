@@ -205,6 +205,19 @@ int hnb_gemm_f32(const float* A, long long lda, int transA, const float* B, long
 /* on-device self test of the tcgen05 descriptor variants; returns 0 and fills max_abs_err[4] (host) */
 int hnb_umma_selftest(float* max_abs_err_host, void* stream);
 
+/* ---- ConvSubsampling4 front end (the step before the hot path) ---------------- */
+
+/* First Conv2d(1 -> C, kernel 3, stride 2) + ReLU of ConvSubsampling4 (src/dcasr/models/encoder.py:55-70),
+ * input [B, T, F] fp32 (one channel), weight [C, 9] fp32, bias [C] fp32.
+ * out: bf16, logical [B, C, T1, F1] stored NHWC, i.e. [B, T1, F1, C] contiguous (T1 = (T-3)/2+1, F1 = (F-3)/2+1):
+ * the layout the tensor-core kernels of the second convolution consume.  C % 8 == 0, C <= 1024. */
+int hnb_subsample_conv1_fwd(const float* feats, const float* w, const float* bias, int B, int T, int F, int C,
+                            void* out, void* stream);
+/* Backward of the same: dout (bf16, NHWC) -> dw [C, 9] and db [C], ACCUMULATED into pre-zeroed fp32 buffers.
+ * The ReLU mask is recomputed from feats / w / bias; the input needs no gradient. */
+int hnb_subsample_conv1_bwd(const float* feats, const float* w, const float* bias, const void* dout, int B,
+                            int T, int F, int C, float* dw, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

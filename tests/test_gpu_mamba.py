@@ -383,3 +383,44 @@ def test_block_at_baseline_dims_vs_oracle(d, L, lengths, dtype, tol):
     gs, gr = dict(blk.named_parameters()), dict(ref.named_parameters())
     for k in ("fwd.in_proj.weight", "bwd.out_proj.weight", "fwd.conv1d.weight", "norm.weight"):
         assert rel_err(gs[k].grad, gr[k].grad) < (tol if dtype == torch.float32 else 3e-2), k
+
+
+@pytest.mark.parametrize("B,T,C", [(3, 203, 128), (2, 1598, 384), (2, 64, 512)])
+def test_subsample_front_end_fused_vs_reference_ops(B, T, C):
+    """ConvSubsampling4 under bf16 autocast: fused conv1+ReLU kernels + NHWC conv2 against the reference's own op
+    sequence (nn.Sequential of Conv2d/ReLU) on the same module, values and parameter gradients."""
+    import dcasr_b200 as dd
+    torch.manual_seed(0)
+    sub = dd.ConvSubsampling4(80, C).to(DEV)
+    feats = torch.randn(B, T, 80, device=DEV)
+    lens = torch.full((B,), T, device=DEV)
+    res = {}
+    for fused in (True, False):
+        sub.fused_front_end = fused
+        sub.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y, ol = sub(feats, lens)
+        (y.float().pow(2).mean()).backward()
+        res[fused] = (y.float().detach(), [p.grad.float().clone() for p in sub.parameters()])
+    assert rel_err(res[True][0], res[False][0]) < 2e-2
+    for g1, g0 in zip(res[True][1], res[False][1]):
+        assert rel_err(g1, g0) < 3e-2, (g1.shape, rel_err(g1, g0))
+
+
+def test_subsample_conv1_kernels_fp32_reference():
+    """The fused kernels alone against fp32 torch ops: relu(conv2d) values (bf16 rounding only) and dW1 / db1."""
+    from dcasr_b200 import ops
+    torch.manual_seed(1)
+    B, T, C = 2, 131, 384
+    feats = torch.randn(B, T, 80, device=DEV)
+    w = (torch.randn(C, 1, 3, 3, device=DEV) * 0.3).requires_grad_()
+    b = (torch.randn(C, device=DEV) * 0.1).requires_grad_()
+    ref = F.relu(F.conv2d(feats.unsqueeze(1), w, b, stride=2))
+    out = ops.subsample_conv1_fwd(feats, w.detach().contiguous(), b.detach().contiguous())
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert rel_err(out.float(), ref) < 4e-3                       # bf16 storage
+    g = torch.randn_like(ref).to(torch.bfloat16)
+    ref.backward(g.float())
+    dw, db = ops.subsample_conv1_bwd(feats, w.detach().contiguous(), b.detach().contiguous(),
+                                     g.contiguous(memory_format=torch.channels_last))
+    assert rel_err(dw, w.grad) < 1e-4 and rel_err(db, b.grad) < 1e-4
