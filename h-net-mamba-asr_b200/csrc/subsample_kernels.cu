@@ -3,7 +3,7 @@
 // 0.96 GB (bf16, 40 x 16 s).  Through cuDNN + ATen the step paid for that tensor eight times (fp32->bf16 casts, a
 // separate ReLU forward/backward, NCHW<->NHWC transposes, an fp32 SGEMM-style conv); here it is written once (forward,
 // straight into the NHWC layout cuDNN's tensor-core kernels of the second convolution want) and read once (backward:
-// the ReLU mask is recomputed from the input, dW1 / db1 are reduced on the fly).
+// ReLU mask from the saved output, dW1 / db1 reduced on the fly).
 //
 // Work decomposition: a block owns RB consecutive (b, t) output rows; a thread owns CPT consecutive channels of one
 // of PX pixel lanes and keeps its 9*CPT taps in registers; the three input rows a (b, t) row needs are staged in shared
@@ -53,22 +53,25 @@ sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
   }
 }
 
-// backward: dA1 (NHWC, bf16) -> dW1 [C, 9], db1 [C] (fp32, accumulated).  The input needs no gradient.
+// backward: dA1 and the saved output A1 (both NHWC, bf16) -> dW1 [C, 9], db1 [C] (fp32, accumulated).  The ReLU mask
+// is A1 > 0, as in the reference's threshold_backward; the input needs no gradient.  A block reduces its rows in
+// registers, then across its pixel lanes through shared memory, then issues 10 vector reductions per channel quad.
 template <int CPT>
-__global__ void __launch_bounds__(256)
-sub_conv1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                     const __nv_bfloat16* __restrict__ dout, int B, int T, int F, int C, int T1, int F1, int rows_per_block,
-                     float* __restrict__ dw, float* __restrict__ db) {
+__global__ void __launch_bounds__(256, 3)
+sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ a1, const __nv_bfloat16* __restrict__ dout,
+                     int B, int T, int F, int C, int T1, int F1, int rows_per_block, float* __restrict__ dw,
+                     float* __restrict__ db) {
+  static_assert(CPT == 4, "vector reductions below assume channel quads");
   extern __shared__ float s_in[];                       // [3][F], then reused for the block reduction
   const int CG = C / CPT;
   const int cgp = threadIdx.x % CG, pl = threadIdx.x / CG, PX = blockDim.x / CG;
   const int c0 = cgp * CPT;
-  float wt[CPT][9], bs[CPT], gw[CPT][9], gb[CPT];
+  float gw[CPT][9], gb[CPT];
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { wt[i][k] = __ldg(w + (long long)(c0 + i) * 9 + k); gw[i][k] = 0.f; }
-    bs[i] = __ldg(bias + c0 + i); gb[i] = 0.f;
+    for (int k = 0; k < 9; ++k) gw[i][k] = 0.f;
+    gb[i] = 0.f;
   }
   const long long rows = (long long)B * T1;
   const long long r_end = min(rows, (long long)(blockIdx.x + 1) * rows_per_block);
@@ -77,26 +80,34 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     __syncthreads();
     for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) s_in[i] = x[((long long)b * T + 2 * t + i / F) * F + i % F];
     __syncthreads();
-    for (int f0 = pl; f0 < F1; f0 += 4 * PX) {          // four gradient vectors in flight per thread
-      float g4[4][CPT];
+    for (int f0 = pl; f0 < F1; f0 += 4 * PX) {          // four pixel vectors of each tensor in flight per thread
+      uint2 gr[4], ar[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int f = f0 + u * PX;
-        if (f < F1) ldv<__nv_bfloat16, CPT>(dout + ((r * F1 + f) * C + c0), g4[u]);
+        if (f < F1) {
+          gr[u] = __ldg(reinterpret_cast<const uint2*>(dout + ((r * F1 + f) * C + c0)));
+          ar[u] = __ldg(reinterpret_cast<const uint2*>(a1 + ((r * F1 + f) * C + c0)));
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int f = f0 + u * PX;
         if (f >= F1) break;
-        float xin[9];
+        float xin[9], g[CPT], a[CPT];
 #pragma unroll
         for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
+        {
+          const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gr[u]);
+          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ar[u]);
+          const float2 g0 = __bfloat1622float2(gh[0]), g1 = __bfloat1622float2(gh[1]);
+          const float2 a0 = __bfloat1622float2(ah[0]), a1v = __bfloat1622float2(ah[1]);
+          g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
+          a[0] = a0.x; a[1] = a0.y; a[2] = a1v.x; a[3] = a1v.y;
+        }
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-          float a = bs[i];
-#pragma unroll
-          for (int k = 0; k < 9; ++k) a = fmaf(wt[i][k], xin[k], a);
-          const float gi = a > 0.f ? g4[u][i] : 0.f;       // ReLU mask recomputed, not stored
+          const float gi = a[i] > 0.f ? g[i] : 0.f;
           gb[i] += gi;
 #pragma unroll
           for (int k = 0; k < 9; ++k) gw[i][k] = fmaf(gi, xin[k], gw[i][k]);
@@ -104,35 +115,37 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       }
     }
   }
-  // pixel lanes -> shared memory -> lane 0 of each channel group -> one global atomic per value and block
   __syncthreads();
-  float* red = s_in;                                     // [PX-1][CG][10*CPT]  (the launch sizes shared memory for it)
+  float* red = s_in;                                     // [PX-1][CG][40]  (the launch sizes shared memory for it)
   if (pl > 0) {
-    float* dst = red + ((long long)(pl - 1) * CG + cgp) * (10 * CPT);
+    float* dst = red + ((long long)(pl - 1) * CG + cgp) * 40;
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) dst[i * 10 + k] = gw[i][k];
-      dst[i * 10 + 9] = gb[i];
+      for (int k = 0; k < 9; ++k) dst[i * 9 + k] = gw[i][k];
+      dst[36 + i] = gb[i];
     }
   }
   __syncthreads();
   if (pl == 0) {
     for (int q = 0; q < PX - 1; ++q) {
-      const float* src = red + ((long long)q * CG + cgp) * (10 * CPT);
+      const float* src = red + ((long long)q * CG + cgp) * 40;
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) gw[i][k] += src[i * 10 + k];
-        gb[i] += src[i * 10 + 9];
+        for (int k = 0; k < 9; ++k) gw[i][k] += src[i * 9 + k];
+        gb[i] += src[36 + i];
       }
     }
+    // dw rows of a channel quad are 36 contiguous floats starting at a multiple of 144 bytes: 9 + 1 vector reductions
+    float* wq = dw + (long long)c0 * 9;
+    const float* flat = &gw[0][0];
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) atomicAdd(dw + (long long)(c0 + i) * 9 + k, gw[i][k]);
-      atomicAdd(db + c0 + i, gb[i]);
-    }
+    for (int k = 0; k < 9; ++k)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wq + 4 * k), "f"(flat[4 * k]), "f"(flat[4 * k + 1]),
+                   "f"(flat[4 * k + 2]), "f"(flat[4 * k + 3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(db + c0), "f"(gb[0]), "f"(gb[1]), "f"(gb[2]), "f"(gb[3])
+                 : "memory");
   }
 }
 
@@ -163,9 +176,11 @@ extern "C" int hnb_subsample_conv1_fwd(const float* feats, const float* w, const
   return HNB_OK;
 }
 
-extern "C" int hnb_subsample_conv1_bwd(const float* feats, const float* w, const float* bias, const void* dout, int B,
-                                       int T, int F, int C, float* dw, float* db, void* stream) {
-  HNB_CHECK_ARG(feats && w && bias && dout && dw && db, "subsample_conv1_bwd: null pointer");
+extern "C" int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const void* dout, int B, int T, int F, int C,
+                                       float* dw, float* db, void* stream) {
+  HNB_CHECK_ARG(feats && a1 && dout && dw && db, "subsample_conv1_bwd: null pointer");
+  HNB_CHECK_ARG(((reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(db)) & 15) == 0,
+                "subsample_conv1_bwd: dw and db must be 16-byte aligned");
   int rc = sub_check("subsample_conv1_bwd", B, T, F, C);
   if (rc) return rc;
   const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
@@ -175,7 +190,7 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const float* w, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   const int CG = C / 4, PX = 256 / CG > 0 ? 256 / CG : 1;
-  int blocks = sms * 4;                                  // few blocks: each ends in 10*C global atomics
+  int blocks = sms * 6;                                  // two waves of three resident blocks; each ends in 10 reductions per quad
   if (blocks > rows) blocks = (int)rows;
   const int rpb = cdiv(rows, blocks);
   blocks = cdiv(rows, rpb);
@@ -183,8 +198,8 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const float* w, const
   const size_t red = (size_t)(PX > 1 ? PX - 1 : 0) * CG * 40 * sizeof(float);
   if (red > smem) smem = red;
   HNB_CUDA_CALL(cudaFuncSetAttribute(sub_conv1_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sub_conv1_bwd_kernel<4><<<blocks, CG * PX, smem, (cudaStream_t)stream>>>(feats, w, bias, (const __nv_bfloat16*)dout, B, T,
-                                                                     F, C, T1, F1, rpb, dw, db);
+  sub_conv1_bwd_kernel<4><<<blocks, CG * PX, smem, (cudaStream_t)stream>>>(feats, (const __nv_bfloat16*)a1,
+      (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
   HNB_LAUNCH_CHECK("subsample_conv1_bwd");
   return HNB_OK;
 }

@@ -51,22 +51,22 @@ def _subsampled_length(lengths: torch.Tensor) -> torch.Tensor:
 class _Conv1ReluFn(torch.autograd.Function):
     """relu(Conv2d(1 -> C, k3, s2)(x)) of ConvSubsampling4 as ONE kernel each way (csrc/subsample_kernels.cu): bf16 result
     written once, directly in the NHWC layout the tensor-core kernels of the second convolution read; the backward
-    recomputes the ReLU mask from the input and reduces dW / db on the fly.  The input features need no gradient."""
+    masks with the saved output (a1 > 0, as threshold_backward does) and reduces dW / db on the fly.  The input features need no gradient."""
 
     @staticmethod
     def forward(ctx, feats, w, b):
         f32 = feats.float().contiguous()
-        wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
-        ctx.save_for_backward(f32, wf, bf)
+        a1 = ops.subsample_conv1_fwd(f32, w.detach().float().contiguous(), b.detach().float().contiguous())
+        ctx.save_for_backward(f32, a1)            # a1 is alive anyway: it is the second convolution's saved input
         ctx.meta = (w.dtype, b.dtype)
-        return ops.subsample_conv1_fwd(f32, wf, bf)
+        return a1
 
     @staticmethod
     def backward(ctx, dout):
-        f32, wf, bf = ctx.saved_tensors
+        f32, a1 = ctx.saved_tensors
         d = dout if dout.dtype == torch.bfloat16 else dout.to(torch.bfloat16)
         d = d.contiguous(memory_format=torch.channels_last)
-        dw, db = ops.subsample_conv1_bwd(f32, wf, bf, d)
+        dw, db = ops.subsample_conv1_bwd(f32, a1, d)
         return None, dw.to(ctx.meta[0]), db.to(ctx.meta[1])
 
 

@@ -293,12 +293,11 @@ def subsample_conv1_fwd(feats, w, b):
     return out.permute(0, 3, 1, 2)                                                      # logical NCHW, channels_last strides
 
 
-def subsample_conv1_bwd(feats, w, b, dout):
-    """dout: bf16 [B, C, T1, F1] channels_last -> (dw [C, 1, 3, 3], db [C]) fp32."""
+def subsample_conv1_bwd(feats, a1, dout):
+    """a1 (forward output), dout: bf16 [B, C, T1, F1] channels_last -> (dw [C, 1, 3, 3], db [C]) fp32."""
     B, T, F = feats.shape
-    C = w.shape[0]
+    C = a1.shape[1]
     acc = torch.zeros(C * 10, dtype=torch.float32, device=feats.device)
     dw, db = acc[:C * 9], acc[C * 9:]
-    lib().call("subsample_conv1_bwd", feats, w, b, dout.permute(0, 2, 3, 1), B, T, F, C, dw, db, stream())
+    lib().call("subsample_conv1_bwd", feats, a1.permute(0, 2, 3, 1), dout.permute(0, 2, 3, 1), B, T, F, C, dw, db, stream())
     return dw.view(C, 1, 3, 3), db
-

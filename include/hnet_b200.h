@@ -213,10 +213,10 @@ int hnb_umma_selftest(float* max_abs_err_host, void* stream);
  * the layout the tensor-core kernels of the second convolution consume.  C % 8 == 0, C <= 1024. */
 int hnb_subsample_conv1_fwd(const float* feats, const float* w, const float* bias, int B, int T, int F, int C,
                             void* out, void* stream);
-/* Backward of the same: dout (bf16, NHWC) -> dw [C, 9] and db [C], ACCUMULATED into pre-zeroed fp32 buffers.
- * The ReLU mask is recomputed from feats / w / bias; the input needs no gradient. */
-int hnb_subsample_conv1_bwd(const float* feats, const float* w, const float* bias, const void* dout, int B,
-                            int T, int F, int C, float* dw, float* db, void* stream);
+/* Backward of the same: a1 (the forward's output) and dout (both bf16, NHWC) -> dw [C, 9] and db [C], ACCUMULATED
+ * into pre-zeroed, 16-byte aligned fp32 buffers.  ReLU mask = a1 > 0; the input needs no gradient. */
+int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const void* dout, int B, int T, int F, int C,
+                            float* dw, float* db, void* stream);
 
 #ifdef __cplusplus
 }
