@@ -48,6 +48,33 @@ template <> struct V16<__nv_bfloat16> {
   }
 };
 
+// 2 channels per thread (backward, bf16): half the taps / windows / accumulators per thread, so twice the resident warps
+template <typename T> struct V8;
+template <> struct V8<float> {
+  static constexpr int N = 2;
+  using raw_t = uint2;
+  static __device__ __forceinline__ raw_t zero() { return make_uint2(0, 0); }
+  static __device__ __forceinline__ raw_t ldg(const float* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  static __device__ __forceinline__ void st(float* p, const raw_t& r) { *reinterpret_cast<uint2*>(p) = r; }
+  static __device__ __forceinline__ void unpack(const raw_t& r, float* v) { v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); }
+  static __device__ __forceinline__ raw_t pack(const float* v) { return make_uint2(__float_as_uint(v[0]), __float_as_uint(v[1])); }
+};
+template <> struct V8<__nv_bfloat16> {
+  static constexpr int N = 2;
+  using raw_t = uint32_t;
+  static __device__ __forceinline__ raw_t zero() { return 0u; }
+  static __device__ __forceinline__ raw_t ldg(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const raw_t& r) { *reinterpret_cast<uint32_t*>(p) = r; }
+  static __device__ __forceinline__ void unpack(const raw_t& r, float* v) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r));
+    v[0] = a.x; v[1] = a.y;
+  }
+  static __device__ __forceinline__ raw_t pack(const float* v) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+};
+
 // sigmoid: the fp32 path keeps ex2+rcp (parity 1e-3 through 20 blocks); bf16 activations take one MUFU (tanh.approx,
 // abs. error ~5e-4, below the bf16 rounding of the result)
 template <typename T> __device__ __forceinline__ float sigmoid_t(float x) { return sigmoid_f(x); }
@@ -153,17 +180,17 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 // backward.  dout[s] for channel c comes from dxc (c < di) or dBC (c >= di), both of the activation dtype; the
 // pre-activation is recomputed from zxbcdt.  d input[s'] = sum_j w[j] dpre[s'+3-j];  dw[j] = sum_s dpre[s] in[s-3+j].
 // A segment owns RUN = TS*NTILE - 3 positions: its last 3 tile positions recompute the dpre halo of the next segment.
-template <typename T, int TS, int NTILE, int MINB = 2>
+template <typename T, typename VIO, int TS, int NTILE, int MINB>
 __global__ void __launch_bounds__(CONV_CT * CONV_SEG, MINB)
 conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long ldz, long long dstride,
                 const T* __restrict__ dBC, const float* __restrict__ ddt, const int* __restrict__ lengths,
                 const float* __restrict__ conv_w, const float* __restrict__ conv_b, const float* __restrict__ dt_bias,
                 int ndir, int B, int L, int di, int N, int H, T* __restrict__ dzx, float* __restrict__ dconv_w,
                 float* __restrict__ dconv_b, float* __restrict__ ddt_bias, int vec_red) {
-  constexpr int VN = V16<T>::N;
+  constexpr int VN = VIO::N;
   constexpr int RUN = TS * NTILE - 3;
-  static_assert(VN == 4 && TS > 3, "layout");
-  __shared__ float s_red[CONV_SEG - 1][20][CONV_CT];      // parameter-gradient partials of segments 1..3
+  static_assert(TS > 3, "layout");
+  __shared__ float s_red[CONV_SEG - 1][5 * VN][CONV_CT];      // parameter-gradient partials of segments 1..3
   __shared__ float s_dtb[64];
   const int ct = threadIdx.x % CONV_CT, sg = threadIdx.x / CONV_CT;
   const int dir = blockIdx.z / B, bi = blockIdx.z % B;
@@ -196,29 +223,29 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
     const long long gld = is_x ? di : 2 * N;
     const T* src = rowbase + xoff + c;
     T* dst = drowbase + xoff + c;
-    typename V16<T>::raw_t h[3];
+    typename VIO::raw_t h[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int s = sb - 3 + k;
-      h[k] = s >= 0 ? V16<T>::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : V16<T>::zero();
+      h[k] = s >= 0 ? VIO::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : VIO::zero();
     }
     float win[3][VN], dp[3][VN];
-    V16<T>::unpack(h[0], win[0]); V16<T>::unpack(h[1], win[1]); V16<T>::unpack(h[2], win[2]);
+    VIO::unpack(h[0], win[0]); VIO::unpack(h[1], win[1]); VIO::unpack(h[2], win[2]);
 #pragma unroll
     for (int i = 0; i < VN; ++i) { dp[0][i] = 0.f; dp[1][i] = 0.f; dp[2][i] = 0.f; }
-    typename V16<T>::raw_t xn[TS], gn[TS];                              // register double buffer (see forward)
+    typename VIO::raw_t xn[TS], gn[TS];                              // register double buffer (see forward)
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
       const bool ok = sb + k < L;
-      xn[k] = ok ? V16<T>::ldg(src + (long long)scan_to_nat(dir, sb + k, len) * ldz) : V16<T>::zero();
-      gn[k] = ok ? V16<T>::ldg(gsrc + (long long)(sb + k) * gld) : V16<T>::zero();
+      xn[k] = ok ? VIO::ldg(src + (long long)scan_to_nat(dir, sb + k, len) * ldz) : VIO::zero();
+      gn[k] = ok ? VIO::ldg(gsrc + (long long)(sb + k) * gld) : VIO::zero();
     }
 #pragma unroll 2
     for (int tile = 0; tile < NTILE; ++tile) {
       const int s0 = sb + tile * TS;
       if (s0 >= se + 3) break;
       const bool first = tile == 0, last = tile == NTILE - 1;
-      typename V16<T>::raw_t xr[TS], gr[TS];
+      typename VIO::raw_t xr[TS], gr[TS];
 #pragma unroll
       for (int k = 0; k < TS; ++k) { xr[k] = xn[k]; gr[k] = gn[k]; }
       if (!last) {
@@ -226,16 +253,16 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
         for (int k = 0; k < TS; ++k) {
           const int s = s0 + TS + k;
           const bool ok = s < L;
-          xn[k] = ok ? V16<T>::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : V16<T>::zero();
-          gn[k] = ok ? V16<T>::ldg(gsrc + (long long)s * gld) : V16<T>::zero();
+          xn[k] = ok ? VIO::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : VIO::zero();
+          gn[k] = ok ? VIO::ldg(gsrc + (long long)s * gld) : VIO::zero();
         }
       }
 #pragma unroll
       for (int k = 0; k < TS; ++k) {
         const int s = s0 + k;
         float cur[VN], g[VN], dcur[VN];
-        V16<T>::unpack(xr[k], cur);
-        V16<T>::unpack(gr[k], g);
+        VIO::unpack(xr[k], cur);
+        VIO::unpack(gr[k], g);
         const bool own = !(k >= TS - 3 && last);                        // halo positions belong to the next segment
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
@@ -254,7 +281,7 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
 #pragma unroll
           for (int i = 0; i < VN; ++i)
             o[i] = w[i][3] * dp[0][i] + w[i][2] * dp[1][i] + w[i][1] * dp[2][i] + w[i][0] * dcur[i];
-          V16<T>::st(dst + (long long)scan_to_nat(dir, sp, len) * ldz, V16<T>::pack(o));
+          VIO::st(dst + (long long)scan_to_nat(dir, sp, len) * ldz, VIO::pack(o));
         }
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
@@ -270,7 +297,7 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
     for (int i = 0; i < VN; ++i) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) s_red[sg - 1][i * 4 + j][ct] = gw[i][j];
-      s_red[sg - 1][16 + i][ct] = gb[i];
+      s_red[sg - 1][4 * VN + i][ct] = gb[i];
     }
   }
   __syncthreads();
@@ -281,13 +308,18 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
       for (int i = 0; i < VN; ++i) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) gw[i][j] += s_red[q][i * 4 + j][ct];
-        gb[i] += s_red[q][16 + i][ct];
+        gb[i] += s_red[q][4 * VN + i][ct];
       }
     }
 #pragma unroll
     for (int i = 0; i < VN; ++i)
       red_add4(dconv_w + ((long long)dir * C + c + i) * 4, gw[i][0], gw[i][1], gw[i][2], gw[i][3], vec_red);
-    red_add4(dconv_b + (long long)dir * C + c, gb[0], gb[1], gb[2], gb[3], vec_red);
+    if (VN == 4) {
+      red_add4(dconv_b + (long long)dir * C + c, gb[0], gb[1], gb[VN - 2], gb[VN - 1], vec_red);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) atomicAdd(dconv_b + (long long)dir * C + c + i, gb[i]);
+    }
   }
   // dt: d raw = ddt * sigmoid(raw + bias); one column block per (row, segment group) does it
   if (blockIdx.x == 0) {
@@ -356,23 +388,27 @@ extern "C" int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long
   int rc = conv_check("conv_bwd", dtype, ldz, dstride, ndir, B, L, di, N, H);
   if (rc) return rc;
   const int C = di + 2 * N;
-  dim3 grid(cdiv(C / 4, CONV_CT), cdiv(L, CONV_SEG * (CONV_B_TS * CONV_B_NT - 3)), ndir * B);
   cudaStream_t st = (cudaStream_t)stream;
   const int vec = ((reinterpret_cast<uintptr_t>(dconv_w) | reinterpret_cast<uintptr_t>(dconv_b)) & 15) == 0;
   static const int variant = getenv("HNB_CONV_BWD_VARIANT") ? atoi(getenv("HNB_CONV_BWD_VARIANT")) : 0;   // tuning knob
-  if (dtype == HNB_BF16 && variant == 1)
-    conv_bwd_kernel<__nv_bfloat16, 8, 4, 2><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+  const int ysegs = cdiv(L, CONV_SEG * (CONV_B_TS * CONV_B_NT - 3));
+  if (dtype == HNB_BF16 && variant == 2) {
+    // 2 channels per thread (64 registers, 4 resident blocks): measured SLOWER (130 vs 89 us), 4-byte accesses cost more than occupancy gains
+    dim3 grid(cdiv(C / 2, CONV_CT), ysegs, ndir * B);
+    conv_bwd_kernel<__nv_bfloat16, V8<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 4><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
         (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
         conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
-  else if (dtype == HNB_BF16)
-    conv_bwd_kernel<__nv_bfloat16, CONV_B_TS, CONV_B_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+  } else if (dtype == HNB_BF16) {
+    dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
+    conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
         (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
         conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
-  else if (dtype == HNB_F32)
-    conv_bwd_kernel<float, CONV_B_TS, CONV_B_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt,
+  } else if (dtype == HNB_F32) {
+    dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
+    conv_bwd_kernel<float, V16<float>, CONV_B_TS, CONV_B_NT, 2><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt,
         (const float*)dxc, ldz, dstride, (const float*)dBC, ddt, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H,
         (float*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
-  else { set_error("conv_bwd: unsupported dtype"); return HNB_ERR_INVALID_ARG; }
+  } else { set_error("conv_bwd: unsupported dtype"); return HNB_ERR_INVALID_ARG; }
   HNB_LAUNCH_CHECK("conv_bwd");
   return HNB_OK;
 }

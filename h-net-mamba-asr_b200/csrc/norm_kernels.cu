@@ -60,7 +60,7 @@ layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, 
 // keeps its dgamma/dbeta columns in registers; one shared-memory reduction + atomics per block.
 // ---------------------------------------------------------------------------------------------
 template <typename TDY, typename TX, typename TDX, int VN, int NV>
-__global__ void __launch_bounds__(NORM_WARPS * 32)
+__global__ void __launch_bounds__(NORM_WARPS * 32, (NV * VN <= 16 ? 3 : 1))
 layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const TDX* __restrict__ dres,
                      long long rows, int d, TDX* __restrict__ dx, float* __restrict__ dgamma,
@@ -131,10 +131,25 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// gated RMSNorm forward: warp per (direction, natural token).  y is read at the token's scan
-// position, z from the natural row of zxbcdt; the result lands in natural order.
+// gated RMSNorm: warp per (direction, natural token).  y is read at the token's scan position, z from the
+// natural row of zxbcdt; results land in natural order.  Both kernels are INSTRUCTION-bound (ncu: issue slots
+// 60-70 % busy at 45-55 % of HBM peak), so the row is read from global memory once, kept packed in registers
+// (NV vectors of VN elements per lane, fully unrolled) and every sigmoid is evaluated once.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VN>
+template <typename T, int VN> struct RawVec;
+template <> struct RawVec<float, 1> { using t = float; };
+template <> struct RawVec<float, 4> { using t = uint4; };
+template <> struct RawVec<__nv_bfloat16, 1> { using t = __nv_bfloat16; };
+template <> struct RawVec<__nv_bfloat16, 4> { using t = uint2; };
+template <> struct RawVec<__nv_bfloat16, 8> { using t = uint4; };
+template <typename T, int VN> __device__ __forceinline__ typename RawVec<T, VN>::t ld_raw(const T* p) {
+  return *reinterpret_cast<const typename RawVec<T, VN>::t*>(p);
+}
+template <typename T, int VN> __device__ __forceinline__ void unpack_raw(const typename RawVec<T, VN>::t& r, float* v) {
+  ldv<T, VN>(reinterpret_cast<const T*>(&r), v);          // register-to-register: the "load" folds into moves / shifts
+}
+
+template <typename T, int VN, int NV>
 __global__ void __launch_bounds__(NORM_WARPS * 32)
 gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long long ldz, long long dstride, const int* __restrict__ lengths,
                       const float* __restrict__ w, int ndir, int B, int L, int di, float eps, T* __restrict__ out,
@@ -150,31 +165,44 @@ gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long lo
   const int s = scan_to_nat(dir, t, len);                           // the map is an involution
   const T* yr = y + ((long long)dir * T_ + (long long)bi * L + s) * di;
   const T* zr = zx + tok * ldz + (long long)dir * dstride;
-  float q = 0.f;
-  for (int c = lane * VN; c < di; c += 32 * VN) {
-    float a[VN], z[VN];
-    ldv<T, VN>(yr + c, a); ldv<T, VN>(zr + c, z);
+  typename RawVec<T, VN>::t ry[NV], rz[NV];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) { const float g = a[i] * z[i] * sigmoid_t<T>(z[i]); q += g * g; }
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * VN;
+    if (c < di) { ry[k] = ld_raw<T, VN>(yr + c); rz[k] = ld_raw<T, VN>(zr + c); }
+  }
+  float g[NV][VN];
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * VN;
+    if (c < di) {
+      float a[VN], z[VN];
+      unpack_raw<T, VN>(ry[k], a); unpack_raw<T, VN>(rz[k], z);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { g[k][i] = a[i] * z[i] * sigmoid_t<T>(z[i]); q = fmaf(g[k][i], g[k][i], q); }
+    }
   }
   const float rs = rsqrtf(warp_sum(q) / di + eps);
   if (lane == 0) rstd_out[(long long)dir * T_ + tok] = rs;
   T* o = out + tok * ((long long)ndir * di) + (long long)dir * di;
   const float* wr = w + (long long)dir * di;
-  for (int c = lane * VN; c < di; c += 32 * VN) {
-    float a[VN], z[VN], ww[VN];
-    ldv<T, VN>(yr + c, a); ldv<T, VN>(zr + c, z); ldv<float, VN>(wr + c, ww);
 #pragma unroll
-    for (int i = 0; i < VN; ++i) a[i] = a[i] * z[i] * sigmoid_t<T>(z[i]) * rs * ww[i];
-    stv<T, VN>(o + c, a);
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * VN;
+    if (c < di) {
+      float ww[VN];
+      ldv<float, VN>(wr + c, ww);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) g[k][i] *= rs * ww[i];
+      stv<T, VN>(o + c, g[k]);
+    }
   }
 }
 
 // backward: dout (natural) -> dy (scan order), dz (natural, into dzxbcdt), dw (accumulated).
-// Two passes over the row (the second one hits L1) keep the live state to the per-lane dw accumulators, so
-// that several CTAs fit per SM; the first version held four row-sized register arrays and ran at 1 CTA/SM.
 template <typename T, int VN, int NV>
-__global__ void __launch_bounds__(NORM_WARPS * 32)
+__global__ void __launch_bounds__(NORM_WARPS * 32, (NV * VN <= 32 ? 2 : 1))
 gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const T* __restrict__ zx, long long ldz,
                       long long dstride, const int* __restrict__ lengths, const float* __restrict__ w,
                       const float* __restrict__ rstd, int ndir, int B, int L, int di, T* __restrict__ dy,
@@ -197,32 +225,46 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
     const T* zr = zx + tok * ldz + (long long)dir * dstride;
     const T* gr = dout + tok * ((long long)ndir * di) + (long long)dir * di;
     const float rs = rstd[(long long)dir * T_ + tok];
+    typename RawVec<T, VN>::t ry[NV], rz[NV], rg[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+      if (c < di) { ry[k] = ld_raw<T, VN>(y + yoff + c); rz[k] = ld_raw<T, VN>(zr + c); rg[k] = ld_raw<T, VN>(gr + c); }
+    }
+    constexpr bool KEEP_SG = NV * VN <= 24;                         // wider rows: re-evaluate rather than spill
+    float sg[KEEP_SG ? NV : 1][VN];                                 // sigmoid(z): one evaluation per element
     float s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * VN;
       if (c < di) {
         float yv[VN], zv[VN], go[VN], ww[VN];
-        ldv<T, VN>(y + yoff + c, yv); ldv<T, VN>(zr + c, zv); ldv<T, VN>(gr + c, go); ldv<float, VN>(wr + c, ww);
+        unpack_raw<T, VN>(ry[k], yv); unpack_raw<T, VN>(rz[k], zv); unpack_raw<T, VN>(rg[k], go);
+        ldv<float, VN>(wr + c, ww);
 #pragma unroll
-        for (int i = 0; i < VN; ++i) s2 += go[i] * ww[i] * yv[i] * zv[i] * sigmoid_t<T>(zv[i]) * rs;
+        for (int i = 0; i < VN; ++i) {
+          const float sgi = sigmoid_t<T>(zv[i]);
+          if (KEEP_SG) sg[k][i] = sgi;
+          s2 = fmaf(go[i] * ww[i], yv[i] * zv[i] * sgi, s2);
+        }
       }
     }
-    s2 = warp_sum(s2) / di;
+    s2 = warp_sum(s2) * rs / di;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * VN;
       if (c < di) {
         float yv[VN], zv[VN], go[VN], ww[VN], o1[VN], o2[VN];
-        ldv<T, VN>(y + yoff + c, yv); ldv<T, VN>(zr + c, zv); ldv<T, VN>(gr + c, go); ldv<float, VN>(wr + c, ww);
+        unpack_raw<T, VN>(ry[k], yv); unpack_raw<T, VN>(rz[k], zv); unpack_raw<T, VN>(rg[k], go);
+        ldv<float, VN>(wr + c, ww);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          const float sg = sigmoid_t<T>(zv[i]);
-          const float gh = yv[i] * zv[i] * sg * rs;                  // normalised gated value
-          aw[k][i] += go[i] * gh;
-          const float dg = rs * (go[i] * ww[i] - gh * s2);
-          o1[i] = dg * zv[i] * sg;                                   // d y
-          o2[i] = dg * yv[i] * sg * (1.f + zv[i] * (1.f - sg));      // d z
+          const float sgi = KEEP_SG ? sg[KEEP_SG ? k : 0][i] : sigmoid_t<T>(zv[i]);
+          const float gh = yv[i] * zv[i] * sgi * rs;                 // normalised gated value
+          aw[k][i] = fmaf(go[i], gh, aw[k][i]);
+          const float dg = rs * (go[i] * ww[i] - gh * s2) * sgi;
+          o1[i] = dg * zv[i];                                        // d y
+          o2[i] = dg * yv[i] * fmaf(zv[i], 1.f - sgi, 1.f);          // d z
         }
         stv<T, VN>(dy + yoff + c, o1);
         stv<T, VN>(dzx + tok * ldz + (long long)dir * dstride + c, o2);
@@ -363,11 +405,22 @@ extern "C" int hnb_gated_norm_fwd(const void* y, const void* zxbcdt, int dtype, 
                   al(out, 4 * esz(dtype)) && al(norm_w, 16);
   const bool v8 = dtype == HNB_BF16 && di % 8 == 0 && ldz % 8 == 0 && dstride % 8 == 0 && al(y, 16) && al(zxbcdt, 16) &&
                   al(out, 16) && al(norm_w, 16);
-#define RUN(T, VN) gated_norm_fwd_kernel<T, VN><<<grid, NORM_WARPS * 32, 0, st>>>( \
+  const int vn = v8 ? 8 : (v4 ? 4 : 1);
+  const int nv = cdiv(di, 32 * vn);
+  HNB_CHECK_ARG(nv <= 16, "gated_norm_fwd: d_inner=%d too large", di);
+#define RUN2(T, VN, NV) gated_norm_fwd_kernel<T, VN, NV><<<grid, NORM_WARPS * 32, 0, st>>>( \
       (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, ndir, B, L, di, eps, (T*)out, rstd)
+#define RUN(T, VN)                                                             \
+  do {                                                                         \
+    if (nv <= 1) RUN2(T, VN, 1); else if (nv <= 2) RUN2(T, VN, 2);             \
+    else if (nv <= 3) RUN2(T, VN, 3); else if (nv <= 4) RUN2(T, VN, 4);        \
+    else if (nv <= 6) RUN2(T, VN, 6); else if (nv <= 8) RUN2(T, VN, 8);        \
+    else if (nv <= 12) RUN2(T, VN, 12); else RUN2(T, VN, 16);                  \
+  } while (0)
   if (v8) RUN(__nv_bfloat16, 8);
   else HNB_DISPATCH_DTYPE(dtype, T, { if (v4) RUN(T, 4); else RUN(T, 1); });
 #undef RUN
+#undef RUN2
   HNB_LAUNCH_CHECK("gated_norm_fwd");
   return HNB_OK;
 }
