@@ -209,6 +209,8 @@ def profile_step(step, pk):
     table = []
     for k, e in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         row = {"kernel": k, "launches": e["n"], "ms": round(e["ms"], 3), "share": round(e["ms"] / total, 4)}
+        if e["ok"]:
+            row["bytes_per_call"] = round(e["bytes"] / e["n"])
         if e["ok"] and e["ms"] > 0:
             sec = e["ms"] * 1e-3
             t_f, t_b = e["flops"] / pf, e["bytes"] / pb          # time each roofline alone would allow
@@ -350,8 +352,15 @@ def run_ours(args):
     if rank == 0:
         top = next((r for r in table if "frac" in r), None)
         if top:
+            traffic = None      # DRAM read+write bytes per call of this entry point, from the committed ncu pass
+            try:
+                tj = json.load(open(os.path.join(REPO, "profiles", "r01_traffic.json")))
+                traffic = round(tj["entries"][top["kernel"]]["dram_bytes_per_call"])
+            except Exception:
+                pass
             line["roofline"] = {"kernel": "hnb_" + top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
-                                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
+                                "algorithmic_bytes_per_call": top.get("bytes_per_call"),
                                 "peak_source": pk_src + (" (sustained)" if top["bound"] == "tensor" else ""),
                                 "share_of_step": top["share"], "launches_per_step": top["launches"]}
         line["kernel_table"] = table[:12]

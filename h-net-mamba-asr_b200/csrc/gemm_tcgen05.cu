@@ -88,6 +88,92 @@ struct GemmParams {
   int atomic;
 };
 
+// Epilogue of one accumulator tile for one warp: TMEM lane quarter at `t_addr`, output row `row`, the warp's column
+// half `chalf` of the BN-wide tile starting at column n0.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_addr, int row, int n0, int chalf) {
+      // TMEM hands each lane one ROW: 32 consecutive columns = 64 B (bf16) / 128 B (fp32) of that row.  They leave as
+      // 256-bit stores, one full 32-byte sector per lane and instruction -- no shared-memory transpose (the first
+      // version spent 12 k warp-instructions per tile in one: the K = 384 projections were epilogue-bound).
+#pragma unroll 1
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+        const int col0 = n0 + c0;
+        if (col0 >= p.N) break;                             // warp-uniform
+        float v[32];
+        umma::tmem_ld32(t_addr + (uint32_t)c0, v);
+        umma::tmem_ld_wait();
+        if (row < p.M) {
+        if (p.bias) {
+          if (col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);       // warp-uniform addresses: broadcast
+          } else {
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        if (p.atomic) {
+          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+          } else {
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(c + j, v[j]);
+          }
+        } else if (p.c_is_f32) {
+          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+          const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 31) == 0)) {
+            if (r) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8];
+                ldg256(r + j, reinterpret_cast<uint32_t*>(t));
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j + e] += t[e];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) stg256(c + j, reinterpret_cast<const uint32_t*>(v + j));
+          } else {
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) c[j] = v[j] + (r ? r[j] : 0.f);
+          }
+        } else {
+          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+          const __nv_bfloat16* r = p.R ? reinterpret_cast<const __nv_bfloat16*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 31) == 0)) {
+            if (r) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 16) {
+                uint32_t t[8];
+                ldg256(r + j, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t[e]));
+                  v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 16) {
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                o[e] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              stg256(c + j, o);
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) c[j] = __float2bfloat16_rn(v[j] + (r ? __bfloat162float(r[j]) : 0.f));
+          }
+        }
+        }
+        __syncwarp();                                       // tcgen05.ld is warp-collective: reconverge before the next one
+      }
+}
+
 // Persistent, warp-specialised: each CTA walks work items (k-split, n-tile, m-tile) with a static stride.
 //   TMA warp  -> smem ring (full/empty mbarriers)
 //   MMA warp  -> tcgen05.mma 128 x BN x 16 into one of TWO TMEM accumulators (tmem_full/tmem_empty mbarriers)
@@ -131,9 +217,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
-    const int tm = item % p.groups_m;
-    const int r = item / p.groups_m;
-    const int tn = r % p.tiles_n, ks = r / p.tiles_n;
+    // column tile fastest: the CTAs working at the same time share their A rows (read from DRAM once, then L2 hits);
+    // B is a weight matrix or a narrow activation and stays in L2 anyway.  (Row-fastest order re-read the 115 MB
+    // dzxbcdt operand of the in-projection dgrad once per column tile: ncu, 207 MB of DRAM reads.)
+    const int tn = item % p.tiles_n;
+    const int r = item / p.tiles_n;
+    const int tm = r % p.groups_m, ks = r / p.groups_m;
     m0 = (tm * CL + crank) * BM; n0 = tn * BN;          // may start beyond M for the odd last tile: loads zero-fill
     kb0 = ks * p.kblocks_per_split;
     nkb = min(p.kblocks_per_split, p.total_kb - kb0);
@@ -227,87 +316,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       umma::mbar_wait(&tmem_full[acc], aph);
       umma::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16);
-      // TMEM hands each lane one ROW: 32 consecutive columns = 64 B (bf16) / 128 B (fp32) of that row.  They leave as
-      // 256-bit stores, one full 32-byte sector per lane and instruction -- no shared-memory transpose (the first
-      // version spent 12 k warp-instructions per tile in one: the K = 384 projections were epilogue-bound).
-      const int row = m0 + lq * 32 + lane;
-#pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
-        const int col0 = n0 + c0;
-        if (col0 >= p.N) break;                             // warp-uniform
-        float v[32];
-        umma::tmem_ld32(t_addr + (uint32_t)c0, v);
-        umma::tmem_ld_wait();
-        if (row < p.M) {
-        if (p.bias) {
-          if (col0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);       // warp-uniform addresses: broadcast
-          } else {
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-          }
-        }
-        if (p.atomic) {
-          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-          } else {
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(c + j, v[j]);
-          }
-        } else if (p.c_is_f32) {
-          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-          const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
-          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 31) == 0)) {
-            if (r) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8];
-                ldg256(r + j, reinterpret_cast<uint32_t*>(t));
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[j + e] += t[e];
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) stg256(c + j, reinterpret_cast<const uint32_t*>(v + j));
-          } else {
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) c[j] = v[j] + (r ? r[j] : 0.f);
-          }
-        } else {
-          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
-          const __nv_bfloat16* r = p.R ? reinterpret_cast<const __nv_bfloat16*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
-          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 31) == 0)) {
-            if (r) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 16) {
-                uint32_t t[8];
-                ldg256(r + j, t);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t[e]));
-                  v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 16) {
-              uint32_t o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                o[e] = *reinterpret_cast<const uint32_t*>(&h);
-              }
-              stg256(c + j, o);
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) c[j] = __float2bfloat16_rn(v[j] + (r ? __bfloat162float(r[j]) : 0.f));
-          }
-        }
-        }
-        __syncwarp();                                       // tcgen05.ld is warp-collective: reconverge before the next one
-      }
+      epilogue_tile<BN>(p, t_addr, m0 + lq * 32 + lane, n0, chalf);
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&tmem_empty[acc]);
@@ -317,6 +326,143 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (CL > 1) umma::cluster_sync_all();        // no CTA leaves while its peer can still signal or fill its shared memory
   if (warp == 1) umma::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---- CTA-pair variant (cta_group::2): 256 x 256 tiles over two SMs --------------------------------------------
+// The long-K GEMMs are paced by TMA latency x bytes in flight per SM.  With the pair MMA each CTA stages only ITS 128
+// rows of A and ITS 128 of the tile's 256 B rows per k-block (32 KB instead of 48 KB), so six stages fit and the
+// same latency covers 1.5x the k-blocks.  Rank 0 ("leader") issues every MMA; both CTAs run a TMA producer whose bytes
+// are counted on the LEADER's full barrier, the MMA's completion is multicast to both CTAs' empty / tmem_full
+// barriers, both CTAs drain their own 128 accumulator rows, and the peer's epilogue warps arrive on the leader's
+// tmem_empty barrier.
+constexpr int PAIR_STAGES = 6, PAIR_BN = 256, PAIR_B_STAGE = 128 * BK * 2;
+constexpr int PAIR_RING = PAIR_STAGES * (A_STAGE + PAIR_B_STAGE);
+constexpr int PAIR_SMEM = PAIR_RING + 256 + 1024;
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + PAIR_STAGES * A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PAIR_RING);
+  uint64_t* empty = full + PAIR_STAGES;
+  uint64_t* tmem_full = empty + PAIR_STAGES;                  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                       // [2]  (the leader's copy is the one that counts)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.groups_m * p.tiles_n * p.splitk;
+  const int crank = (int)umma::cluster_ctarank();
+  const int first_item = blockIdx.x / 2, item_stride = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmA);
+    umma::prefetch_tmap(&tmB);
+    for (int s = 0; s < PAIR_STAGES; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], 2 * EPI_WARPS); }
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc_pair(tmem_slot, 2 * PAIR_BN);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync_all();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
+    const int tn = item % p.tiles_n;                           // column tile fastest, as above
+    const int r = item / p.tiles_n;
+    const int tm = r % p.groups_m, ks = r / p.groups_m;
+    m0 = tm * 2 * BM; n0 = tn * PAIR_BN;                       // the PAIR's 256 x 256 tile
+    kb0 = ks * p.kblocks_per_split;
+    nkb = min(p.kblocks_per_split, p.total_kb - kb0);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs): my 128 rows of A, my 128 of the tile's B rows ----------------
+      uint32_t it = 0;
+      for (int item = first_item; item < n_items; item += item_stride) {
+        int m0, n0, kb0, nkb;
+        decode(item, m0, n0, kb0, nkb);
+        const int ma = m0 + crank * BM, nb = n0 + crank * 128;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % PAIR_STAGES;
+          const uint32_t ph = (it / PAIR_STAGES) & 1;
+          umma::mbar_wait(&empty[s], ph ^ 1);
+          if (crank == 0) umma::mbar_expect_tx(&full[s], 2 * (A_STAGE + PAIR_B_STAGE));     // both CTAs' bytes
+          const int k0 = (kb0 + i) * BK;
+          uint8_t* a = sA + s * A_STAGE;
+          uint8_t* b = sB + s * PAIR_B_STAGE;
+          if (TA == 0) {
+            umma::tma_load_2d_pair(a, &tmA, &full[s], k0, ma);
+          } else {
+            umma::tma_load_2d_pair(a, &tmA, &full[s], ma, k0);
+            umma::tma_load_2d_pair(a + 8192, &tmA, &full[s], ma + 64, k0);
+          }
+          if (TB == 0) {
+            umma::tma_load_2d_pair(b, &tmB, &full[s], k0, nb);
+          } else {
+            umma::tma_load_2d_pair(b, &tmB, &full[s], nb, k0);
+            umma::tma_load_2d_pair(b + 8192, &tmB, &full[s], nb + 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // ---------------- MMA issuer (leader only) ----------------
+      constexpr uint32_t idesc = umma::make_idesc_bf16(2 * BM, PAIR_BN, TA, TB);
+      uint32_t it = 0, li = 0;
+      for (int item = first_item; item < n_items; item += item_stride, ++li) {
+        int m0, n0, kb0, nkb;
+        decode(item, m0, n0, kb0, nkb);
+        const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+        umma::mbar_wait(&tmem_empty[acc], aph ^ 1);                        // both CTAs have drained this accumulator
+        umma::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * PAIR_BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % PAIR_STAGES;
+          const uint32_t ph = (it / PAIR_STAGES) & 1;
+          umma::mbar_wait(&full[s], ph);
+          umma::tc_fence_after();
+          const uint32_t a = umma::smem_u32(sA + s * A_STAGE);
+          const uint32_t b = umma::smem_u32(sB + s * PAIR_B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = (TA == 0) ? umma::make_smem_desc(a + k * 32, 16, 1024)
+                                          : umma::make_smem_desc(a + k * 2048, 8192, 1024);
+            const uint64_t db = (TB == 0) ? umma::make_smem_desc(b + k * 32, 16, 1024)
+                                          : umma::make_smem_desc(b + k * 2048, 8192, 1024);
+            umma::mma_bf16_ss_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma::mma_commit_pair(&empty[s], 0x3);                           // frees the slot in both CTAs
+        }
+        umma::mma_commit_pair(&tmem_full[acc], 0x3);
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): my 128 rows of the accumulator ----------------
+    const int lq = warp & 3, chalf = (warp - 2) >> 2;
+    uint32_t li = 0;
+    for (int item = first_item; item < n_items; item += item_stride, ++li) {
+      int m0, n0, kb0, nkb;
+      decode(item, m0, n0, kb0, nkb);
+      const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+      umma::mbar_wait(&tmem_full[acc], aph);
+      umma::tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * PAIR_BN + ((uint32_t)(lq * 32) << 16);
+      epilogue_tile<PAIR_BN>(p, t_addr, m0 + crank * BM + lq * 32 + lane, n0, chalf);
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::cluster_sync_all();
+  if (warp == 1) umma::tmem_dealloc_pair(tmem_base, 2 * PAIR_BN);
 }
 
 // naive reference for the self test
@@ -364,22 +510,39 @@ static int gemm_tile_n(int N) {
   return best;
 }
 
+// CTA-pair MMAs pay off when the main loop, not the epilogue, sets the pace: 256-wide tiles, at least 4 row tiles and
+// at least 12 k-blocks per work item (the K = 384..512 projections drain one accumulator per 6-8 k-blocks).
 static int gemm_sm_count() {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   return sms;
 }
 
+// Cost model shared by the split-K hint and the launch: waves x (k-blocks per item + fixed per-item cost), a pair's
+// k-block costing ~3/4 of a single CTA's (measured on the long-K GEMMs).  Pairs only where they are not slower.
+static double gemm_cost(int tiles_m, int tiles_n, int kb_per, int sk, bool pair) {
+  const int sms = gemm_sm_count();
+  const long long items = (long long)(pair ? cdiv(tiles_m, 2) : tiles_m) * tiles_n * sk;
+  return (double)cdiv(items, pair ? sms / 2 : sms) * ((pair ? 0.75 : 1.0) * kb_per + 8.0);
+}
+static bool gemm_use_pair(int M, int N, int BN, int kb_per, int sk) {
+  static const int cl_env = getenv("HNB_GEMM_CLUSTER") ? atoi(getenv("HNB_GEMM_CLUSTER")) : 3;
+  if (!(cl_env == 3 && BN == 256 && cdiv(M, 128) >= 4 && kb_per >= 12)) return false;
+  const int tm = cdiv(M, 128), tn = cdiv(N, BN);
+  return gemm_cost(tm, tn, kb_per, sk, true) <= gemm_cost(tm, tn, kb_per, sk, false);
+}
+
 // Split-K factor for a weight-gradient GEMM (K = tokens): the one that minimises  waves x (k-blocks per item + fixed
 // per-item cost)  for the tile grid hnb_gemm_bf16 will actually use.  The caller zero-fills C when the answer is > 1.
 extern "C" int hnb_gemm_splitk_hint(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 1;
-  const int tiles = cdiv(M, 128) * cdiv(N, gemm_tile_n(N)), kb = cdiv(K, 64), sms = gemm_sm_count();
+  const int BN = gemm_tile_n(N), tiles_m = cdiv(M, 128), tiles_n = cdiv(N, BN), kb = cdiv(K, 64);
   int best = 1;
   double best_cost = 1e30;
   for (int sk = 1; sk <= 32 && sk * 4 <= kb; ++sk) {
     const int per = cdiv(kb, sk), eff_sk = cdiv(kb, per);
-    const double cost = (double)cdiv((long long)tiles * eff_sk, sms) * (per + 8.0) + 0.5 * eff_sk;
+    const bool pair = gemm_use_pair(M, N, BN, per, eff_sk);         // pairs of row tiles on pairs of SMs
+    const double cost = gemm_cost(tiles_m, tiles_n, per, eff_sk, pair) + 0.5 * eff_sk;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = eff_sk; }
   }
   return best;
@@ -396,8 +559,14 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   if (splitk < 1) splitk = 1;
   HNB_CHECK_ARG(splitk == 1 || (c_dtype == HNB_F32 && !bias && !R), "gemm_bf16: split-K needs fp32 C and no bias/residual");
   const int BN = gemm_tile_n(N);
-  static const int cl_env = getenv("HNB_GEMM_CLUSTER") ? atoi(getenv("HNB_GEMM_CLUSTER")) : 1;   // tuning knob
-  const int CL = (cl_env == 2 && cdiv(M, BM) >= 4 && BN != 192) ? 2 : 1;
+  // HNB_GEMM_CLUSTER: 1 = single-CTA tiles, 2 = 2-CTA multicast of B (1-SM MMAs), 3 (default) = CTA-pair MMAs
+  // (cta_group::2) where gemm_use_pair() says so
+  static const int cl_env = getenv("HNB_GEMM_CLUSTER") ? atoi(getenv("HNB_GEMM_CLUSTER")) : 3;
+  const int kb_total = cdiv(K, BK);
+  const int sk_req = splitk < 1 ? 1 : (splitk > kb_total ? kb_total : splitk);
+  const int per_req = cdiv(kb_total, sk_req);
+  const bool pair = gemm_use_pair(M, N, BN, per_req, cdiv(kb_total, per_req));
+  const int CL = (cl_env == 2 && cdiv(M, BM) >= 4 && BN != 192) ? 2 : (pair ? 2 : 1);
   CUtensorMap tmA, tmB;
   int rc;
   {
@@ -407,7 +576,7 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
     else         { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
     st[0] = (uint64_t)lda * 2;
     if ((rc = make_tmap_bf16(&tmA, A, 2, dims, st, box))) return rc;
-    if (!transB) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)(BN / CL); }
+    if (!transB) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)(BN / CL); }   // pair / multicast: half of B
     else         { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
     st[0] = (uint64_t)ldb * 2;
     if ((rc = make_tmap_bf16(&tmB, B, 2, dims, st, box))) return rc;
@@ -447,10 +616,23 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
     else if (BN == 192) { LAUNCH(TA, TB, 192, 1); }                                                                  \
     else                { if (CL == 2) LAUNCH(TA, TB, 128, 2); else LAUNCH(TA, TB, 128, 1); }                         \
   } while (0)
-  if (!transA && !transB) LAUNCH_BN(0, 0);
+#define LAUNCH_PAIR(TA, TB)                                                                                          \
+  do {                                                                                                               \
+    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_pair_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       PAIR_SMEM));                                                                  \
+    cfg.dynamicSmemBytes = PAIR_SMEM;                                                                                \
+    HNB_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<TA, TB>, tmA, tmB, p));                              \
+  } while (0)
+  if (pair) {
+    if (!transA && !transB) LAUNCH_PAIR(0, 0);
+    else if (!transA && transB) LAUNCH_PAIR(0, 1);
+    else if (transA && !transB) LAUNCH_PAIR(1, 0);
+    else LAUNCH_PAIR(1, 1);
+  } else if (!transA && !transB) LAUNCH_BN(0, 0);
   else if (!transA && transB) LAUNCH_BN(0, 1);
   else if (transA && !transB) LAUNCH_BN(1, 0);
   else LAUNCH_BN(1, 1);
+#undef LAUNCH_PAIR
 #undef LAUNCH_BN
 #undef LAUNCH
   HNB_LAUNCH_CHECK("gemm_bf16");
@@ -458,24 +640,24 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
 }
 
 // Runs the four operand-major combinations (with ragged M, N, K tails) plus a split-K case against a naive kernel, once
-// with 3 row tiles (single-CTA path) and once with 5 (2-CTA multicast path, odd tile count: the last cluster's second
-// CTA owns no rows).  Allocates scratch with cudaMalloc: diagnostic entry point, not a hot-path call.
+// with 3 row tiles (single-CTA path, 128-wide tiles) and once with 5 row tiles x 256-wide tiles (the CTA-pair or
+// multicast path when enabled; odd tile count: the last cluster's second CTA owns no rows).  Allocates scratch with cudaMalloc: diagnostic entry point, not a hot-path call.
 extern "C" int hnb_umma_selftest(float* max_abs_err_host, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const int N = 200, K = 424, LD = 608;                        // LD covers [M,K], [K,M], [N,K], [K,N] storage
+  const int K = 424, LD = 608;                                 // LD covers [M,K], [K,M], [N,K], [K,N] storage
   __nv_bfloat16 *A, *B;
   float *C, *Cref, *err;
   HNB_CUDA_CALL(cudaMalloc(&A, sizeof(__nv_bfloat16) * LD * LD));
   HNB_CUDA_CALL(cudaMalloc(&B, sizeof(__nv_bfloat16) * LD * LD));
-  HNB_CUDA_CALL(cudaMalloc(&C, sizeof(float) * LD * N));
-  HNB_CUDA_CALL(cudaMalloc(&Cref, sizeof(float) * LD * N));
+  HNB_CUDA_CALL(cudaMalloc(&C, sizeof(float) * LD * LD));
+  HNB_CUDA_CALL(cudaMalloc(&Cref, sizeof(float) * LD * LD));
   HNB_CUDA_CALL(cudaMalloc(&err, sizeof(float) * 8));
   HNB_CUDA_CALL(cudaMemsetAsync(err, 0, sizeof(float) * 8, st));
   fill_kernel<<<cdiv(LD * LD, 256), 256, 0, st>>>(A, LD * LD, 1u);
   fill_kernel<<<cdiv(LD * LD, 256), 256, 0, st>>>(B, LD * LD, 7u);
   int rc = HNB_OK;
   for (int pass = 0; pass < 2 && rc == HNB_OK; ++pass) {
-    const int M = pass == 0 ? 328 : 600;
+    const int M = pass == 0 ? 328 : 600, N = pass == 0 ? 200 : 500;   // pass 1: 5 row tiles x 2 256-wide column tiles
     for (int combo = 0; combo < 5 && rc == HNB_OK; ++combo) {
       const int ta = combo & 1, tb = (combo >> 1) & 1;
       const int splitk = combo == 4 ? 3 : 1;

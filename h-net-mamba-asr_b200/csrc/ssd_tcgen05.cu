@@ -294,7 +294,12 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       }
       if (loader && nit < n_items) {                                   // next step's tiles land during this step's epilogues
         umma::mbar_wait(bar_free, par);
+        const long long tl0 = clock64();
         issue_load(nit, ncn, buf ^ 1);
+        if (p.dbg && blockIdx.x == 0) {                                // debug only: how long the TMA group takes to land
+          umma::mbar_wait(bar_load, par ^ 1);
+          p.dbg[5] += clock64() - tl0; p.dbg[7] += tl0 - tk1;
+        }
       }
       umma::mbar_wait(bar_g, par);
       umma::tc_fence_after();
@@ -1073,7 +1078,8 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
     cudaFree(p.dbg);
     const double n = h[6] > 0 ? (double)h[6] : 1.0;
     fprintf(stderr, "[ssd_fwd CTA0] steps %lld | cycles/step: wait load %.0f, G mma wait (+Xw) %.0f, epi1 %.0f, "
-            "mma2 wait %.0f, epi2+3 %.0f\n", h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n);
+            "mma2 wait %.0f, epi2+3 %.0f | next load issued %.0f after step start, lands %.0f later\n", h[6], h[0] / n,
+            h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[7] / n, h[5] / n);
   }
   return HNB_OK;
 }

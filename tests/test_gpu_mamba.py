@@ -28,14 +28,16 @@ def test_umma_selftest():
     assert max(errs) < 2e-3, errs          # K=424 bf16 products, fp32 accumulation order differences only
 
 
-def test_umma_selftest_cluster_path():
-    """The optional 2-CTA multicast path of the GEMM (HNB_GEMM_CLUSTER=2, read once per process) against the naive kernel."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_umma_selftest_other_gemm_paths(mode):
+    """The default process runs the CTA-pair (cta_group::2) GEMM where it applies; this checks the single-CTA path
+    (HNB_GEMM_CLUSTER=1) and the 2-CTA multicast path (=2) against the naive kernel (the knob is read once per process)."""
     import subprocess
     import sys
     code = ("import sys, ctypes; sys.path[:0] = %r; from dcasr_b200._lib import lib, stream; import torch; "
             "err = (ctypes.c_float * 8)(); rc = lib().raw('umma_selftest')(ctypes.cast(err, ctypes.c_void_p), stream()); "
             "torch.cuda.synchronize(); print('ERRS', rc, max(err[i] for i in range(5)))") % (sys.path,)
-    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "HNB_GEMM_CLUSTER": "2"}, capture_output=True,
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "HNB_GEMM_CLUSTER": mode}, capture_output=True,
                          text=True, timeout=300)
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("ERRS")]
     assert line, out.stdout + out.stderr
