@@ -90,18 +90,36 @@ struct GemmParams {
 
 // Epilogue of one accumulator tile for one warp: TMEM lane quarter at `t_addr`, output row `row`, the warp's column
 // half `chalf` of the BN-wide tile starting at column n0.
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_addr, int row, int n0, int chalf) {
+// `release` is the accumulator's tmem_empty barrier: the warp arrives on it (on the pair leader's copy when PAIR) as soon
+// as its last TMEM load has landed in registers, i.e. before the last block is converted and stored.
+template <int BN, bool PAIR>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_addr, int row, int n0, int chalf,
+                                              uint64_t* release, int lane) {
       // TMEM hands each lane one ROW: 32 consecutive columns = 64 B (bf16) / 128 B (fp32) of that row.  They leave as
       // 256-bit stores, one full 32-byte sector per lane and instruction -- no shared-memory transpose (the first
-      // version spent 12 k warp-instructions per tile in one: the K = 384 projections were epilogue-bound).
-#pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+      // version spent 12 k warp-instructions per tile in one: the K = 384 projections were epilogue-bound).  The TMEM
+      // load of block j+1 is in flight while block j is converted and stored (two register buffers).
+      constexpr int NBLK = BN / 64;
+      const int cbase = chalf * (BN / 2);
+      float vbuf[2][32];
+      bool released = false;
+      if (n0 + cbase < p.N) umma::tmem_ld32(t_addr + (uint32_t)cbase, vbuf[0]);
+#pragma unroll
+      for (int jb = 0; jb < NBLK; ++jb) {
+        const int c0 = cbase + 32 * jb;
         const int col0 = n0 + c0;
         if (col0 >= p.N) break;                             // warp-uniform
-        float v[32];
-        umma::tmem_ld32(t_addr + (uint32_t)c0, v);
         umma::tmem_ld_wait();
+        const bool more = jb + 1 < NBLK && col0 + 32 < p.N;
+        if (more) {
+          umma::tmem_ld32(t_addr + (uint32_t)(c0 + 32), vbuf[(jb + 1) & 1]);
+        } else {
+          umma::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (PAIR) umma::mbar_arrive_leader(release); else umma::mbar_arrive(release); }
+          released = true;
+        }
+        float* v = vbuf[jb & 1];
         if (row < p.M) {
         if (p.bias) {
           if (col0 + 32 <= p.N) {
@@ -171,6 +189,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ad
         }
         }
         __syncwarp();                                       // tcgen05.ld is warp-collective: reconverge before the next one
+      }
+      if (!released) {                                      // tile entirely beyond N for this warp's column half
+        umma::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) umma::mbar_arrive_leader(release); else umma::mbar_arrive(release); }
       }
 }
 
@@ -316,10 +339,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       umma::mbar_wait(&tmem_full[acc], aph);
       umma::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(lq * 32) << 16);
-      epilogue_tile<BN>(p, t_addr, m0 + lq * 32 + lane, n0, chalf);
-      umma::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&tmem_empty[acc]);
+      epilogue_tile<BN, false>(p, t_addr, m0 + lq * 32 + lane, n0, chalf, &tmem_empty[acc], lane);
     }
   }
   umma::tc_fence_before();
@@ -453,10 +473,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       umma::mbar_wait(&tmem_full[acc], aph);
       umma::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * PAIR_BN + ((uint32_t)(lq * 32) << 16);
-      epilogue_tile<PAIR_BN>(p, t_addr, m0 + crank * BM + lq * 32 + lane, n0, chalf);
-      umma::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive_leader(&tmem_empty[acc]);
+      epilogue_tile<PAIR_BN, true>(p, t_addr, m0 + crank * BM + lq * 32 + lane, n0, chalf, &tmem_empty[acc], lane);
     }
   }
   umma::tc_fence_before();
