@@ -60,7 +60,7 @@ layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, 
 // keeps its dgamma/dbeta columns in registers; one shared-memory reduction + atomics per block.
 // ---------------------------------------------------------------------------------------------
 template <typename TDY, typename TX, typename TDX, int VN, int NV>
-__global__ void __launch_bounds__(NORM_WARPS * 32, (NV * VN <= 16 ? 3 : 1))
+__global__ void __launch_bounds__(NORM_WARPS * 32, (NV * VN <= 16 ? 2 : 1))
 layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const TDX* __restrict__ dres,
                      long long rows, int d, TDX* __restrict__ dx, float* __restrict__ dgamma,
@@ -75,40 +75,63 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
     for (int i = 0; i < VN; ++i) { ag[k][i] = 0.f; ab[k][i] = 0.f; gm[k][i] = 0.f; }
     if (c < d) ldv<float, VN>(gamma + c, gm[k]);
   }
-  for (long long row = (long long)blockIdx.x * NORM_WARPS + w; row < rows; row += (long long)gridDim.x * NORM_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NV][VN], g[NV][VN];
-    float s1 = 0.f, s2 = 0.f;
+  // two rows per iteration (d <= 384): both rows' loads are issued before either row's reduction, so a warp has twice the bytes
+  // in flight (these 384..512-element rows are too short to hide a DRAM round trip otherwise)
+  constexpr int R = NV * VN <= 12 ? 2 : 1;                          // wider rows: one at a time (register budget)
+  const long long stride = (long long)gridDim.x * NORM_WARPS;
+  for (long long row0 = (long long)blockIdx.x * NORM_WARPS + w; row0 < rows; row0 += R * stride) {
+    float xv[R][NV][VN], g[R][NV][VN], rr[R][NV][VN];
+    float mu[R], rs[R];
+    bool have[R];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = (k * 32 + lane) * VN;
+    for (int u = 0; u < R; ++u) {
+      const long long row = row0 + u * stride;
+      have[u] = row < rows;
+      if (have[u]) {
+        mu[u] = mean[row]; rs[u] = rstd[row];
 #pragma unroll
-      for (int i = 0; i < VN; ++i) { xh[k][i] = 0.f; g[k][i] = 0.f; }
-      if (c < d) {
-        float xv[VN];
-        ldv<TX, VN>(x + row * d + c, xv);
-        ldv<TDY, VN>(dy + row * d + c, g[k]);
-#pragma unroll
-        for (int i = 0; i < VN; ++i) {
-          xh[k][i] = (xv[i] - mu) * rs;
-          ag[k][i] += g[k][i] * xh[k][i];
-          ab[k][i] += g[k][i];
-          const float gg = g[k][i] * gm[k][i];
-          s1 += gg; s2 += gg * xh[k][i];
+        for (int k = 0; k < NV; ++k) {
+          const int c = (k * 32 + lane) * VN;
+          if (c < d) {
+            ldv<TX, VN>(x + row * d + c, xv[u][k]);
+            ldv<TDY, VN>(dy + row * d + c, g[u][k]);
+            if (dres) ldv<TDX, VN>(dres + row * d + c, rr[u][k]);
+          }
         }
       }
     }
-    s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = (k * 32 + lane) * VN;
-      if (c < d) {
-        float o[VN], r[VN];
-        if (dres) ldv<TDX, VN>(dres + row * d + c, r);
+    for (int u = 0; u < R; ++u) {
+      if (!have[u]) continue;                                        // warp-uniform
+      const long long row = row0 + u * stride;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < VN; ++i)
-          o[i] = rs * (g[k][i] * gm[k][i] - s1 - xh[k][i] * s2) + (dres ? r[i] : 0.f);
-        stv<TDX, VN>(dx + row * d + c, o);
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * VN;
+        if (c < d) {
+#pragma unroll
+          for (int i = 0; i < VN; ++i) {
+            const float xh = (xv[u][k][i] - mu[u]) * rs[u];
+            xv[u][k][i] = xh;
+            ag[k][i] += g[u][k][i] * xh;
+            ab[k][i] += g[u][k][i];
+            const float gg = g[u][k][i] * gm[k][i];
+            g[u][k][i] = gg;
+            s1 += gg; s2 += gg * xh;
+          }
+        }
+      }
+      s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * VN;
+        if (c < d) {
+          float o[VN];
+#pragma unroll
+          for (int i = 0; i < VN; ++i)
+            o[i] = rs[u] * (g[u][k][i] - s1 - xv[u][k][i] * s2) + (dres ? rr[u][k][i] : 0.f);
+          stv<TDX, VN>(dx + row * d + c, o);
+        }
       }
     }
   }
@@ -290,14 +313,19 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
 // in_proj.weight -> rows [dir*dstride, +dip) of Win (pad rows zeroed), out_proj.weight -> columns [dir*di, +di) of
 // Wout, both cast to the activation dtype; the small fp32 vectors are copied into their [ndir, ...] stacks.
 // ---------------------------------------------------------------------------------------------
+struct PackSrc { const float* p[2][8]; };          // per direction: in_w, out_w, conv_w, conv_b, dt_bias, A_log, D, norm_w
+
 template <typename TW>
 __global__ void __launch_bounds__(256)
-pack_mixer_kernel(const float* __restrict__ in_w, const float* __restrict__ out_w, const float* __restrict__ conv_w,
-                  const float* __restrict__ conv_b, const float* __restrict__ dt_bias, const float* __restrict__ A_log,
-                  const float* __restrict__ Dk, const float* __restrict__ norm_w, int dir, int ndir, int d, int di,
+pack_mixer_kernel(const PackSrc src, int dir0, int ndir, int d, int di,
                   int N, int H, int dstride, TW* __restrict__ Win, TW* __restrict__ Wout, float* __restrict__ conv_w_o,
                   float* __restrict__ conv_b_o, float* __restrict__ dt_bias_o, float* __restrict__ A_log_o,
                   float* __restrict__ D_o, float* __restrict__ norm_w_o) {
+  const int dir = dir0 + blockIdx.y;                                // one launch packs gridDim.y directions
+  const float* __restrict__ in_w = src.p[blockIdx.y][0]; const float* __restrict__ out_w = src.p[blockIdx.y][1];
+  const float* __restrict__ conv_w = src.p[blockIdx.y][2]; const float* __restrict__ conv_b = src.p[blockIdx.y][3];
+  const float* __restrict__ dt_bias = src.p[blockIdx.y][4]; const float* __restrict__ A_log = src.p[blockIdx.y][5];
+  const float* __restrict__ Dk = src.p[blockIdx.y][6]; const float* __restrict__ norm_w = src.p[blockIdx.y][7];
   const int dip = 2 * di + 2 * N + H, C = di + 2 * N;
   const long long n_in = (long long)dstride * d / 4, n_out = (long long)d * di / 4;
   const long long n_small = (long long)C * 4 + C + 3 * H + di;
@@ -457,21 +485,47 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
   return HNB_OK;
 }
 
+static int pack_launch(const PackSrc& src, int ndirs, int dir0, int ndir, int d, int di, int N, int H, int dstride,
+                       void* Win, void* Wout, int w_dtype, float* conv_w_o, float* conv_b_o, float* dt_bias_o,
+                       float* A_log_o, float* D_o, float* norm_w_o, void* stream) {
+  HNB_CHECK_ARG(Win && Wout && conv_w_o && conv_b_o && dt_bias_o && A_log_o && D_o && norm_w_o, "pack_mixer_params: null pointer");
+  for (int r = 0; r < ndirs; ++r)
+    for (int k = 0; k < 8; ++k) HNB_CHECK_ARG(src.p[r][k] != nullptr, "pack_mixer_params: null pointer");
+  HNB_CHECK_ARG(d % 4 == 0 && di % 4 == 0 && dir0 >= 0 && dir0 + ndirs <= ndir && dstride >= 2 * di + 2 * N + H,
+                "pack_mixer_params: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = ((long long)dstride * d + (long long)d * di) / 4 + (long long)(di + 2 * N) * 5 + 3 * H + di;
+  int gx = cdiv(total, 256);
+  if (gx > 148 * 8 / ndirs) gx = 148 * 8 / ndirs;
+  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<dim3(gx, ndirs), 256, 0, st>>>(src, dir0, ndir, d, di, N, H,
+      dstride, (TW*)Win, (TW*)Wout, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o, norm_w_o)));
+  HNB_LAUNCH_CHECK("pack_mixer_params");
+  return HNB_OK;
+}
+
 extern "C" int hnb_pack_mixer_params(const float* in_w, const float* out_w, const float* conv_w, const float* conv_b,
                                      const float* dt_bias, const float* A_log, const float* Dk, const float* norm_w,
                                      int dir, int ndir, int d, int di, int N, int H, int dstride, void* Win, void* Wout,
                                      int w_dtype, float* conv_w_o, float* conv_b_o, float* dt_bias_o, float* A_log_o,
                                      float* D_o, float* norm_w_o, void* stream) {
-  HNB_CHECK_ARG(in_w && out_w && conv_w && conv_b && dt_bias && A_log && Dk && norm_w && Win && Wout && conv_w_o &&
-                conv_b_o && dt_bias_o && A_log_o && D_o && norm_w_o, "pack_mixer_params: null pointer");
-  HNB_CHECK_ARG(d % 4 == 0 && di % 4 == 0 && dir >= 0 && dir < ndir && dstride >= 2 * di + 2 * N + H,
-                "pack_mixer_params: bad sizes");
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long total = ((long long)dstride * d + (long long)d * di) / 4 + (long long)(di + 2 * N) * 5 + 3 * H + di;
-  int grid = cdiv(total, 256);
-  if (grid > 148 * 8) grid = 148 * 8;
-  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<grid, 256, 0, st>>>(in_w, out_w, conv_w, conv_b, dt_bias, A_log,
-      Dk, norm_w, dir, ndir, d, di, N, H, dstride, (TW*)Win, (TW*)Wout, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o, norm_w_o)));
-  HNB_LAUNCH_CHECK("pack_mixer_params");
-  return HNB_OK;
+  PackSrc src = {};
+  const float* one[8] = {in_w, out_w, conv_w, conv_b, dt_bias, A_log, Dk, norm_w};
+  for (int k = 0; k < 8; ++k) src.p[0][k] = one[k];
+  return pack_launch(src, 1, dir, ndir, d, di, N, H, dstride, Win, Wout, w_dtype, conv_w_o, conv_b_o, dt_bias_o, A_log_o,
+                     D_o, norm_w_o, stream);
+}
+
+extern "C" int hnb_pack_mixer_params2(const float* in_w0, const float* out_w0, const float* conv_w0, const float* conv_b0,
+                                      const float* dt_bias0, const float* A_log0, const float* Dk0, const float* norm_w0,
+                                      const float* in_w1, const float* out_w1, const float* conv_w1, const float* conv_b1,
+                                      const float* dt_bias1, const float* A_log1, const float* Dk1, const float* norm_w1,
+                                      int d, int di, int N, int H, int dstride, void* Win, void* Wout, int w_dtype,
+                                      float* conv_w_o, float* conv_b_o, float* dt_bias_o, float* A_log_o, float* D_o,
+                                      float* norm_w_o, void* stream) {
+  PackSrc src = {};
+  const float* a[8] = {in_w0, out_w0, conv_w0, conv_b0, dt_bias0, A_log0, Dk0, norm_w0};
+  const float* b[8] = {in_w1, out_w1, conv_w1, conv_b1, dt_bias1, A_log1, Dk1, norm_w1};
+  for (int k = 0; k < 8; ++k) { src.p[0][k] = a[k]; src.p[1][k] = b[k]; }
+  return pack_launch(src, 2, 0, 2, d, di, N, H, dstride, Win, Wout, w_dtype, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o,
+                     norm_w_o, stream);
 }

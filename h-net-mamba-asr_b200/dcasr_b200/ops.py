@@ -265,13 +265,19 @@ def pack_mixer_params(params, ndir, d, di, N, H, dstride, w_dtype, device):
     conv_w, conv_b, dt_bias, A_log, Dk, norm_w = small.split(
         [ndir * C * 4, ndir * C, ndir * H, ndir * H, ndir * H, ndir * di])
     L_ = lib()
-    for r in range(ndir):
-        inw, cw, cb, dtb, al, dk, nw, outw = params[r * 8:(r + 1) * 8]
-        for t in (inw, cw, cb, dtb, al, dk, nw, outw):
-            if t.dtype != torch.float32:
-                raise HnbError("mixer parameters must be fp32 masters")
-        L_.call("pack_mixer_params", inw, outw, cw, cb, dtb, al, dk, nw, r, ndir, d, di, N, H, dstride, Win, Wout,
+    for t in params:
+        if t.dtype != torch.float32:
+            raise HnbError("mixer parameters must be fp32 masters")
+    if ndir == 2:                                                  # both directions in one launch
+        a, b = params[:8], params[8:16]
+        L_.call("pack_mixer_params2", a[0], a[7], a[1], a[2], a[3], a[4], a[5], a[6],
+                b[0], b[7], b[1], b[2], b[3], b[4], b[5], b[6], d, di, N, H, dstride, Win, Wout,
                 dtype_code(w_dtype), conv_w, conv_b, dt_bias, A_log, Dk, norm_w, stream())
+    else:
+        for r in range(ndir):
+            inw, cw, cb, dtb, al, dk, nw, outw = params[r * 8:(r + 1) * 8]
+            L_.call("pack_mixer_params", inw, outw, cw, cb, dtb, al, dk, nw, r, ndir, d, di, N, H, dstride, Win, Wout,
+                    dtype_code(w_dtype), conv_w, conv_b, dt_bias, A_log, Dk, norm_w, stream())
     return (Win, Wout, conv_w.view(ndir, C, 4), conv_b.view(ndir, C), dt_bias.view(ndir, H), A_log.view(ndir, H),
             Dk.view(ndir, H), norm_w.view(ndir, di))
 

@@ -182,6 +182,14 @@ int hnb_pack_mixer_params(const float* in_w, const float* out_w, const float* co
                           int dir, int ndir, int d, int di, int N, int H, int dstride, void* Win, void* Wout,
                           int w_dtype, float* conv_w_o, float* conv_b_o, float* dt_bias_o, float* A_log_o,
                           float* D_o, float* norm_w_o, void* stream);
+/* the same for BOTH directions of a bidirectional block in one launch (ndir = 2; *0 = forward, *1 = backward mixer) */
+int hnb_pack_mixer_params2(const float* in_w0, const float* out_w0, const float* conv_w0, const float* conv_b0,
+                           const float* dt_bias0, const float* A_log0, const float* Dk0, const float* norm_w0,
+                           const float* in_w1, const float* out_w1, const float* conv_w1, const float* conv_b1,
+                           const float* dt_bias1, const float* A_log1, const float* Dk1, const float* norm_w1,
+                           int d, int di, int N, int H, int dstride, void* Win, void* Wout, int w_dtype,
+                           float* conv_w_o, float* conv_b_o, float* dt_bias_o, float* A_log_o, float* D_o,
+                           float* norm_w_o, void* stream);
 
 /* ---- dense projections (in_proj / out_proj / router W_q,W_k / proj_in,out) ---------------- */
 /* C[M,N] = op(A) op(B) (+ bias[N]) (+ R[M,N]) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
