@@ -149,6 +149,54 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
   }
 }
 
+// ---- bias + ReLU over an NHWC tensor viewed as [rows, C] (the second convolution's output) ----------------------
+// forward: in place.  backward: dpre = dout * [out > 0] and db[c] += sum_rows dpre in the same pass (ATen ran a strided
+// broadcast add, a clamp, a threshold_backward and a 116 M-element bf16 column reduction: four passes each way).
+__global__ void __launch_bounds__(256)
+bias_relu_fwd_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ bias, long long rows, int C) {
+  const int CG = C / 8, cgp = threadIdx.x % CG, rl = threadIdx.x / CG, RL = blockDim.x / CG;
+  float b[8];
+  ldv<float, 8>(bias + cgp * 8, b);
+  for (long long r = (long long)blockIdx.x * RL + rl; r < rows; r += (long long)gridDim.x * RL) {
+    float v[8];
+    __nv_bfloat16* p = x + r * C + cgp * 8;
+    ldv<__nv_bfloat16, 8>(p, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + b[i], 0.f);
+    stv<__nv_bfloat16, 8>(p, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bias_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                     __nv_bfloat16* __restrict__ dpre, float* __restrict__ db, long long rows, int C) {
+  extern __shared__ float s_red[];                      // [RL-1][CG][8]
+  const int CG = C / 8, cgp = threadIdx.x % CG, rl = threadIdx.x / CG, RL = blockDim.x / CG;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long r = (long long)blockIdx.x * RL + rl; r < rows; r += (long long)gridDim.x * RL) {
+    float g[8], o[8];
+    const long long off = r * C + cgp * 8;
+    ldv<__nv_bfloat16, 8>(dout + off, g);
+    ldv<__nv_bfloat16, 8>(out + off, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = o[i] > 0.f ? g[i] : 0.f; acc[i] += g[i]; }
+    stv<__nv_bfloat16, 8>(dpre + off, g);
+  }
+  if (rl > 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[((rl - 1) * CG + cgp) * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int q = 0; q < RL - 1; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += s_red[(q * CG + cgp) * 8 + i];
+    float* d = db + cgp * 8;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(acc[4]), "f"(acc[5]), "f"(acc[6]), "f"(acc[7]) : "memory");
+  }
+}
+
 }  // namespace hnb
 
 using namespace hnb;
@@ -201,5 +249,40 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const
   sub_conv1_bwd_kernel<4><<<blocks, CG * PX, smem, (cudaStream_t)stream>>>(feats, (const __nv_bfloat16*)a1,
       (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
   HNB_LAUNCH_CHECK("subsample_conv1_bwd");
+  return HNB_OK;
+}
+
+static int bias_relu_geometry(const char* who, long long rows, int C, int* threads, int* blocks) {
+  if (!(rows > 0 && C > 0 && C % 8 == 0 && C <= 2048)) { set_error("%s: C must be a multiple of 8, at most 2048", who); return HNB_ERR_INVALID_ARG; }
+  const int CG = C / 8, RL = 256 / CG > 0 ? 256 / CG : 1;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  *threads = CG * RL;
+  long long b = (rows + RL - 1) / RL;
+  *blocks = (int)(b < (long long)sms * 8 ? b : (long long)sms * 8);
+  return HNB_OK;
+}
+
+extern "C" int hnb_bias_relu_fwd(void* x, const float* bias, long long rows, int C, void* stream) {
+  HNB_CHECK_ARG(x && bias && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+                "bias_relu_fwd: null or misaligned pointer");
+  int threads, blocks, rc = bias_relu_geometry("bias_relu_fwd", rows, C, &threads, &blocks);
+  if (rc) return rc;
+  bias_relu_fwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, bias, rows, C);
+  HNB_LAUNCH_CHECK("bias_relu_fwd");
+  return HNB_OK;
+}
+
+extern "C" int hnb_bias_relu_bwd(const void* dout, const void* out, void* dpre, float* db, long long rows, int C, void* stream) {
+  HNB_CHECK_ARG(dout && out && dpre && db && (reinterpret_cast<uintptr_t>(db) & 15) == 0, "bias_relu_bwd: null or misaligned pointer");
+  int threads, blocks, rc = bias_relu_geometry("bias_relu_bwd", rows, C, &threads, &blocks);
+  if (rc) return rc;
+  const int CG = C / 8, RL = threads / CG;
+  const size_t smem = (size_t)(RL > 1 ? RL - 1 : 0) * CG * 8 * sizeof(float);
+  bias_relu_bwd_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out,
+                                                                       (__nv_bfloat16*)dpre, db, rows, C);
+  HNB_LAUNCH_CHECK("bias_relu_bwd");
   return HNB_OK;
 }

@@ -70,6 +70,29 @@ class _Conv1ReluFn(torch.autograd.Function):
         return None, dw.to(ctx.meta[0]), db.to(ctx.meta[1])
 
 
+class _BiasReluFn(torch.autograd.Function):
+    """relu(x + bias) on the second convolution's NHWC output, in place; backward masks and reduces db in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, bias):                       # x: bf16 [B, C, T, F], channels_last, fresh conv output
+        B, C, T, F = x.shape
+        x2 = x.permute(0, 2, 3, 1).reshape(B * T * F, C)            # a view of the NHWC storage
+        ops.bias_relu_fwd_(x2, bias.detach().float().contiguous())
+        ctx.mark_dirty(x)
+        ctx.save_for_backward(x)
+        ctx.bdtype = bias.dtype
+        return x
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        B, C, T, F = out.shape
+        d = dout if dout.dtype == torch.bfloat16 else dout.to(torch.bfloat16)
+        d = d.contiguous(memory_format=torch.channels_last)
+        dpre, db = ops.bias_relu_bwd(d.permute(0, 2, 3, 1).reshape(B * T * F, C), out.permute(0, 2, 3, 1).reshape(B * T * F, C))
+        return dpre.view(B, T, F, C).permute(0, 3, 1, 2), db.to(ctx.bdtype)
+
+
 class ConvSubsampling4(nn.Module):
     """x4 time downsample (two Conv2d k3 s2 + ReLU, then Linear) -- reference encoder.py:55-70; same module tree and
     state_dict.  Under CUDA bf16 autocast (the training configuration) the one-input-channel first convolution + ReLU
@@ -92,7 +115,11 @@ class ConvSubsampling4(nn.Module):
         if fused:
             a1 = _Conv1ReluFn.apply(feats, c1.weight, c1.bias)             # bf16, channels_last
             w2 = c2.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            x = torch.relu(torch.nn.functional.conv2d(a1, w2, c2.bias.to(torch.bfloat16), stride=2))
+            x = torch.nn.functional.conv2d(a1, w2, None, stride=2)
+            if x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0 and x.shape[1] <= 2048:
+                x = _BiasReluFn.apply(x, c2.bias)
+            else:
+                x = torch.relu(x + c2.bias.to(x.dtype).view(1, -1, 1, 1))
         else:
             x = self.conv(feats.unsqueeze(1))
         B, C, T, F = x.shape

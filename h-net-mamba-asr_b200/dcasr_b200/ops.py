@@ -307,3 +307,19 @@ def subsample_conv1_bwd(feats, a1, dout):
     dw, db = acc[:C * 9], acc[C * 9:]
     lib().call("subsample_conv1_bwd", feats, a1.permute(0, 2, 3, 1), dout.permute(0, 2, 3, 1), B, T, F, C, dw, db, stream())
     return dw.view(C, 1, 3, 3), db
+
+
+def bias_relu_fwd_(x2d, bias):
+    """x2d [rows, C] bf16 contiguous (an NHWC tensor flattened), in place: relu(x + bias)."""
+    rows, C = x2d.shape
+    lib().call("bias_relu_fwd", x2d, bias, rows, C, stream())
+    return x2d
+
+
+def bias_relu_bwd(dout2d, out2d):
+    rows, C = out2d.shape
+    dpre = torch.empty_like(out2d)
+    db = torch.zeros(C, dtype=torch.float32, device=out2d.device)
+    lib().call("bias_relu_bwd", dout2d, out2d, dpre, db, rows, C, stream())
+    return dpre, db
+

@@ -226,6 +226,11 @@ int hnb_subsample_conv1_fwd(const float* feats, const float* w, const float* bia
 int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const void* dout, int B, int T, int F, int C,
                             float* dw, float* db, void* stream);
 
+/* bias + ReLU of the second convolution's output (encoder.py:61-62), bf16 NHWC viewed as [rows, C], IN PLACE */
+int hnb_bias_relu_fwd(void* x, const float* bias, long long rows, int C, void* stream);
+/* its backward in one pass: dpre = dout * [out > 0] (bf16), db [C] ACCUMULATED (pre-zeroed fp32, 16-byte aligned) */
+int hnb_bias_relu_bwd(const void* dout, const void* out, void* dpre, float* db, long long rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
