@@ -28,6 +28,10 @@ template <> struct V16<float> {
   static __device__ __forceinline__ raw_t pack(const float* v) {
     return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
   }
+  static __device__ __forceinline__ raw_t add(const raw_t& a, const raw_t& b) {
+    return make_uint4(__float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x)), __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y)),
+                      __float_as_uint(__uint_as_float(a.z) + __uint_as_float(b.z)), __float_as_uint(__uint_as_float(a.w) + __uint_as_float(b.w)));
+  }
 };
 template <> struct V16<__nv_bfloat16> {
   static constexpr int N = 4;
@@ -46,6 +50,14 @@ template <> struct V16<__nv_bfloat16> {
     h[0] = __floats2bfloat162_rn(v[0], v[1]); h[1] = __floats2bfloat162_rn(v[2], v[3]);
     return r;
   }
+  static __device__ __forceinline__ raw_t add(const raw_t& a, const raw_t& b) {          // packed bf16 adds
+    raw_t r;
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+    h[0] = __hadd2(x[0], y[0]); h[1] = __hadd2(x[1], y[1]);
+    return r;
+  }
 };
 
 // 2 channels per thread (backward, bf16): half the taps / windows / accumulators per thread, so twice the resident warps
@@ -58,6 +70,9 @@ template <> struct V8<float> {
   static __device__ __forceinline__ void st(float* p, const raw_t& r) { *reinterpret_cast<uint2*>(p) = r; }
   static __device__ __forceinline__ void unpack(const raw_t& r, float* v) { v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); }
   static __device__ __forceinline__ raw_t pack(const float* v) { return make_uint2(__float_as_uint(v[0]), __float_as_uint(v[1])); }
+  static __device__ __forceinline__ raw_t add(const raw_t& a, const raw_t& b) {
+    return make_uint2(__float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x)), __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y)));
+  }
 };
 template <> struct V8<__nv_bfloat16> {
   static constexpr int N = 2;
@@ -71,6 +86,10 @@ template <> struct V8<__nv_bfloat16> {
   }
   static __device__ __forceinline__ raw_t pack(const float* v) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ raw_t add(const raw_t& a, const raw_t& b) {
+    const __nv_bfloat162 h = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
     return *reinterpret_cast<const uint32_t*>(&h);
   }
 };
@@ -180,13 +199,14 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 // backward.  dout[s] for channel c comes from dxc (c < di) or dBC (c >= di), both of the activation dtype; the
 // pre-activation is recomputed from zxbcdt.  d input[s'] = sum_j w[j] dpre[s'+3-j];  dw[j] = sum_s dpre[s] in[s-3+j].
 // A segment owns RUN = TS*NTILE - 3 positions: its last 3 tile positions recompute the dpre halo of the next segment.
-template <typename T, typename VIO, int TS, int NTILE, int MINB>
+template <typename T, typename VIO, int TS, int NTILE, int MINB, bool PARTS2>
 __global__ void __launch_bounds__(CONV_CT * CONV_SEG, MINB)
 conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long ldz, long long dstride,
                 const T* __restrict__ dBC, const float* __restrict__ ddt, const int* __restrict__ lengths,
                 const float* __restrict__ conv_w, const float* __restrict__ conv_b, const float* __restrict__ dt_bias,
                 int ndir, int B, int L, int di, int N, int H, T* __restrict__ dzx, float* __restrict__ dconv_w,
-                float* __restrict__ dconv_b, float* __restrict__ ddt_bias, int vec_red) {
+                float* __restrict__ dconv_b, float* __restrict__ ddt_bias, int vec_red, int dbc_parts,
+                long long dbc_part_stride) {
   constexpr int VN = VIO::N;
   constexpr int RUN = TS * NTILE - 3;
   static_assert(TS > 3, "layout");
@@ -223,6 +243,11 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
     const long long gld = is_x ? di : 2 * N;
     const T* src = rowbase + xoff + c;
     T* dst = drowbase + xoff + c;
+    // dB | dC may arrive as TWO partial sums (one per head group of the SSD dB/dC kernel).  The second part is
+    // prefetched next to the first and added (packed) when the tile is consumed, a whole tile after its load was
+    // issued; `two` is uniform over the block (a block's 256 channels lie on one side of the x | BC border).
+    const bool two = PARTS2 && !is_x;                                // (the one-part instantiation carries no gn2)
+    const T* gsrc2 = gsrc + dbc_part_stride;
     typename VIO::raw_t h[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -233,12 +258,13 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
     VIO::unpack(h[0], win[0]); VIO::unpack(h[1], win[1]); VIO::unpack(h[2], win[2]);
 #pragma unroll
     for (int i = 0; i < VN; ++i) { dp[0][i] = 0.f; dp[1][i] = 0.f; dp[2][i] = 0.f; }
-    typename VIO::raw_t xn[TS], gn[TS];                              // register double buffer (see forward)
+    typename VIO::raw_t xn[TS], gn[TS], gn2[PARTS2 ? TS : 1];                     // register double buffer (see forward)
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
       const bool ok = sb + k < L;
       xn[k] = ok ? VIO::ldg(src + (long long)scan_to_nat(dir, sb + k, len) * ldz) : VIO::zero();
       gn[k] = ok ? VIO::ldg(gsrc + (long long)(sb + k) * gld) : VIO::zero();
+      if (PARTS2) gn2[k] = (ok && two) ? VIO::ldg(gsrc2 + (long long)(sb + k) * gld) : VIO::zero();
     }
 #pragma unroll 2
     for (int tile = 0; tile < NTILE; ++tile) {
@@ -247,7 +273,7 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
       const bool first = tile == 0, last = tile == NTILE - 1;
       typename VIO::raw_t xr[TS], gr[TS];
 #pragma unroll
-      for (int k = 0; k < TS; ++k) { xr[k] = xn[k]; gr[k] = gn[k]; }
+      for (int k = 0; k < TS; ++k) { xr[k] = xn[k]; gr[k] = (PARTS2 && two) ? VIO::add(gn[k], gn2[PARTS2 ? k : 0]) : gn[k]; }
       if (!last) {
 #pragma unroll
         for (int k = 0; k < TS; ++k) {
@@ -255,6 +281,7 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
           const bool ok = s < L;
           xn[k] = ok ? VIO::ldg(src + (long long)scan_to_nat(dir, s, len) * ldz) : VIO::zero();
           gn[k] = ok ? VIO::ldg(gsrc + (long long)s * gld) : VIO::zero();
+          if (PARTS2 && two) gn2[k] = ok ? VIO::ldg(gsrc2 + (long long)s * gld) : VIO::zero();
         }
       }
 #pragma unroll
@@ -382,9 +409,11 @@ extern "C" int hnb_conv_fwd(const void* zxbcdt, int dtype, long long ldz, long l
 extern "C" int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long long ldz, long long dstride,
                             const void* dBC, const float* ddt, const int32_t* lengths, const float* conv_w,
                             const float* conv_b, const float* dt_bias, int ndir, int B, int L, int di, int N, int H,
-                            void* dzxbcdt, float* dconv_w, float* dconv_b, float* ddt_bias, void* stream) {
+                            void* dzxbcdt, float* dconv_w, float* dconv_b, float* ddt_bias, int dbc_parts, void* stream) {
   HNB_CHECK_ARG(zxbcdt && dxc && dBC && ddt && conv_w && conv_b && dt_bias && dzxbcdt && dconv_w && dconv_b && ddt_bias,
                 "conv_bwd: null pointer");
+  HNB_CHECK_ARG(dbc_parts == 1 || (dbc_parts == 2 && dtype == HNB_BF16), "conv_bwd: dbc_parts must be 1 (or 2 with bf16 activations)");
+  const long long pstride = (long long)ndir * B * L * 2 * N;
   int rc = conv_check("conv_bwd", dtype, ldz, dstride, ndir, B, L, di, N, H);
   if (rc) return rc;
   const int C = di + 2 * N;
@@ -392,22 +421,27 @@ extern "C" int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long
   const int vec = ((reinterpret_cast<uintptr_t>(dconv_w) | reinterpret_cast<uintptr_t>(dconv_b)) & 15) == 0;
   static const int variant = getenv("HNB_CONV_BWD_VARIANT") ? atoi(getenv("HNB_CONV_BWD_VARIANT")) : 0;   // tuning knob
   const int ysegs = cdiv(L, CONV_SEG * (CONV_B_TS * CONV_B_NT - 3));
-  if (dtype == HNB_BF16 && variant == 2) {
+  if (dtype == HNB_BF16 && variant == 2 && dbc_parts == 1) {
     // 2 channels per thread (64 registers, 4 resident blocks): measured SLOWER (130 vs 89 us), 4-byte accesses cost more than occupancy gains
     dim3 grid(cdiv(C / 2, CONV_CT), ysegs, ndir * B);
-    conv_bwd_kernel<__nv_bfloat16, V8<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 4><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+    conv_bwd_kernel<__nv_bfloat16, V8<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 4, false><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
         (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
-        conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
+        conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
+  } else if (dtype == HNB_BF16 && dbc_parts == 2) {
+    dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
+    conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2, true><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+        (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
+        conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
   } else if (dtype == HNB_BF16) {
     dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
-    conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+    conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2, false><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
         (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
-        conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
+        conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
   } else if (dtype == HNB_F32) {
     dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
-    conv_bwd_kernel<float, V16<float>, CONV_B_TS, CONV_B_NT, 2><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt,
+    conv_bwd_kernel<float, V16<float>, CONV_B_TS, CONV_B_NT, 2, false><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt,
         (const float*)dxc, ldz, dstride, (const float*)dBC, ddt, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H,
-        (float*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec);
+        (float*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
   } else { set_error("conv_bwd: unsupported dtype"); return HNB_ERR_INVALID_ARG; }
   HNB_LAUNCH_CHECK("conv_bwd");
   return HNB_OK;

@@ -569,7 +569,12 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
                    int di, int N, int H, void* y, void* states, void* stream);
 int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
                    const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
-                   void* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream);
+                   void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, void* stream);
+int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H);
+
+extern "C" int hnb_ssd_dbc_parts(int ndir, int B, int L, int H, int impl) {
+  return impl == 1 ? hnb_ssd_dbc_parts_tc(ndir, B, L, H) : 1;
+}
 
 template <typename T>
 static int ssd_fwd_impl(const T* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B,
@@ -640,8 +645,8 @@ static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt
 
 extern "C" int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int dtype, const float* dt,
                            const float* A_log, const float* Dskip, const void* states, int ndir, int B, int L, int di,
-                           int N, int H, void* dxc, void* dBC, float* ddt, float* dA_log, float* dD, void* ws2,
-                           int impl, void* stream) {
+                           int N, int H, void* dxc, void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD,
+                           void* ws2, int impl, void* stream) {
   HNB_CHECK_ARG(dy && xconv && y && dt && A_log && Dskip && states && dxc && dBC && ddt && dA_log && dD && ws2,
                 "ssd_bwd: null pointer");
   int rc = ssd_check("ssd_bwd", ndir, B, L, di, N, H);
@@ -649,9 +654,10 @@ extern "C" int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) {
     HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_bwd: the tcgen05 path takes bf16 activations");
-    return hnb_ssd_bwd_tc(dy, xconv, y, dt, A_log, Dskip, states, ndir, B, L, di, N, H, dxc, dBC, ddt, dA_log, dD, ws2,
-                          stream);
+    return hnb_ssd_bwd_tc(dy, xconv, y, dt, A_log, Dskip, states, ndir, B, L, di, N, H, dxc, dBC, dbc_parts, ddt, dA_log,
+                          dD, ws2, stream);
   }
+  HNB_CHECK_ARG(dbc_parts == 1, "ssd_bwd: the CUDA-core path writes one dBC part");
   if (dtype == HNB_BF16)
     return ssd_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)xconv, (const __nv_bfloat16*)y,
                                        dt, A_log, Dskip, (const float*)states, ndir, B, L, di, H, (__nv_bfloat16*)dxc,

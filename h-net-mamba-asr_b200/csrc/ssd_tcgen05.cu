@@ -407,11 +407,21 @@ struct BwdParams {
   const float* tables;           // [ndir*B, H, nc, TAB_FLOATS]  (built by the forward)
   __nv_bfloat16* gstates;        // [ndir*B, H, nc, 128, 64]
   __nv_bfloat16* dxc;            // [ndir*B*L, di]
-  __nv_bfloat16* dBC;            // [ndir*B*L, 2N]
+  __nv_bfloat16* dBC;            // [HG][ndir*B*L, 2N]: one partial sum per head group (summed by the conv backward)
+  long long dbc_part_stride;     // elements between the parts
+  int HG;                        // head groups of the dB/dC kernel (H % HG == 0)
   float* ddt;                    // [ndir*B*L, H]
   float* dA_log; float* dD;      // [ndir, H]
   int ndirB, B, L, H, di, nc;
   FastDiv dH, dB, dnc;
+  // Work-item order of the dx and dB/dC kernels: every full 128-frame chunk first, the partly filled last chunk of
+  // each row (cheap: its MMAs and epilogues are trimmed to the valid frames) at the end, so that the static
+  // round-robin over CTAs hands out the expensive items evenly and the cheap ones fill the last wave.
+  int nfc, n_full;               // full chunks per row, ndirB * nfc
+  FastDiv dnfc, dHG;
+  __device__ __forceinline__ void chunk_of(int base, int& db, int& c) const {
+    if (base < n_full) dnfc.divmod(base, db, c); else { db = base - n_full; c = nc - 1; }
+  }
   long long* dbg;                // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
 };
 
@@ -558,7 +568,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr uint32_t idesc_km64 = umma::make_idesc_bf16(128, 64, 0, 1);
   constexpr uint32_t idesc_mm64 = umma::make_idesc_bf16(128, 64, 1, 1);
   auto issue_load = [&](int item, int buf) {
-    int t1, h, db, c; p.dH.divmod(item, t1, h); p.dnc.divmod(t1, db, c);
+    int t1, h, db, c; p.dH.divmod(item, t1, h); p.chunk_of(t1, db, c);
     const int srow = (((db * H + h) * nc) + c) * TN;
     umma::mbar_expect_tx(bar_load, 8 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(srow / TN) * TAB_FLOATS, TAB_BYTES, bar_load);
@@ -588,7 +598,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     float* s_pdot = s_ddtx + 4 * TQ;                                  // [NT] <Gst, S_in>
     float* s_psc = s_pdot + NT;                                       // [NT] d cs_last from the chunk state
     float* s_pdd = s_psc + NT;                                        // [NT] dD
-    int t1, h, db, c; p.dH.divmod(it, t1, h); p.dnc.divmod(t1, db, c);
+    int t1, h, db, c; p.dH.divmod(it, t1, h); p.chunk_of(t1, db, c);
     const int dir = p.dB.div(db);
     const float A = -__expf(p.A_log[dir * H + h]);
     const float Dh = p.Dskip[dir * H + h];
@@ -850,12 +860,14 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
-  const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * nc;
+  // an item = (row, chunk, head group): with all heads in one CTA the 320 / 160 items of the outer / main stack fill
+  // 2.2 / 1.1 waves of 148 SMs; head groups (partial dB/dC sums, added up by the conv backward) fill whole waves
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc, HG = p.HG, Hh = H / HG, n_items = p.ndirB * nc * HG;
   constexpr uint32_t i_kk = umma::make_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t i_km = umma::make_idesc_bf16(128, 128, 0, 1);
   constexpr uint32_t i_mm = umma::make_idesc_bf16(128, 128, 1, 1);
   auto load_cb = [&](int item) {
-    int db, c; p.dnc.divmod(item, db, c);
+    int db, c; p.chunk_of(p.dHG.div(item), db, c);
     umma::mbar_expect_tx(bar_cb, 4 * HALF);
     umma::tma_load_3d(sC, &tmX, bar_cb, di + TN, c * TQ, db);
     umma::tma_load_3d(sC + HALF, &tmX, bar_cb, di + TN + 64, c * TQ, db);
@@ -865,16 +877,18 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   // Per head-step two load groups: X | dY | tables (free again as soon as R and the scaled copies are made) and
   // S_in | Gst (free when the second MMA group retires), so the first group of the NEXT step is in flight, and its
   // R = dY X^T already queued on the tensor pipe, while this step's second MMA group runs.
-  auto load_xd = [&](int item, int h, int buf) {
-    int db, c; p.dnc.divmod(item, db, c);
+  auto load_xd = [&](int item, int hh, int buf) {               // hh: head index inside the item's group
+    int base, hg, db, c; p.dHG.divmod(item, base, hg); p.chunk_of(base, db, c);
+    const int h = hg * Hh + hh;
     const int srow = ((db * H + h) * nc) + c;
     umma::mbar_expect_tx(bar_xd, 2 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)srow * TAB_FLOATS, TAB_BYTES, bar_xd);
     umma::tma_load_3d(sX, &tmX, bar_xd, h * TP, c * TQ, db);
     umma::tma_load_3d(sdY, &tmDY, bar_xd, h * TP, c * TQ, db);
   };
-  auto load_sg = [&](int item, int h) {
-    int db, c; p.dnc.divmod(item, db, c);
+  auto load_sg = [&](int item, int hh) {
+    int base, hg, db, c; p.dHG.divmod(item, base, hg); p.chunk_of(base, db, c);
+    const int h = hg * Hh + hh;
     const int srow = (((db * H + h) * nc) + c) * TN;
     umma::mbar_expect_tx(bar_sg, 2 * HALF);
     umma::tma_load_2d(sS, &tmS, bar_sg, 0, srow);
@@ -897,16 +911,16 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     issue_r();
   }
   for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
-    int db, c; p.dnc.divmod(it, db, c);
+    int base, hg, db, c; p.dHG.divmod(it, base, hg); p.chunk_of(base, db, c);
     const int q0 = c * TQ, qv = min(TQ, L - q0);
     const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;             // row blocks / k-steps that hold valid frames
     const long long row0 = (long long)db * L + q0;
-    for (int h = 0; h < H; ++h, ++hseq) {
+    for (int h = 0; h < Hh; ++h, ++hseq) {                             // h: head index inside this item's group
       const uint32_t par = hseq & 1;
       const float* tab = tabs + (hseq & 1) * TAB_FLOATS;
       const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
       int nit = it, nh = h + 1;                                        // the head-step after this one
-      if (nh == H) { nit = it + gridDim.x; nh = 0; }
+      if (nh == Hh) { nit = it + gridDim.x; nh = 0; }
       const long long tk0 = clock64();
       umma::mbar_wait(bar_xd, par);
       const long long tk1 = clock64();
@@ -1005,7 +1019,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           umma::tmem_ld32(t_lane + (part == 0 ? 256u : 128u) + 32u * J, v);
           umma::tmem_ld_wait();
           if (t < qv) {
-            __nv_bfloat16* og = p.dBC + (row0 + t) * (2 * TN) + part * TN + 32 * J;
+            __nv_bfloat16* og = p.dBC + hg * p.dbc_part_stride + (row0 + t) * (2 * TN) + part * TN + 32 * J;
 #pragma unroll
             for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(og + 8 * k) = pack8(v + 8 * k);
           }
@@ -1084,9 +1098,28 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   return HNB_OK;
 }
 
+// Head groups of the dB/dC kernel (1 or 2).  Items are handed out round-robin in descending cost order, so the
+// first CTA carries the largest item of every round: its load is the makespan.  Cost unit: one head-step of a full
+// chunk; a partly filled chunk costs its fixed latency plus the trimmed share.  A second part costs the convolution
+// backward one extra read of dB | dC (about two head-steps' worth of time).
+int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H) {
+  const int sms = sm_count(), nc = cdiv(L, TQ), rem = L - (nc - 1) * TQ;
+  const int nfull = ndir * B * (rem == TQ ? nc : nc - 1), npart = ndir * B * nc - nfull;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int hg = 1; hg <= 2; ++hg) {
+    if (H % hg) continue;
+    const double full = H / hg + 0.6, part = (0.45 + 0.55 * rem / TQ) * (H / hg) + 0.6;
+    double cost = 2.0 * (hg - 1);
+    for (long long i = 0; i < (long long)(nfull + npart) * hg; i += sms) cost += i < (long long)nfull * hg ? full : part;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = hg; }
+  }
+  return best;
+}
+
 int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
                    const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
-                   void* dBC, float* ddt, float* dA_log, float* dD, void* ws2, void* stream) {
+                   void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, void* stream) {
   (void)y;
   HNB_CHECK_ARG(N == TN && di == H * TP, "ssd_bwd(tcgen05): built for d_state=128, headdim=64");
   const int C = di + 2 * N, nc = cdiv(L, TQ);
@@ -1109,8 +1142,12 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   BwdParams p;
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.gstates = (__nv_bfloat16*)ws2; p.dxc = (__nv_bfloat16*)dxc;
   p.dBC = (__nv_bfloat16*)dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
+  HNB_CHECK_ARG((dbc_parts == 1 || dbc_parts == 2) && H % dbc_parts == 0, "ssd_bwd(tcgen05): dbc_parts must be 1 or 2 and divide H");
+  p.HG = dbc_parts; p.dbc_part_stride = (long long)ndir * B * L * 2 * N;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = nc;
   p.dH = FastDiv(H); p.dB = FastDiv(B); p.dnc = FastDiv(nc);
+  p.nfc = (L % TQ == 0) ? nc : nc - 1; p.n_full = p.ndirB * p.nfc;
+  p.dnfc = FastDiv(p.nfc > 0 ? p.nfc : 1); p.dHG = FastDiv(dbc_parts);
   HNB_CHECK_ARG((long long)ndir * B * H * nc * (H > B ? H : B) < (1LL << 31), "ssd_bwd(tcgen05): problem too large");
   p.tables = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.dbg = nullptr;
@@ -1126,7 +1163,7 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   items = ndir * B * nc * H;
   ssd_bwd_dx_tc_kernel<BWD_THREADS><<<items < sms ? items : sms, BWD_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dx_tc");
-  items = ndir * B * nc;
+  items = ndir * B * nc * dbc_parts;
   ssd_bwd_dbc_tc_kernel<BWD_THREADS><<<items < sms ? items : sms, BWD_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dbc_tc");
   if (debug) {

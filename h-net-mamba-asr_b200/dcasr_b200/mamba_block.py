@@ -117,7 +117,8 @@ def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, ln_a
     a_cw, a_cb, a_nw = accs[0].view(ndir, C, 4), accs[1].view(ndir, C), accs[2].view(ndir, di)
     a_dA, a_dD, a_dtb = accs[3].view(ndir, H), accs[4].view(ndir, H), accs[5].view(ndir, H)
     dy, dnorm_w = ops.gated_norm_bwd(dyn, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx, acc=a_nw)
-    dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, acc=(a_dA, a_dD))
+    dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, acc=(a_dA, a_dD),
+                                        keep_parts=True)
     dconv_w, dconv_b, ddt_bias = ops.conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias,
                                               ndir, B, L, di, N, H, dzx, acc=(a_cw, a_cb, a_dtb))
     dh2 = ops.gemm(dzx, Win, trans_b=True)                               # dgrad [B*L, d]

@@ -205,8 +205,9 @@ def conv_bwd(zx, dxc, dBC, ddt, dstride, lengths, conv_w, conv_b, dt_bias, ndir,
     if acc is None:
         acc = (torch.zeros_like(conv_w), torch.zeros_like(conv_b), torch.zeros_like(dt_bias))
     dw, db, ddtb = acc
+    parts = dBC.shape[0] if dBC.dim() == 4 else 1          # [parts, ndir, B*L, 2N]: partial sums of the SSD dB/dC kernel
     lib().call("conv_bwd", zx, dxc, dtype_code(zx.dtype), zx.stride(0), dstride, dBC, ddt, lengths, conv_w, conv_b,
-               dt_bias, ndir, B, L, di, N, H, dzx, dw, db, ddtb, stream())
+               dt_bias, ndir, B, L, di, N, H, dzx, dw, db, ddtb, parts, stream())
     return dw, db, ddtb
 
 
@@ -225,17 +226,21 @@ def ssd_fwd(xconv, dt, A_log, D, ndir, B, L, di, N, H, impl=None):
     return y, ws
 
 
-def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H, impl=None, acc=None):
-    """acc: optional pre-zeroed (dA_log, dD) accumulators."""
+def ssd_bwd(dy, xconv, y, dt, A_log, D, ws, ndir, B, L, di, N, H, impl=None, acc=None, keep_parts=False):
+    """acc: optional pre-zeroed (dA_log, dD) accumulators.  keep_parts: return dBC as [parts, ndir, B*L, 2N] partial sums
+    (what conv_bwd consumes) instead of their sum."""
     L_ = lib()
     impl = ssd_impl_for(dy.dtype) if impl is None else impl
     dxc = torch.empty_like(dy)
-    dBC = _empty((ndir, B * L, 2 * N), dy.dtype, dy)
+    parts = int(L_.raw("ssd_dbc_parts")(ndir, B, L, H, impl))
+    dBC = _empty((parts, ndir, B * L, 2 * N), dy.dtype, dy)
     ddt = torch.empty_like(dt)
     dA, dD = acc if acc is not None else (torch.zeros_like(A_log), torch.zeros_like(D))
     ws2 = _empty((L_.raw("ssd_ws_bytes")(ndir, B, L, di, N, H) // 4,), torch.float32, dy)
-    L_.call("ssd_bwd", dy, xconv, y, dtype_code(dy.dtype), dt, A_log, D, ws, ndir, B, L, di, N, H, dxc, dBC, ddt,
+    L_.call("ssd_bwd", dy, xconv, y, dtype_code(dy.dtype), dt, A_log, D, ws, ndir, B, L, di, N, H, dxc, dBC, parts, ddt,
             dA, dD, ws2, impl, stream())
+    if not keep_parts:
+        dBC = dBC[0] if parts == 1 else dBC.float().sum(0).to(dy.dtype)
     return dxc, dBC, ddt, dA, dD
 
 

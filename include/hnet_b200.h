@@ -134,13 +134,13 @@ int hnb_conv_fwd(const void* zxbcdt, int dtype, long long ldz, long long dstride
                  const float* conv_w, const float* conv_b, const float* dt_bias,
                  int ndir, int B, int L, int di, int N, int H,
                  void* xconv, float* dt, void* stream);
-/* backward: reads dxc [ndir,B*L,di] and dBC [ndir,B*L,2N] (both act dtype: d wrt conv'd x | B | C), ddt
- * [ndir,B*L,H] float (all scan order); writes the xBC and dt columns of dzxbcdt (natural order) and
- * ACCUMULATES dconv_w, dconv_b, ddt_bias. */
+/* backward: reads dxc [ndir,B*L,di] and dBC [dbc_parts][ndir,B*L,2N] (both act dtype: d wrt conv'd x | B | C; the
+ * dbc_parts partial sums of hnb_ssd_bwd are added up on the fly), ddt [ndir,B*L,H] float (all scan order); writes the
+ * xBC and dt columns of dzxbcdt (natural order) and ACCUMULATES dconv_w, dconv_b, ddt_bias. */
 int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long long ldz, long long dstride, const void* dBC,
                  const float* ddt, const int32_t* lengths, const float* conv_w, const float* conv_b,
                  const float* dt_bias, int ndir, int B, int L, int di, int N, int H,
-                 void* dzxbcdt, float* dconv_w, float* dconv_b, float* ddt_bias, void* stream);
+                 void* dzxbcdt, float* dconv_w, float* dconv_b, float* ddt_bias, int dbc_parts, void* stream);
 
 /* SSD selective scan in scan order (mamba_ssm mamba_chunk_scan_combined):
  *   h_t = exp(dt_t A) h_{t-1} + dt_t B_t (x) x_t ,  y_t = C_t . h_t + D x_t
@@ -152,13 +152,16 @@ int hnb_ssd_chunk(void);
 int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const float* A_log, const float* Dskip,
                 int ndir, int B, int L, int di, int N, int H, void* y, void* states, int impl,
                 void* stream);
-/* backward.  dy [ndir,B*L,di].  Outputs: dxc [ndir,B*L,di] (act dtype), dBC [ndir,B*L,2N] float
- * (zero-initialised by the call), ddt [ndir,B*L,H] float, and ACCUMULATED dA_log, dD [ndir,H].
+/* backward.  dy [ndir,B*L,di].  Outputs: dxc [ndir,B*L,di] (act dtype), dBC [dbc_parts][ndir,B*L,2N] (act dtype),
+ * ddt [ndir,B*L,H] float, and ACCUMULATED dA_log, dD [ndir,H].
+ * dbc_parts = hnb_ssd_dbc_parts(...): the tcgen05 dB/dC kernel may split the heads into two groups (1 or 2 parts) so that its
+ * work items fill whole waves of SMs; each group writes its own partial sum and hnb_conv_bwd adds the parts up.
  * ws2: second workspace of hnb_ssd_ws_bytes() bytes. */
+int hnb_ssd_dbc_parts(int ndir, int B, int L, int H, int impl);
 int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int dtype, const float* dt,
                 const float* A_log, const float* Dskip, const void* states,
                 int ndir, int B, int L, int di, int N, int H,
-                void* dxc, void* dBC, float* ddt, float* dA_log, float* dD, void* ws2, int impl,
+                void* dxc, void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, int impl,
                 void* stream);
 
 /* gated RMSNorm  rmsnorm(y * silu(z)) * w  (mamba_ssm RMSNormGated, norm_before_gate=False, eps 1e-5)

@@ -56,8 +56,8 @@ for (T, d, di, H, tag) in ((15920, 384, 768, 12, "outer"), (7840, 512, 1024, 16,
     dzx = torch.zeros_like(zx)
     rec(f"{tag} gated_norm_bwd", timeit(lambda: ops.gated_norm_bwd(yn, yy, zx, ds, lens, nw, rs, 2, B, L, di, dzx)), None, 2 * T * di * 10)
     dy = bf(2, T, di)
-    _lib.profile_start(); ops.ssd_bwd(dy, xconv, yy, dt, Al, Dk, ws, 2, B, L, di, N, H, impl=1); _lib.profile_stop()
-    rec(f"{tag} ssd_bwd tc (3 kernels)", timeit(lambda: ops.ssd_bwd(dy, xconv, yy, dt, Al, Dk, ws, 2, B, L, di, N, H, impl=1)), 2.5 * 4.0 * di * N * 2 * T, 2 * T * (C * 2 + di * 3) * 2)
-    dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, yy, dt, Al, Dk, ws, 2, B, L, di, N, H, impl=1)
+    _lib.profile_start(); ops.ssd_bwd(dy, xconv, yy, dt, Al, Dk, ws, 2, B, L, di, N, H, impl=1, keep_parts=True); _lib.profile_stop()
+    rec(f"{tag} ssd_bwd tc (3 kernels)", timeit(lambda: ops.ssd_bwd(dy, xconv, yy, dt, Al, Dk, ws, 2, B, L, di, N, H, impl=1, keep_parts=True)), 2.5 * 4.0 * di * N * 2 * T, 2 * T * (C * 2 + di * 3) * 2)
+    dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, yy, dt, Al, Dk, ws, 2, B, L, di, N, H, impl=1, keep_parts=True)
     rec(f"{tag} conv_bwd", timeit(lambda: ops.conv_bwd(zx, dxc, dBC, ddt, ds, lens, cw, cb, dtb, 2, B, L, di, N, H, dzx)), None, 2 * T * C * 6)
 json.dump(rows, open("gpurun_out/kbench.json", "w"), indent=1)
