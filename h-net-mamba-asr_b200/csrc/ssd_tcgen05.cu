@@ -32,6 +32,9 @@
 namespace hnb {
 namespace {
 
+// phase timers exist only in the DBG instantiations (HNB_SSD_DEBUG=1): they cost ten live registers otherwise
+#define HNB_CLK() (DBG ? clock64() : 0LL)
+
 constexpr int TQ = 128;                 // chunk length
 constexpr int TP = 64;                  // head dim
 constexpr int TN = 128;                 // state dim
@@ -166,7 +169,7 @@ struct FwdParams {
   long long* dbg;         // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
 };
 
-template <int NT>
+template <int NT, bool DBG>
 __global__ void __launch_bounds__(NT, 1)
 ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   constexpr int NCG = NT / 128;           // column groups: warp w -> TMEM lane quarter w%4, column group w/4
@@ -249,9 +252,9 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
 #pragma unroll
         for (int k = 0; k < 2 * NB; ++k) *reinterpret_cast<uint4*>(sg + 8 * k) = pack8(Sreg + 8 * k);
       }
-      const long long tk0 = clock64();
+      const long long tk0 = HNB_CLK();
       umma::mbar_wait(bar_load, par);
-      const long long tk1 = clock64();
+      const long long tk1 = HNB_CLK();
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
@@ -294,16 +297,16 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       }
       if (loader && nit < n_items) {                                   // next step's tiles land during this step's epilogues
         umma::mbar_wait(bar_free, par);
-        const long long tl0 = clock64();
+        const long long tl0 = HNB_CLK();
         issue_load(nit, ncn, buf ^ 1);
-        if (p.dbg && blockIdx.x == 0) {                                // debug only: how long the TMA group takes to land
+        if (DBG && p.dbg && blockIdx.x == 0) {                                // debug only: how long the TMA group takes to land
           umma::mbar_wait(bar_load, par ^ 1);
-          p.dbg[5] += clock64() - tl0; p.dbg[7] += tl0 - tk1;
+          p.dbg[5] += HNB_CLK() - tl0; p.dbg[7] += tl0 - tk1;
         }
       }
       umma::mbar_wait(bar_g, par);
       umma::tc_fence_after();
-      const long long tk2 = clock64();
+      const long long tk2 = HNB_CLK();
       // ---- epilogue 1: M[t,s] = G[t,s] e^{cs_t - cs_s} dt_s (s <= t), bf16, K-major swizzled
       if ((row >> 5) < nblk) {                                         // padding rows: their M rows only feed unused y rows
         const int t = row, I = t >> 5;
@@ -332,7 +335,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       umma::fence_async_smem();
       umma::tc_fence_before();
       __syncthreads();
-      const long long tk3 = clock64();
+      const long long tk3 = HNB_CLK();
       if (issuer) {
         umma::tc_fence_after();
 #pragma unroll
@@ -346,7 +349,7 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       }
       umma::mbar_wait(bar_y, par);
       umma::tc_fence_after();
-      const long long tk4 = clock64();
+      const long long tk4 = HNB_CLK();
       // ---- epilogue 2: y = Yd + e^{cs_t} Yo + D x          (thread = row t, 64/NCG of the 64 columns)
 #pragma unroll
       for (int bb = 0; bb < NB; ++bb) {
@@ -387,8 +390,8 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
       umma::fence_async_smem();
       umma::tc_fence_before();
       __syncthreads();
-      if (p.dbg && blockIdx.x == 0 && tid == 0) {
-        const long long tk5 = clock64();
+      if (DBG && p.dbg && blockIdx.x == 0 && tid == 0) {
+        const long long tk5 = HNB_CLK();
         p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
         p.dbg[4] += tk5 - tk4; p.dbg[6] += 1;
       }
@@ -419,6 +422,8 @@ struct BwdParams {
   // round-robin over CTAs hands out the expensive items evenly and the cheap ones fill the last wave.
   int nfc, n_full;               // full chunks per row, ndirB * nfc
   FastDiv dnfc, dHG;
+  int dxHh;                      // dx kernel: heads per work item (C, B and G = C B^T are shared by an item's heads)
+  FastDiv dHGx;                  // H / dxHh
   __device__ __forceinline__ void chunk_of(int base, int& db, int& c) const {
     if (base < n_full) dnfc.divmod(base, db, c); else { db = base - n_full; c = nc - 1; }
   }
@@ -531,7 +536,7 @@ constexpr int D2_OFF_EXTRA = D2_OFF_TAB + 2 * TAB_BYTES;
 constexpr int D2_OFF_BAR = D2_OFF_EXTRA + 2 * EXTRA_FLOATS * 4;     // partial sums double-buffered by item parity
 constexpr int D2_SMEM = D2_OFF_BAR + 64 + 1024;
 
-template <int NT>
+template <int NT, bool DBG>
 __global__ void __launch_bounds__(NT, 1)
 ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                      const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
@@ -549,7 +554,8 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* bar1 = bar_load + 1;
   uint64_t* bar2 = bar_load + 2;
   uint64_t* bar1b = bar_load + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
+  uint64_t* bar_cb = bar_load + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2, row = lq * 32 + lane;
   const bool issuer = tid == NTAB;
@@ -557,40 +563,55 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (tid == 0) {
     umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
     umma::mbar_init(bar_load, 1); umma::mbar_init(bar1, 1); umma::mbar_init(bar2, 1); umma::mbar_init(bar1b, 1);
+    umma::mbar_init(bar_cb, 1);
     umma::fence_barrier_init();
   }
   if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
   umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
-  const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * nc * H;
+  // A work item = (row, chunk, group of Hh heads): C, B (64 of the 144 KB a head-step used to load) and the score
+  // tile G = C B^T do not depend on the head, so they are fetched / computed once per item and G stays in TMEM.
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc, Hh = p.dxHh, n_items = p.ndirB * nc * (H / Hh);
   constexpr uint32_t idesc_kk128 = umma::make_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t idesc_km64 = umma::make_idesc_bf16(128, 64, 0, 1);
   constexpr uint32_t idesc_mm64 = umma::make_idesc_bf16(128, 64, 1, 1);
-  auto issue_load = [&](int item, int buf) {
-    int t1, h, db, c; p.dH.divmod(item, t1, h); p.chunk_of(t1, db, c);
+  auto load_cb = [&](int item) {
+    int base, hg, db, c; p.dHGx.divmod(item, base, hg); p.chunk_of(base, db, c);
+    umma::mbar_expect_tx(bar_cb, 4 * HALF);
+    umma::tma_load_3d(sC, &tmX, bar_cb, di + TN, c * TQ, db);
+    umma::tma_load_3d(sC + HALF, &tmX, bar_cb, di + TN + 64, c * TQ, db);
+    umma::tma_load_3d(sB, &tmX, bar_cb, di, c * TQ, db);
+    umma::tma_load_3d(sB + HALF, &tmX, bar_cb, di + 64, c * TQ, db);
+  };
+  auto load_head = [&](int item, int hh, int buf) {
+    int base, hg, db, c; p.dHGx.divmod(item, base, hg); p.chunk_of(base, db, c);
+    const int h = hg * Hh + hh;
     const int srow = (((db * H + h) * nc) + c) * TN;
-    umma::mbar_expect_tx(bar_load, 8 * HALF + TAB_BYTES);
+    umma::mbar_expect_tx(bar_load, 4 * HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(srow / TN) * TAB_FLOATS, TAB_BYTES, bar_load);
-    umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
-    umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
-    umma::tma_load_3d(sB, &tmX, bar_load, di, c * TQ, db);
-    umma::tma_load_3d(sB + HALF, &tmX, bar_load, di + 64, c * TQ, db);
     umma::tma_load_3d(sX, &tmX, bar_load, h * TP, c * TQ, db);
     umma::tma_load_3d(sdY, &tmDY, bar_load, h * TP, c * TQ, db);
     umma::tma_load_2d(sS, &tmS, bar_load, 0, srow);
     umma::tma_load_2d(sG, &tmG, bar_load, 0, srow);
   };
-  uint32_t seq = 0;
+  uint32_t iseq = 0, seq = 0;                                          // item / head-step sequence numbers of this CTA
   for (int i = tid; i < 2 * HALF / 16; i += NT) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);   // finite padding rows
   umma::fence_async_smem();
-  if (blockIdx.x < n_items && issuer) issue_load(blockIdx.x, 0);
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++seq) {
+  if (blockIdx.x < n_items && issuer) { load_cb(blockIdx.x); load_head(blockIdx.x, 0, 0); }
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
+   int base, hg, db, c; p.dHGx.divmod(it, base, hg); p.chunk_of(base, db, c);
+   const int dir = p.dB.div(db);
+   const int q0 = c * TQ, qv = min(TQ, L - q0);
+   const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;              // row blocks / k-steps that hold valid frames
+   const long long row0 = (long long)db * L + q0;
+   for (int hh = 0; hh < Hh; ++hh, ++seq) {
+    const int h = hg * Hh + hh;
     const uint32_t par = seq & 1;
     const float* tab = tabs + (seq & 1) * TAB_FLOATS;
     const float* s_dt = tab + TQ; const float* s_ecs = tab + 3 * TQ; const float* s_eq = tab + 4 * TQ;
-    // partial sums of this item, one slot per (column group, row) or per warp (shared-memory float atomics are CAS
-    // loops); double-buffered by item parity so that warp 0 can finish item i while the others start item i+1
+    // partial sums of this head-step, one slot per (column group, row) or per warp (shared-memory float atomics are
+    // CAS loops); double-buffered by parity so that warp 0 can finish step i while the others start step i+1
     float* s_dcsA = xtra + (seq & 1) * EXTRA_FLOATS;                  // [4][128]  d cs_t, row terms (epilogue A)
     float* s_dcsB = s_dcsA + 4 * TQ;                                  // [4][128]  d cs_q, column terms (epilogue B)
     float* s_ddtx = s_dcsB + 4 * TQ;                                  // [4][128]  <du_q, x_q>
@@ -598,24 +619,23 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     float* s_pdot = s_ddtx + 4 * TQ;                                  // [NT] <Gst, S_in>
     float* s_psc = s_pdot + NT;                                       // [NT] d cs_last from the chunk state
     float* s_pdd = s_psc + NT;                                        // [NT] dD
-    int t1, h, db, c; p.dH.divmod(it, t1, h); p.chunk_of(t1, db, c);
-    const int dir = p.dB.div(db);
     const float A = -__expf(p.A_log[dir * H + h]);
     const float Dh = p.Dskip[dir * H + h];
-    const int q0 = c * TQ, qv = min(TQ, L - q0);
-    const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;             // row blocks / k-steps that hold valid frames
-    const long long row0 = (long long)db * L + q0;
-    const int nit = it + gridDim.x;
-    long long tk0 = clock64();
+    int nit = it, nh = hh + 1;                                         // the head-step after this one
+    if (nh == Hh) { nit = it + gridDim.x; nh = 0; }
+    long long tk0 = HNB_CLK();
     umma::mbar_wait(bar_load, par);
-    long long tk1 = clock64();
+    long long tk1 = HNB_CLK();
     if (issuer) {
+      if (hh == 0) umma::mbar_wait(bar_cb, iseq & 1);
       umma::tc_fence_after();
+      if (hh == 0) {
 #pragma unroll
-      for (int kb = 0; kb < 8; ++kb) {                                 // G = C B^T
-        const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
-        umma::mma_bf16_ss(tmem + 0, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
-                          umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024), idesc_kk128, kb > 0);
+        for (int kb = 0; kb < 8; ++kb) {                               // G = C B^T  (kept in TMEM for the item's other heads)
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + 0, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024), idesc_kk128, kb > 0);
+        }
       }
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb)                                   // R = dY X^T
@@ -650,7 +670,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     umma::mbar_wait(bar1, par);
     umma::tc_fence_after();
-    long long tk2 = clock64();
+    long long tk2 = HNB_CLK();
     // ---- epilogue A (thread = row t, 128/NCG of the 128 columns): K = G o L -> smem;
     //      d cs_t += sum_q W G  +  e^{cs_t} <dY_t, Yo_t>
     if ((row >> 5) >= nblk) {
@@ -709,7 +729,7 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       s_dcsA[cg * TQ + t] = acc + s_ecs[t] * yd;
     }
     umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();
-    long long tk3 = clock64();
+    long long tk3 = HNB_CLK();
     if (issuer) {
       umma::tc_fence_after();
 #pragma unroll
@@ -729,9 +749,12 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     umma::mbar_wait(bar2, par);
     umma::tc_fence_after();
-    long long tk4 = clock64();
+    long long tk4 = HNB_CLK();
     __syncthreads();                                                   // every smem operand has been consumed
-    if (issuer && nit < n_items) issue_load(nit, (seq & 1) ^ 1);
+    if (issuer && nit < n_items) {
+      if (nh == 0) load_cb(nit);
+      load_head(nit, nh, (seq & 1) ^ 1);
+    }
     // ---- epilogue B (thread = row q, 64/NCG of the 64 columns): dx, and the remaining d cs terms
     if ((q >> 5) >= nblk) {
       s_dcsB[cg * TQ + q] = 0.f; s_ddtx[cg * TQ + q] = 0.f;
@@ -812,11 +835,12 @@ ssd_bwd_dx_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       accA = warp_sum(accA);
       if (lane == 0) { atomicAdd(p.dA_log + dir * H + h, accA * A); atomicAdd(p.dD + dir * H + h, dd); }
     }
-    if (p.dbg && blockIdx.x == 0 && tid == 160) {                      // a warp that does not run the tail
-      const long long tk5 = clock64();
+    if (DBG && p.dbg && blockIdx.x == 0 && tid == 160) {                      // a warp that does not run the tail
+      const long long tk5 = HNB_CLK();
       p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
       p.dbg[4] += tk5 - tk4; p.dbg[6] += 1;
     }
+   }
   }
   umma::tc_fence_before(); __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
@@ -828,7 +852,7 @@ constexpr int D3_OFF_C = 0, D3_OFF_B = 2 * HALF, D3_OFF_X = 4 * HALF, D3_OFF_DY 
 constexpr int D3_OFF_BAR = D3_OFF_TAB + 2 * TAB_BYTES;
 constexpr int D3_SMEM = D3_OFF_BAR + 64 + 1024;
 
-template <int NT>
+template <int NT, bool DBG>
 __global__ void __launch_bounds__(NT, 1)
 ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                       const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
@@ -921,9 +945,9 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
       int nit = it, nh = h + 1;                                        // the head-step after this one
       if (nh == Hh) { nit = it + gridDim.x; nh = 0; }
-      const long long tk0 = clock64();
+      const long long tk0 = HNB_CLK();
       umma::mbar_wait(bar_xd, par);
-      const long long tk1 = clock64();
+      const long long tk1 = HNB_CLK();
       for (int i = tid; i < TQ * 8; i += NT) {                         // Xw = w_q X,  dYs = e^{cs_t} dY
         const float w = s_w[i >> 3], e = s_ecs[i >> 3];
         float a[8], b[8];
@@ -936,7 +960,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       umma::mbar_wait(bar_r, par);
       umma::tc_fence_after();
-      const long long tk2 = clock64();
+      const long long tk2 = HNB_CLK();
       if ((row >> 5) < nblk) {            // W[t,q] = R[t,q] L[t,q] dt_q; padding rows are never read (k-trimmed MMAs)
         const int t = row, I = t >> 5;
         const float cs_t = tab[t], e_ref = I > 0 ? __expf(cs_t - tab[32 * I - 1]) : 0.f;
@@ -962,7 +986,7 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
       }
       umma::fence_async_smem(); umma::tc_fence_before(); __syncthreads();   // W, Xw, dYs written; R, X, dY, tables consumed
-      const long long tk3 = clock64();
+      const long long tk3 = HNB_CLK();
       if (issuer) {
         // next step's first load group goes out BEFORE this step's MMAs: the issuing thread stalls on the tensor-core
         // queue while it feeds 24 MMAs, and a TMA request placed behind them would start ~1.5k cycles late
@@ -1002,8 +1026,8 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (nh == 0) load_cb(nit);
         load_sg(nit, nh);
       }
-      if (p.dbg && blockIdx.x == 0 && tid == 0) {
-        const long long tk4 = clock64();
+      if (DBG && p.dbg && blockIdx.x == 0 && tid == 0) {
+        const long long tk4 = HNB_CLK();
         p.dbg[8] += tk1 - tk0; p.dbg[9] += tk2 - tk1; p.dbg[10] += tk3 - tk2; p.dbg[11] += tk4 - tk3; p.dbg[14] += 1;
       }
     }
@@ -1082,8 +1106,10 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   p.dbg = nullptr;
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
   if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, (cudaStream_t)stream); }
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-  ssd_fwd_tc_kernel<FWD_THREADS><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  if (debug) ssd_fwd_tc_kernel<FWD_THREADS, true><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
+  else ssd_fwd_tc_kernel<FWD_THREADS, false><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
   HNB_LAUNCH_CHECK("ssd_fwd_tc");
   if (debug) {
     long long h[8];
@@ -1113,6 +1139,25 @@ int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H) {
     double cost = 2.0 * (hg - 1);
     for (long long i = 0; i < (long long)(nfull + npart) * hg; i += sms) cost += i < (long long)nfull * hg ? full : part;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = hg; }
+  }
+  return best;
+}
+
+// Heads per work item of the dx kernel.  More heads per item amortise the C | B loads and the G = C B^T product, fewer
+// heads balance the static round-robin better; the first CTA carries the largest item of every round (descending cost
+// order), so its load is the makespan.  Cost unit: one head-step of a full chunk with nothing shared.
+static int dx_heads_per_item(int ndirB, int L, int H, int sms) {
+  const int nc = cdiv(L, TQ), rem = L - (nc - 1) * TQ;
+  const long long nfull = (long long)ndirB * (rem == TQ ? nc : nc - 1), npart = (long long)ndirB * nc - nfull;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int hh = 1; hh <= 8; ++hh) {
+    if (H % hh) continue;
+    const int groups = H / hh;
+    const double step = 1.0 - 0.12 * (1.0 - 1.0 / hh), full = hh * step, part = (0.45 + 0.55 * rem / TQ) * full;
+    double cost = 0.0;
+    for (long long i = 0; i < (nfull + npart) * groups; i += sms) cost += i < nfull * groups ? full : part;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = hh; }
   }
   return best;
 }
@@ -1148,6 +1193,11 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   p.dH = FastDiv(H); p.dB = FastDiv(B); p.dnc = FastDiv(nc);
   p.nfc = (L % TQ == 0) ? nc : nc - 1; p.n_full = p.ndirB * p.nfc;
   p.dnfc = FastDiv(p.nfc > 0 ? p.nfc : 1); p.dHG = FastDiv(dbc_parts);
+  {
+    static const int force = getenv("HNB_SSD_DX_HEADS") ? atoi(getenv("HNB_SSD_DX_HEADS")) : 0;   // tuning knob
+    p.dxHh = (force > 0 && H % force == 0) ? force : dx_heads_per_item(p.ndirB, L, H, sm_count());
+    p.dHGx = FastDiv(H / p.dxHh);
+  }
   HNB_CHECK_ARG((long long)ndir * B * H * nc * (H > B ? H : B) < (1LL << 31), "ssd_bwd(tcgen05): problem too large");
   p.tables = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.dbg = nullptr;
@@ -1155,16 +1205,20 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   if (debug) { cudaMalloc(&p.dbg, 128); cudaMemsetAsync(p.dbg, 0, 128, st); }
   const int sms = sm_count();
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dstate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D1_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel<BWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel<BWD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel<BWD_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel<BWD_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel<BWD_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
+  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel<BWD_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
   int items = ndir * B * H;
   ssd_bwd_dstate_tc_kernel<<<items < 2 * sms ? items : 2 * sms, D1_THREADS, D1_SMEM, st>>>(tmX, tmDY, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dstate_tc");
-  items = ndir * B * nc * H;
-  ssd_bwd_dx_tc_kernel<BWD_THREADS><<<items < sms ? items : sms, BWD_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  items = ndir * B * nc * (H / p.dxHh);
+  if (debug) ssd_bwd_dx_tc_kernel<BWD_THREADS, true><<<items < sms ? items : sms, BWD_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  else ssd_bwd_dx_tc_kernel<BWD_THREADS, false><<<items < sms ? items : sms, BWD_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dx_tc");
   items = ndir * B * nc * dbc_parts;
-  ssd_bwd_dbc_tc_kernel<BWD_THREADS><<<items < sms ? items : sms, BWD_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  if (debug) ssd_bwd_dbc_tc_kernel<BWD_THREADS, true><<<items < sms ? items : sms, BWD_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+  else ssd_bwd_dbc_tc_kernel<BWD_THREADS, false><<<items < sms ? items : sms, BWD_THREADS, D3_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dbc_tc");
   if (debug) {
     long long h[16];
