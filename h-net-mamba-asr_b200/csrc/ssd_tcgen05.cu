@@ -110,8 +110,9 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ dtp, int 
 // them sits on a kernel's critical path any more.
 __global__ void __launch_bounds__(TQ)
 ssd_tables_kernel(const float* __restrict__ dt, const float* __restrict__ A_log, float* __restrict__ tables, int B, int L,
-                  int H, int nc) {
+                  int H, int nc, int* __restrict__ work_counter) {
   __shared__ float tab[TAB_FLOATS];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *work_counter = 0;          // the forward kernel's dynamic work queue
   const int item = blockIdx.x;                                        // ((db * H) + h) * nc + c
   const int c = item % nc, h = (item / nc) % H, db = item / (nc * H), dir = db / B;
   const int q0 = c * TQ;
@@ -164,6 +165,8 @@ struct FwdParams {
   __nv_bfloat16* y;       // [ndir*B*L, di]
   __nv_bfloat16* states;  // [ndir*B, H, nc, 128(n), 64(p)]  state ENTERING each chunk
   const float* tables;    // [ndir*B, H, nc, TAB_FLOATS]
+  const __nv_bfloat16* xconv;   // [ndir*B*L, di + 2N]  (the two-CTA kernel reads x for the D x term from here)
+  int* counter;                 // two-CTA kernel: next unclaimed (row, head) item minus gridDim.x (zeroed by ssd_tables_kernel)
   int ndirB, B, L, H, di, nc;
   FastDiv dH, dB, dnc;
   long long* dbg;         // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
@@ -400,6 +403,264 @@ ssd_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// ===================================================================================================
+// forward, two CTAs per SM
+// ===================================================================================================
+// The one-CTA forward above is latency-bound: every chunk step is a chain  TMA -> G -> epilogue -> Yd -> epilogue ->
+// barrier  with the tensor pipe ~15 % and the issue slots ~30 % busy.  Two independent chains per SM hide each other's
+// waits, which needs <= 113 KB of shared memory and <= 256 TMEM columns per CTA:
+//   * the bf16 score tile M goes to TMEM (packed pairs) and is the A operand of Yd = M X straight from there
+//     (tcgen05.mma with A in TMEM): no 32 KB smem tile, no proxy fence on that hand-off;
+//   * w o X overwrites X in place once Yd has retired (x for the D x term is re-read from global: L2 hits);
+//   * one X buffer, loads for the next step issued as their buffers retire (C | tables after Yo, B | X after dS);
+//   * TMEM: G [0,128) -> reused by Yo [0,64) and dS [64,128) once epilogue 1 has read G;  M [128,192);  Yd [192,256).
+// 256 threads: warp w reads TMEM lane quarter w % 4 and column half w / 4.
+constexpr int F2_THREADS = 256;
+constexpr int F2_OFF_C = 0, F2_OFF_B = 2 * HALF, F2_OFF_X = 4 * HALF, F2_OFF_S = 5 * HALF, F2_OFF_TAB = 6 * HALF;
+constexpr int F2_OFF_BAR = F2_OFF_TAB + 2 * TAB_BYTES;
+constexpr int F2_SMEM = F2_OFF_BAR + 64 + 1024;
+static_assert(2 * (F2_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
+
+__global__ void __launch_bounds__(F2_THREADS, 2)
+ssd_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
+  uint8_t* sC = base + F2_OFF_C; uint8_t* sB = base + F2_OFF_B; uint8_t* sX = base + F2_OFF_X; uint8_t* sS = base + F2_OFF_S;
+  float* tabs = reinterpret_cast<float*>(base + F2_OFF_TAB);
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(base + F2_OFF_BAR);
+  uint64_t* bar_g = bar_load + 1;
+  uint64_t* bar_y = bar_load + 2;
+  uint64_t* bar_free = bar_load + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
+  volatile int* s_next = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2] next item of this CTA, by item parity
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, cg = warp >> 2;                 // TMEM lane quarter, column half
+  const int row = lq * 32 + lane;
+  const bool issuer = tid == 0;                            // warps 0 and 4 own the lightest score-tile rows
+  const bool loader = tid == 128;
+  if (tid == 0) {
+    umma::prefetch_tmap(&tmX);
+    umma::mbar_init(bar_load, 2);                          // two load groups per step, each one arrive.expect_tx
+    umma::mbar_init(bar_g, 1); umma::mbar_init(bar_y, 1); umma::mbar_init(bar_free, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 256);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
+  constexpr uint32_t TM_G = 0, TM_YO = 0, TM_DS = 64, TM_M = 128, TM_YD = 192;
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc, C = di + 2 * TN;
+  const int n_items = p.ndirB * H;
+  constexpr uint32_t idesc_g = umma::make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_y = umma::make_idesc_bf16(128, 64, 0, 1);
+  constexpr uint32_t idesc_s = umma::make_idesc_bf16(128, 64, 1, 1);
+
+  auto load_a = [&](int item, int c, int buf) {            // C | tables: free once G and Yo have retired
+    int db, h; p.dH.divmod(item, db, h);
+    umma::mbar_expect_tx(bar_load, 2 * HALF + TAB_BYTES);
+    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)(item * nc + c) * TAB_FLOATS, TAB_BYTES, bar_load);
+    umma::tma_load_3d(sC, &tmX, bar_load, di + TN, c * TQ, db);
+    umma::tma_load_3d(sC + HALF, &tmX, bar_load, di + TN + 64, c * TQ, db);
+  };
+  auto load_b = [&](int item, int c) {                     // B | X: free once dS has retired
+    int db, h; p.dH.divmod(item, db, h);
+    umma::mbar_expect_tx(bar_load, 3 * HALF);
+    umma::tma_load_3d(sB, &tmX, bar_load, di, c * TQ, db);
+    umma::tma_load_3d(sB + HALF, &tmX, bar_load, di + 64, c * TQ, db);
+    umma::tma_load_3d(sX, &tmX, bar_load, h * TP, c * TQ, db);
+  };
+
+  uint32_t seq = 0, fseq = 0, iseq = 0;                    // chunk steps / dS steps / items of this CTA
+  if (blockIdx.x < n_items && loader) { load_a(blockIdx.x, 0, 0); load_b(blockIdx.x, 0); }
+
+  // Items are handed out round-robin, or (HNB_SSD_FWD_DYNAMIC=1) claimed from a global counter.  Measured at the
+  // headline shapes the two are within 2 % of each other (equal-cost items: 960 on 296 CTAs is 4 rounds either way);
+  // the counter is for ragged batches, where rows differ in their number of chunks.
+  int my_next = n_items;                                   // loader only: the item after this one
+  for (int it = blockIdx.x; it < n_items; ++iseq) {
+    if (loader)                                            // consumed after the first G wait: the atomic's latency is hidden
+      my_next = p.counter ? (int)gridDim.x + atomicAdd(p.counter, 1) : it + (int)gridDim.x;
+    int db, h; p.dH.divmod(it, db, h);
+    const int dir = p.dB.div(db);
+    const float Dh = p.Dskip[dir * H + h];
+    float Sreg[32];                                        // thread = state row n, 32 of the 64 columns
+#pragma unroll
+    for (int j = 0; j < 32; ++j) Sreg[j] = 0.f;
+    for (int i = tid; i < HALF / 16; i += F2_THREADS) reinterpret_cast<uint4*>(sS)[i] = make_uint4(0, 0, 0, 0);
+
+    for (int c = 0; c < nc; ++c, ++seq) {
+      const int buf = seq & 1;
+      const uint32_t par = seq & 1;
+      const float* tab = tabs + buf * TAB_FLOATS;
+      const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
+      const int q0 = c * TQ, qv = min(TQ, L - q0);
+      const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;
+      const bool last_chunk = c == nc - 1;
+      const long long row0 = (long long)db * L + q0;
+      int nit = it, ncn = c + 1;                                       // the step after this one (loader only)
+      if (ncn == nc) { nit = my_next; ncn = 0; }
+      {   // state entering this chunk, kept for the backward
+        __nv_bfloat16* sg = p.states + ((((long long)db * H + h) * nc + c) * TN + row) * TP + 32 * cg;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sg + 8 * k) = pack8(Sreg + 8 * k);
+      }
+      umma::mbar_wait(bar_load, par);
+      if (issuer) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {                               // G = C B^T
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + TM_G, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024), idesc_g, kb > 0);
+        }
+        umma::mma_commit(bar_g);
+      }
+      umma::mbar_wait(bar_g, par);
+      umma::tc_fence_after();
+      if (loader && c == 0) s_next[iseq & 1] = my_next;
+      // ---- epilogue 1: M[t,s] = G[t,s] e^{cs_t - cs_s} dt_s (s <= t) -> bf16 pairs in TMEM (A operand of Yd)
+      if ((row >> 5) < nblk) {                                         // padding rows only feed unused y rows
+        const int t = row, I = t >> 5;
+        const float cs_t = tab[t], e_ref = I > 0 ? __expf(cs_t - tab[32 * I - 1]) : 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {                               // two 32-column blocks per TMEM round trip
+          float g[2][16];
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            if (2 * kp + kk <= I) umma::tmem_ld16(t_lane + TM_G + (uint32_t)(32 * (2 * kp + kk) + 16 * cg), g[kk]);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = 2 * kp + kk, s0 = 32 * k + 16 * cg;
+            uint32_t pk[8];
+            if (k <= I) {
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                float l[8], d8[8];
+                decay8(l, t, I, k, s0 + 8 * hf, cs_t, e_ref, tab);
+                load8(d8, s_dt + s0 + 8 * hf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[kk][8 * hf + j] *= l[j] * d8[j];
+                const uint4 q = pack8(g[kk] + 8 * hf);
+                pk[4 * hf] = q.x; pk[4 * hf + 1] = q.y; pk[4 * hf + 2] = q.z; pk[4 * hf + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = 0u;
+            }
+            umma::tmem_st8(t_lane + TM_M + (uint32_t)(16 * k + 8 * cg), pk);
+          }
+        }
+        umma::tmem_st_wait();
+      }
+      umma::fence_async_smem();                                        // the state tile written through the generic proxy
+      umma::tc_fence_before();
+      __syncthreads();
+      if (issuer) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb)                                 // Yd = M X   (k = time: valid frames only)
+          if (kb < nkb)
+            umma::mma_bf16_ts(tmem + TM_YD, tmem + TM_M + 8 * kb,
+                              umma::make_smem_desc(umma::smem_u32(sX) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {                               // Yo = C S_in  (into the columns G has left)
+          const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+          umma::mma_bf16_ss(tmem + TM_YO, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                            umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), idesc_y, kb > 0);
+        }
+        umma::mma_commit(bar_y);
+      }
+      // x of this thread's row for the D x term: the lines TMA fetched a moment ago, still in L2
+      uint4 xg[4];
+      {
+        const uint4* xp = reinterpret_cast<const uint4*>(p.xconv + (row0 + row) * C + h * TP + 32 * cg);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xg[k] = row < qv ? __ldg(xp + k) : make_uint4(0, 0, 0, 0);
+      }
+      umma::mbar_wait(bar_y, par);
+      umma::tc_fence_after();
+      if (loader && nit < n_items) {
+        load_a(nit, ncn, buf ^ 1);
+        if (last_chunk) load_b(nit, ncn);                              // no dS step: B and X are free as well
+      }
+      // ---- epilogue 2: y = Yd + e^{cs_t} Yo + D x
+      if ((row >> 5) < nblk) {
+        const int t = row;
+        const float ecs = s_ecs[t];
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int c16 = 2 * cg + bb;
+          float yd[16], yo[16];
+          umma::tmem_ld16(t_lane + TM_YD + 16u * c16, yd);
+          umma::tmem_ld16(t_lane + TM_YO + 16u * c16, yo);
+          umma::tmem_ld_wait();
+          if (t < qv) {
+            __nv_bfloat16* yg = p.y + (row0 + t) * di + h * TP + 16 * c16;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              float x[8], o[8];
+              unpack8(xg[2 * bb + k], x);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = yd[8 * k + e] + ecs * yo[8 * k + e] + Dh * x[e];
+              *reinterpret_cast<uint4*>(yg + 8 * k) = pack8(o);
+            }
+          }
+        }
+      }
+      if (!last_chunk) {
+        // Xw = w_s X, in place (Yd has retired; the swizzle permutes 16-byte chunks inside a row only)
+        for (int i = tid; i < TQ * 8; i += F2_THREADS) {
+          const float w = s_w[i >> 3];
+          float v[8];
+          unpack8(reinterpret_cast<const uint4*>(sX)[i], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= w;
+          reinterpret_cast<uint4*>(sX)[i] = pack8(v);
+        }
+        umma::fence_async_smem();
+        umma::tc_fence_before();
+        __syncthreads();                                               // Xw visible; Yo read by every thread
+        if (issuer) {
+          umma::tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb)                               // dS = B^T (w o X)   (k = time: valid frames only)
+            if (kb < nkb)
+              umma::mma_bf16_ss(tmem + TM_DS, umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024),
+                                umma::make_smem_desc(umma::smem_u32(sX) + kb * 2048, 1024, 1024), idesc_s, kb > 0);
+          umma::mma_commit(bar_free);
+        }
+        umma::mbar_wait(bar_free, fseq & 1);
+        ++fseq;
+        umma::tc_fence_after();
+        if (loader && nit < n_items) load_b(nit, ncn);
+        // ---- epilogue 3: S = e^{cs_last} S + dS  (thread = state row n)
+        const float decay = s_ecs[TQ - 1];
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int c16 = 2 * cg + bb;
+          float ds[16];
+          umma::tmem_ld16(t_lane + TM_DS + 16u * c16, ds);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) Sreg[16 * bb + j] = decay * Sreg[16 * bb + j] + ds[j];
+          *reinterpret_cast<uint4*>(sS + swz(row, 2 * c16)) = pack8(Sreg + 16 * bb);
+          *reinterpret_cast<uint4*>(sS + swz(row, 2 * c16 + 1)) = pack8(Sreg + 16 * bb + 8);
+        }
+      }
+      umma::fence_async_smem();
+      umma::tc_fence_before();
+      __syncthreads();
+    }
+    it = s_next[iseq & 1];                                 // written at the start of this item, several barriers ago
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 // ===================================================================================================
@@ -1092,7 +1353,7 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   int rc = make_tmap_bf16(&tm, xconv, 3, dims, strides, box);
   if (rc) return rc;
   FwdParams p;
-  p.dt = dt; p.A_log = A_log; p.Dskip = Dskip;
+  p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.xconv = (const __nv_bfloat16*)xconv;
   p.y = (__nv_bfloat16*)y; p.states = (__nv_bfloat16*)states;
   p.ndirB = ndir * B; p.B = B; p.L = L; p.H = H; p.di = di; p.nc = cdiv(L, TQ);
   p.dH = FastDiv(H); p.dB = FastDiv(B); p.dnc = FastDiv(p.nc);
@@ -1100,11 +1361,23 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   float* tables = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.tables = tables;
   const int items = ndir * B * H;
-  ssd_tables_kernel<<<items * p.nc, TQ, 0, (cudaStream_t)stream>>>(dt, A_log, tables, B, L, H, p.nc);
+  int* counter = reinterpret_cast<int*>(tables + (size_t)items * p.nc * TAB_FLOATS);   // the workspace's spare 128 bytes
+  ssd_tables_kernel<<<items * p.nc, TQ, 0, (cudaStream_t)stream>>>(dt, A_log, tables, B, L, H, p.nc, counter);
+  static const bool dynamic = getenv("HNB_SSD_FWD_DYNAMIC") && atoi(getenv("HNB_SSD_FWD_DYNAMIC")) != 0;
+  p.counter = dynamic ? counter : nullptr;
   HNB_LAUNCH_CHECK("ssd_tables");
-  const int grid = items < sm_count() ? items : sm_count();
   p.dbg = nullptr;
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
+  static const int variant = getenv("HNB_SSD_FWD") ? atoi(getenv("HNB_SSD_FWD")) : 2;   // 1: the one-CTA-per-SM kernel
+  if (variant == 2 && !debug) {
+    static const int per_sm = getenv("HNB_SSD_FWD2_PER_SM") ? atoi(getenv("HNB_SSD_FWD2_PER_SM")) : 2;   // diagnosis
+    const int grid2 = items < per_sm * sm_count() ? items : per_sm * sm_count();
+    HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    ssd_fwd2_tc_kernel<<<grid2, F2_THREADS, F2_SMEM, (cudaStream_t)stream>>>(tm, p);
+    HNB_LAUNCH_CHECK("ssd_fwd2_tc");
+    return HNB_OK;
+  }
+  const int grid = items < sm_count() ? items : sm_count();
   if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, (cudaStream_t)stream); }
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
