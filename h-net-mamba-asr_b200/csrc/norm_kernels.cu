@@ -55,6 +55,63 @@ layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, 
   }
 }
 
+// Register-resident variant for the widths of this model (d <= 768, multiple of 4): each row is read from global
+// memory ONCE, two rows per warp with all their loads issued before the first reduction.  The generic kernel above
+// walks a row three times and keeps a single 1.5 KB row in flight per warp -- too little to cover a DRAM round trip.
+template <typename TX, typename TY, int NV>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+layernorm_fwd_reg_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         long long rows, int d, float eps, TY* __restrict__ y, float* __restrict__ mean_out,
+                         float* __restrict__ rstd_out) {
+  constexpr int VN = 4, R = 2;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  float xv[R][NV][VN];
+#pragma unroll
+  for (int u = 0; u < R; ++u)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) xv[u][k][i] = 0.f;
+      if (c < d && row0 + u < rows) ldv<TX, VN>(x + (row0 + u) * d + c, xv[u][k]);
+    }
+  const float inv_d = 1.f / d;
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    if (row0 + u >= rows) break;                                     // warp-uniform
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int i = 0; i < VN; ++i) s += xv[u][k][i];
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+      if (c < d) {
+#pragma unroll
+        for (int i = 0; i < VN; ++i) { const float t = xv[u][k][i] - mean; xv[u][k][i] = t; q = fmaf(t, t, q); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    if (lane == 0) { mean_out[row0 + u] = mean; rstd_out[row0 + u] = rstd; }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+      if (c < d) {
+        float g[VN], b[VN], o[VN];
+        ldv<float, VN>(gamma + c, g); ldv<float, VN>(beta + c, b);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) o[i] = fmaf(xv[u][k][i] * rstd, g[i], b[i]);
+        stv<TY, VN>(y + (row0 + u) * d + c, o);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward (+ residual gradient).  Persistent-style grid: each warp strides over rows and
 // keeps its dgamma/dbeta columns in registers; one shared-memory reduction + atomics per block.
@@ -317,7 +374,7 @@ struct PackSrc { const float* p[2][8]; };          // per direction: in_w, out_w
 
 template <typename TW>
 __global__ void __launch_bounds__(256)
-pack_mixer_kernel(const PackSrc src, int dir0, int ndir, int d, int di,
+pack_mixer_kernel(const PackSrc src, int dir0, int ndir, int d, int di, const FastDiv dd4, const FastDiv ddi4,
                   int N, int H, int dstride, TW* __restrict__ Win, TW* __restrict__ Wout, float* __restrict__ conv_w_o,
                   float* __restrict__ conv_b_o, float* __restrict__ dt_bias_o, float* __restrict__ A_log_o,
                   float* __restrict__ D_o, float* __restrict__ norm_w_o) {
@@ -327,36 +384,57 @@ pack_mixer_kernel(const PackSrc src, int dir0, int ndir, int d, int di,
   const float* __restrict__ dt_bias = src.p[blockIdx.y][4]; const float* __restrict__ A_log = src.p[blockIdx.y][5];
   const float* __restrict__ Dk = src.p[blockIdx.y][6]; const float* __restrict__ norm_w = src.p[blockIdx.y][7];
   const int dip = 2 * di + 2 * N + H, C = di + 2 * N;
-  const long long n_in = (long long)dstride * d / 4, n_out = (long long)d * di / 4;
-  const long long n_small = (long long)C * 4 + C + 3 * H + di;
-  const long long total = n_in + n_out + n_small;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    if (i < n_in) {                                          // d % 4 == 0 (checked on the host)
-      const long long e = i * 4;
-      const int r = (int)(e / d), c = (int)(e % d);
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (r < dip) ldv<float, 4>(in_w + (long long)r * d + c, v);
-      stv<TW, 4>(Win + ((long long)dir * dstride + r) * d + c, v);
-    } else if (i < n_in + n_out) {
-      const long long e = (i - n_in) * 4;
-      const int r = (int)(e / di), c = (int)(e % di);
-      float v[4];
-      ldv<float, 4>(out_w + (long long)r * di + c, v);
-      stv<TW, 4>(Wout + (long long)r * ndir * di + (long long)dir * di + c, v);
-    } else {
-      long long j = i - n_in - n_out;
-      if (j < (long long)C * 4) { conv_w_o[(long long)dir * C * 4 + j] = conv_w[j]; continue; }
-      j -= (long long)C * 4;
-      if (j < C) { conv_b_o[(long long)dir * C + j] = conv_b[j]; continue; }
-      j -= C;
-      if (j < H) { dt_bias_o[dir * H + j] = dt_bias[j]; continue; }
-      j -= H;
-      if (j < H) { A_log_o[dir * H + j] = A_log[j]; continue; }
-      j -= H;
-      if (j < H) { D_o[dir * H + j] = Dk[j]; continue; }
-      j -= H;
-      norm_w_o[(long long)dir * di + j] = norm_w[j];
+  // The two weight matrices are 99.9 % of the bytes: 32-bit index arithmetic (multiply-high division) and four
+  // independent 16-byte loads in flight per thread -- the first version spent its time in 64-bit divisions
+  // (0.6 TB/s on a pure copy-and-cast).
+  const int d4 = d >> 2, di4 = di >> 2;
+  const int n_in = dstride * d4, n_out = d * di4;                  // float4 units (checked < 2^31 on the host)
+  const int nthreads = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  TW* __restrict__ win_o = Win + (long long)dir * dstride * d;
+  for (int i0 = t0; i0 < n_in; i0 += 4 * nthreads) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthreads;
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (i < n_in && dd4.div(i) < dip) ldv<float, 4>(in_w + (long long)i * 4, v[u]);   // rows [dip, dstride) are padding
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < n_in) stv<TW, 4>(win_o + (long long)i * 4, v[u]);
+    }
+  }
+  for (int i0 = t0; i0 < n_out; i0 += 4 * nthreads) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < n_out) ldv<float, 4>(out_w + (long long)i * 4, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < n_out) {
+        int r, c4; ddi4.divmod(i, r, c4);
+        stv<TW, 4>(Wout + (long long)r * ndir * di + (long long)dir * di + c4 * 4, v[u]);
+      }
+    }
+  }
+  const int n_small = C * 5 + 3 * H + di;
+  for (int j0 = t0; j0 < n_small; j0 += nthreads) {
+    int j = j0;
+    if (j < C * 4) { conv_w_o[(long long)dir * C * 4 + j] = conv_w[j]; continue; }
+    j -= C * 4;
+    if (j < C) { conv_b_o[(long long)dir * C + j] = conv_b[j]; continue; }
+    j -= C;
+    if (j < H) { dt_bias_o[dir * H + j] = dt_bias[j]; continue; }
+    j -= H;
+    if (j < H) { A_log_o[dir * H + j] = A_log[j]; continue; }
+    j -= H;
+    if (j < H) { D_o[dir * H + j] = Dk[j]; continue; }
+    j -= H;
+    norm_w_o[(long long)dir * di + j] = norm_w[j];
   }
 }
 
@@ -375,7 +453,18 @@ extern "C" int hnb_layernorm_fwd(const void* x, int x_dtype, const float* gamma,
   const bool v4 = d % 4 == 0 && al(x, 4 * esz(x_dtype)) && al(y, 4 * esz(y_dtype)) && al(gamma, 16) && al(beta, 16);
 #define RUN(TX, TY, VN) layernorm_fwd_kernel<TX, TY, VN><<<grid, NORM_WARPS * 32, 0, st>>>( \
       (const TX*)x, gamma, beta, rows, d, eps, (TY*)y, mean, rstd)
-  HNB_DISPATCH_DTYPE(x_dtype, TX, HNB_DISPATCH_DTYPE(y_dtype, TY, { if (v4) RUN(TX, TY, 4); else RUN(TX, TY, 1); }));
+  const int nv = cdiv(d, 128);
+  if (v4 && nv <= 6) {
+    const int grid2 = cdiv(rows, NORM_WARPS * 2);
+#define RUNR(TX, TY, NV) layernorm_fwd_reg_kernel<TX, TY, NV><<<grid2, NORM_WARPS * 32, 0, st>>>( \
+      (const TX*)x, gamma, beta, rows, d, eps, (TY*)y, mean, rstd)
+    HNB_DISPATCH_DTYPE(x_dtype, TX, HNB_DISPATCH_DTYPE(y_dtype, TY, {
+      if (nv <= 1) RUNR(TX, TY, 1); else if (nv <= 2) RUNR(TX, TY, 2); else if (nv <= 3) RUNR(TX, TY, 3);
+      else if (nv <= 4) RUNR(TX, TY, 4); else RUNR(TX, TY, 6); }));
+#undef RUNR
+  } else {
+    HNB_DISPATCH_DTYPE(x_dtype, TX, HNB_DISPATCH_DTYPE(y_dtype, TY, { if (v4) RUN(TX, TY, 4); else RUN(TX, TY, 1); }));
+  }
 #undef RUN
   HNB_LAUNCH_CHECK("layernorm_fwd");
   return HNB_OK;
@@ -495,9 +584,11 @@ static int pack_launch(const PackSrc& src, int ndirs, int dir0, int ndir, int d,
                 "pack_mixer_params: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = ((long long)dstride * d + (long long)d * di) / 4 + (long long)(di + 2 * N) * 5 + 3 * H + di;
-  int gx = cdiv(total, 256);
+  HNB_CHECK_ARG((long long)dstride * d < (1LL << 31) && (long long)d * di < (1LL << 31), "pack_mixer_params: weights too large");
+  int gx = cdiv(total, 256 * 4);
   if (gx > 148 * 8 / ndirs) gx = 148 * 8 / ndirs;
-  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<dim3(gx, ndirs), 256, 0, st>>>(src, dir0, ndir, d, di, N, H,
+  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<dim3(gx, ndirs), 256, 0, st>>>(src, dir0, ndir, d, di,
+      FastDiv(d / 4), FastDiv(di / 4), N, H,
       dstride, (TW*)Win, (TW*)Wout, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o, norm_w_o)));
   HNB_LAUNCH_CHECK("pack_mixer_params");
   return HNB_OK;
