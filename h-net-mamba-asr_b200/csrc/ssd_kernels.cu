@@ -566,7 +566,7 @@ static int ssd_check(const char* who, int ndir, int B, int L, int di, int N, int
 }
 
 int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B, int L,
-                   int di, int N, int H, void* y, void* states, void* stream);
+                   int di, int N, int H, void* y, void* states, void* stream, int variant);
 int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
                    const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
                    void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, void* stream);
@@ -604,9 +604,9 @@ extern "C" int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const 
   int rc = ssd_check("ssd_fwd", ndir, B, L, di, N, H);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1) {
+  if (impl == 1 || impl == 2) {                       // 2: the one-CTA-per-SM forward kernel (same outputs, kept under test)
     HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_fwd: the tcgen05 path takes bf16 activations");
-    return hnb_ssd_fwd_tc(xconv, dt, A_log, Dskip, ndir, B, L, di, N, H, y, states, stream);
+    return hnb_ssd_fwd_tc(xconv, dt, A_log, Dskip, ndir, B, L, di, N, H, y, states, stream, impl == 2 ? 1 : 0);
   }
   if (dtype == HNB_BF16)
     return ssd_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)xconv, dt, A_log, Dskip, ndir, B, L, di, H,

@@ -1343,7 +1343,7 @@ long long hnb_ssd_tc_ws_bytes(int ndir, int B, int L, int H) {
 }
 
 int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B, int L,
-                   int di, int N, int H, void* y, void* states, void* stream) {
+                   int di, int N, int H, void* y, void* states, void* stream, int variant_req) {
   HNB_CHECK_ARG(N == TN && di == H * TP, "ssd_fwd(tcgen05): built for d_state=128, headdim=64");
   const int C = di + 2 * N;
   CUtensorMap tm;
@@ -1368,7 +1368,8 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   HNB_LAUNCH_CHECK("ssd_tables");
   p.dbg = nullptr;
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
-  static const int variant = getenv("HNB_SSD_FWD") ? atoi(getenv("HNB_SSD_FWD")) : 2;   // 1: the one-CTA-per-SM kernel
+  static const int variant_env = getenv("HNB_SSD_FWD") ? atoi(getenv("HNB_SSD_FWD")) : 2;   // 1: the one-CTA-per-SM kernel
+  const int variant = variant_req > 0 ? variant_req : variant_env;
   if (variant == 2 && !debug) {
     static const int per_sm = getenv("HNB_SSD_FWD2_PER_SM") ? atoi(getenv("HNB_SSD_FWD2_PER_SM")) : 2;   // diagnosis
     const int grid2 = items < per_sm * sm_count() ? items : per_sm * sm_count();
