@@ -544,7 +544,8 @@ static double gemm_cost(int tiles_m, int tiles_n, int kb_per, int sk, bool pair)
 }
 static bool gemm_use_pair(int M, int N, int BN, int kb_per, int sk) {
   static const int cl_env = getenv("HNB_GEMM_CLUSTER") ? atoi(getenv("HNB_GEMM_CLUSTER")) : 3;
-  if (!(cl_env == 3 && BN == 256 && cdiv(M, 128) >= 4 && kb_per >= 12)) return false;
+  static const int min_kb = getenv("HNB_GEMM_PAIR_MINKB") ? atoi(getenv("HNB_GEMM_PAIR_MINKB")) : 12;   // tuning knob
+  if (!(cl_env == 3 && BN == 256 && cdiv(M, 128) >= 4 && kb_per >= min_kb)) return false;
   const int tm = cdiv(M, 128), tn = cdiv(N, BN);
   return gemm_cost(tm, tn, kb_per, sk, true) <= gemm_cost(tm, tn, kb_per, sk, false);
 }

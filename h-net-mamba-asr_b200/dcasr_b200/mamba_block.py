@@ -102,7 +102,12 @@ def _mixer_forward(h2, lengths, B, L, ndir, di, N, H, params):
     return yn, Wout, saved, dstride
 
 
-def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, ln_acc_d=0):
+def _acc_sizes(ndir, C, di, H, ln_acc_d):
+    """fp32 accumulators of one block backward: conv_w, conv_b, norm_w, dA_log, dD, ddt_bias, LayerNorm (dgamma | dbeta)."""
+    return [ndir * C * 4, ndir * C, ndir * di, ndir * H, ndir * H, ndir * H, 2 * ln_acc_d]
+
+
+def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, ln_acc_d=0, arena=None):
     """dyn = d loss / d ynorm [B*L, ndir*di] -> (dh2, per-direction parameter grads except out_proj, LN accumulator)."""
     Win, zx, conv_w, conv_b, dt_bias, A_log, Dk, norm_w, xconv, dt, y, ws, yn, rstd, Wout = saved
     dip = 2 * di + 2 * N + H
@@ -112,8 +117,11 @@ def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, ln_a
         dzx.view(-1, ndir, dstride)[:, :, dip:] = 0                      # pad columns feed the GEMMs below
     # one zero-filled buffer for every accumulated parameter gradient of the block (one fill instead of ten)
     # (conv accumulators first: C % 4 == 0 keeps them 16-byte aligned for the kernel's vector reductions)
-    sizes = [ndir * C * 4, ndir * C, ndir * di, ndir * H, ndir * H, ndir * H, 2 * ln_acc_d]
-    accs = torch.zeros(sum(sizes), dtype=torch.float32, device=zx.device).split(sizes)
+    sizes = _acc_sizes(ndir, C, di, H, ln_acc_d)
+    d = h2.shape[1]
+    if arena is None:
+        arena = torch.zeros(ndir * dstride * d + sum(sizes), dtype=torch.float32, device=zx.device)
+    dWin_buf, *accs = arena[-(ndir * dstride * d + sum(sizes)):].split([ndir * dstride * d] + sizes)
     a_cw, a_cb, a_nw = accs[0].view(ndir, C, 4), accs[1].view(ndir, C), accs[2].view(ndir, di)
     a_dA, a_dD, a_dtb = accs[3].view(ndir, H), accs[4].view(ndir, H), accs[5].view(ndir, H)
     dy, dnorm_w = ops.gated_norm_bwd(dyn, y, zx, dstride, lengths, norm_w, rstd, ndir, B, L, di, dzx, acc=a_nw)
@@ -123,7 +131,8 @@ def _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, ln_a
                                               ndir, B, L, di, N, H, dzx, acc=(a_cw, a_cb, a_dtb))
     dh2 = ops.gemm(dzx, Win, trans_b=True)                               # dgrad [B*L, d]
     sk = ops.wgrad_splitk(B * L, Win.shape[0], Win.shape[1]) if dzx.dtype == torch.bfloat16 else 1
-    dWin = ops.gemm(dzx, h2, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)   # [ndir*dstride, d]
+    dWin = ops.gemm(dzx, h2, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32,
+                    out=dWin_buf.view(ndir * dstride, d))                # [ndir*dstride, d], pre-zeroed (split-K accumulates)
     grads = []
     for r in range(ndir):
         grads.append((dWin[r * dstride: r * dstride + dip], dconv_w[r].reshape(-1, 1, 4), dconv_b[r], ddt_bias[r],
@@ -172,9 +181,17 @@ class _MixerFn(torch.autograd.Function):
         dout2 = dout2 if dout2.is_contiguous() else dout2.contiguous()
         da = dout2 if dout2.dtype == adt else dout2.to(adt)
         dyn = ops.gemm(da, Wout, trans_b=True)                           # [B*L, ndir*di]
+        # ONE zero fill per block backward: the split-K weight gradients and every accumulated parameter gradient are
+        # views of this arena (three fills per block before).  out_proj's gradient stays ONE GEMM over both directions:
+        # a GEMM per direction (contiguous [d, di] blocks, no strided copy in AccumulateGrad) was measured 0.3 ms per
+        # step slower -- half-width weight-gradient GEMMs fill the SMs worse than the copies cost.
+        n_acc = sum(_acc_sizes(ndir, di + 2 * N, di, H, d if block else 0))
+        arena = torch.zeros(ndir * d * di + ndir * dstride * d + n_acc, dtype=torch.float32, device=da.device)
         sk = ops.wgrad_splitk(B * L, d, ndir * di) if adt == torch.bfloat16 else 1
-        dWout = ops.gemm(da, yn, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)   # [d, ndir*di]
-        dh2, grads, ln_acc = _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, d if block else 0)
+        dWout = ops.gemm(da, yn, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32,
+                         out=arena[:ndir * d * di].view(d, ndir * di))   # [d, ndir*di]
+        dh2, grads, ln_acc = _mixer_backward(dyn, h2, lengths, B, L, ndir, di, N, H, dstride, saved, d if block else 0,
+                                             arena=arena)
         if block:
             dres = dout2 if dout2.dtype == xdt else dout2.to(xdt)
             dx2, dg, db = ops.layernorm_bwd(dh2, x2, ln_w.float(), mean, rstd_ln, dres, acc=ln_acc)

@@ -38,13 +38,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
     if K != Kb:
         raise HnbError(f"gemm: inner dimensions differ ({K} vs {Kb})")
     L = lib()
+    if not (a.is_cuda and b.is_cuda):
+        raise HnbError("gemm: the hot path is CUDA-only")
+
+    def ptr(t):                        # row-strided views (column blocks of a wider matrix) go in by address + row stride
+        return t if t is None or t.is_contiguous() else t.data_ptr()
     if a.dtype == torch.float32:
         if b.dtype != torch.float32:
             raise HnbError("gemm: mixed operand dtypes")
         c = out if out is not None else _empty((M, N), torch.float32, a)
         r = residual
-        L.call("gemm_f32", a, a.stride(0), int(trans_a), b, b.stride(0), int(trans_b), M, N, K,
-               bias, r, r.stride(0) if r is not None else 0, c, c.stride(0), 0, stream())
+        L.call("gemm_f32", ptr(a), a.stride(0), int(trans_a), ptr(b), b.stride(0), int(trans_b), M, N, K,
+               bias, ptr(r), r.stride(0) if r is not None else 0, ptr(c), c.stride(0), 0, stream())
         return c
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
         raise HnbError(f"gemm: unsupported operand dtypes {a.dtype}, {b.dtype}")
@@ -57,8 +62,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
     r = residual
     if r is not None and r.dtype != od:
         raise HnbError("gemm: residual dtype must equal the output dtype")
-    L.call("gemm_bf16", a, a.stride(0), int(trans_a), b, b.stride(0), int(trans_b), M, N, K, bias,
-           r, r.stride(0) if r is not None else 0, c, c.stride(0), dtype_code(od), int(splitk), stream())
+    L.call("gemm_bf16", ptr(a), a.stride(0), int(trans_a), ptr(b), b.stride(0), int(trans_b), M, N, K, bias,
+           ptr(r), r.stride(0) if r is not None else 0, ptr(c), c.stride(0), dtype_code(od), int(splitk), stream())
     return c
 
 
