@@ -275,9 +275,19 @@ def run_ours(args):
     def step_resident():
         return fwd_bwd(feats_d, lens_d)
 
+    from dcasr_b200.distributed import HostBatchPrefetcher
+    pref = HostBatchPrefetcher(dev)
+    e2e_left = [0]                                  # steps still to run in the current e2e loop
+
     def step_e2e():
-        f = feats_pin.to(dev, non_blocking=True)
-        l = lens_pin.to(dev, non_blocking=True)
+        # every step copies its own batch from pinned host memory (exactly one H2D copy per step, all of them inside
+        # the timed region); the copy for step i+1 is started on a side stream before step i's kernels are launched
+        if pref.empty():
+            pref.push(feats_pin, lens_pin)
+        f, l = pref.pop()
+        e2e_left[0] -= 1
+        if e2e_left[0] > 0:
+            pref.push(feats_pin, lens_pin)
         return float(fwd_bwd(f, l))                 # .item(): device -> host read of the step's result
 
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
@@ -320,8 +330,10 @@ def run_ours(args):
     with ClockSampler(local) as cs:
         sec, wall, launches = timed(step_resident, args.steps)
     clocks = cs.summary()
+    e2e_left[0] = 2
     for _ in range(2):
         step_e2e()
+    e2e_left[0] = args.steps
     sec_e2e, _, _ = timed(step_e2e, args.steps)
 
     for _ in range(2):

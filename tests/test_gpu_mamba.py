@@ -178,7 +178,8 @@ def _ssd_inputs(ndir, B, L, H, seed=0):
 
 
 @pytest.mark.parametrize("impl", [1, 2], ids=["two_cta_tmem_operand", "one_cta"])
-@pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 1498, 16), (1, 5, 77, 4), (2, 40, 196, 16)])
+@pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 1498, 16), (1, 5, 77, 4), (2, 40, 196, 16),
+                                       (1, 2, 1, 2), (1, 3, 17, 2), (2, 2, 129, 4), (2, 1, 256, 1)])
 def test_ssd_tcgen05_forward_vs_exact(ndir, B, L, H, impl):
     """tcgen05/TMEM SSD forward (impl 1: two CTAs per SM, score tile as a TMEM operand; impl 2: one CTA per SM) against
     the fp32 CUDA-core path (impl 0) on identical bf16 inputs; the chunk states saved for the backward must agree too."""
@@ -197,7 +198,30 @@ def test_ssd_tcgen05_forward_vs_exact(ndir, B, L, H, impl):
         assert rel_err(s1, s2) < 1e-2 and rel_err(y1, y2) < 1e-2
 
 
-@pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 700, 16), (1, 5, 77, 4)])
+def test_ssd_tcgen05_kernels_repeatable():
+    """Five runs on the same inputs give bit-identical activations and activation gradients: an unsynchronised read
+    of a tile still in flight, or a TMEM column reused too early, shows up as run-to-run noise long before it breaks a
+    1e-2 tolerance.  (dA_log / dD are fp32 atomic sums over work items and are compared with a tolerance.)"""
+    from dcasr_b200 import ops
+    ndir, B, L, H = 2, 24, 398, 12
+    xconv, dt, A_log, Dk, di, N = _ssd_inputs(ndir, B, L, H, seed=3)
+    dy = (torch.randn(ndir, B * L, di, device=DEV) * 0.5).to(torch.bfloat16)
+    ref = None
+    for _ in range(5):
+        y, ws = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1)
+        dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, impl=1)
+        torch.cuda.synchronize()
+        cur = (y.clone(), dxc.clone(), dBC.clone(), ddt.clone(), dA.clone(), dD.clone())
+        if ref is None:
+            ref = cur
+            continue
+        for name, a, b in zip(("y", "dxc", "dBC", "ddt"), cur, ref):
+            assert torch.equal(a, b), f"{name} differs between runs"
+        assert rel_err(cur[4], ref[4]) < 1e-5 and rel_err(cur[5], ref[5]) < 1e-5
+
+
+@pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 700, 16), (1, 5, 77, 4), (2, 40, 196, 16),
+                                       (1, 3, 17, 2), (2, 2, 129, 4)])
 def test_ssd_tcgen05_backward_vs_exact(ndir, B, L, H):
     """tcgen05 SSD backward (3 kernels) against the fp32 CUDA-core backward on identical bf16 inputs."""
     from dcasr_b200 import ops
@@ -432,3 +456,21 @@ def test_subsample_conv1_kernels_fp32_reference():
     ref.backward(g.float())
     dw, db = ops.subsample_conv1_bwd(feats, out, g.contiguous(memory_format=torch.channels_last))
     assert rel_err(dw, w.grad) < 1e-4 and rel_err(db, b.grad) < 1e-4
+
+
+def test_host_batch_prefetcher_round_trip():
+    """Side-stream H2D staging used by bench.py's e2e leg: what pop() returns is what was pushed, and a second push
+    before the pop is refused."""
+    from dcasr_b200.distributed import HostBatchPrefetcher
+    pref = HostBatchPrefetcher(DEV)
+    a = torch.randn(40, 1598, 80).pin_memory()
+    b = torch.arange(40, dtype=torch.int64).pin_memory()
+    assert pref.empty()
+    pref.push(a, b)
+    with pytest.raises(RuntimeError):
+        pref.push(a, b)
+    da, db = pref.pop()
+    torch.cuda.synchronize()
+    assert pref.empty() and torch.equal(da.cpu(), a) and torch.equal(db.cpu(), b)
+    with pytest.raises(RuntimeError):
+        pref.pop()
