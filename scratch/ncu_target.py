@@ -13,10 +13,12 @@ with torch.no_grad():
 x = torch.randn(B, L, d, device=dev, requires_grad=True)
 lens = torch.full((B,), L, device=dev, dtype=torch.int32)
 for it in range(3):
+    if it == 2:
+        torch.cuda.synchronize(); torch.cuda.profiler.start()      # ncu --profile-from-start off: third iteration only
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y = blk(x, lens)
         co = ch.chunk(y.float())
         z = ch.dechunk(co.z.to(torch.bfloat16), co, residual=y.float())
     (z.float().pow(2).mean() + 0.03 * co.ratio_loss).backward()
-torch.cuda.synchronize()
+torch.cuda.synchronize(); torch.cuda.profiler.stop()
 print("ok", float(co.kept_fraction))

@@ -3,7 +3,7 @@ profiles/<out>.json: DRAM traffic and duration per C-ABI entry point (sums over 
 per step and per call.  bench.py reads it for the `traffic` field of its roofline object."""
 import csv, json, re, sys, collections
 src, out, steps = sys.argv[1], sys.argv[2], float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
-ENTRY = [("ssd_bwd", r"ssd_bwd_(dstate|dx|dbc)"), ("ssd_fwd", r"ssd_fwd_tc|ssd_tables"), ("gemm_bf16", r"gemm_bf16_kernel"),
+ENTRY = [("ssd_bwd", r"ssd_bwd_(dstate|dx|dbc)"), ("ssd_fwd", r"ssd_fwd2?_tc|ssd_tables"), ("gemm_bf16", r"gemm_bf16_(pair_)?kernel"),
          ("conv_bwd", r"conv_bwd_kernel"), ("conv_fwd", r"conv_fwd_kernel"), ("gated_norm_bwd", r"gated_norm_bwd"),
          ("gated_norm_fwd", r"gated_norm_fwd"), ("layernorm_bwd", r"layernorm_bwd"), ("layernorm_fwd", r"layernorm_fwd"),
          ("pack_mixer_params", r"pack_mixer"), ("subsample_conv1_fwd", r"sub_conv1_fwd"), ("subsample_conv1_bwd", r"sub_conv1_bwd")]
