@@ -474,3 +474,25 @@ def test_host_batch_prefetcher_round_trip():
     assert pref.empty() and torch.equal(da.cpu(), a) and torch.equal(db.cpu(), b)
     with pytest.raises(RuntimeError):
         pref.pop()
+
+
+def test_conv_bwd_adds_two_dbc_parts():
+    """hnb_conv_bwd with dB|dC given as two partial sums (the head groups of the tcgen05 dB/dC kernel) equals the call
+    with their sum, on a ragged batch (packed bf16 adds: one extra rounding of dB|dC, far below the 1e-2 bar)."""
+    from dcasr_b200 import ops
+    torch.manual_seed(5)
+    ndir, B, L, H, N = 2, 6, 200, 16, 128
+    di = 64 * H; C = di + 2 * N; dip = 2 * di + 2 * N + H; ds = (dip + 7) // 8 * 8; T = B * L
+    bf = lambda *s: (torch.randn(*s, device=DEV) * 0.5).to(torch.bfloat16)
+    zx, dxc, ddt = bf(T, ndir * ds), bf(ndir, T, di), torch.randn(ndir, T, H, device=DEV)
+    parts = bf(2, ndir, T, 2 * N)
+    cw, cb, dtb = torch.randn(ndir, C, 4, device=DEV), torch.randn(ndir, C, device=DEV), torch.randn(ndir, H, device=DEV)
+    lens = torch.tensor([200, 131, 7, 200, 64, 199], dtype=torch.int32, device=DEV)
+    summed = (parts[0].float() + parts[1].float()).to(torch.bfloat16)
+    dz1, dz2 = torch.zeros_like(zx), torch.zeros_like(zx)
+    g1 = ops.conv_bwd(zx, dxc, summed, ddt, ds, lens, cw, cb, dtb, ndir, B, L, di, N, H, dz1)
+    g2 = ops.conv_bwd(zx, dxc, parts, ddt, ds, lens, cw, cb, dtb, ndir, B, L, di, N, H, dz2)
+    torch.cuda.synchronize()
+    assert rel_err(dz2, dz1) < 2e-3
+    for a, b in zip(g2, g1):
+        assert rel_err(a, b) < 2e-3
