@@ -285,6 +285,11 @@ def run_ours(args):
     def step_e2e():
         # every step copies its own batch from pinned host memory (exactly one H2D copy per step, all of them inside
         # the timed region); the copy for step i+1 is started on a side stream before step i's kernels are launched
+        mode = int(os.environ.get("HNB_BENCH_E2E_MODE", "2"))     # diagnosis: 0 same-stream copy + blocking read, 1 prefetch + blocking read
+        if mode == 0:
+            f, l = feats_pin.to(dev, non_blocking=True), lens_pin.to(dev, non_blocking=True)
+            e2e_losses.append(float(fwd_bwd(f, l)))
+            return
         if pref.empty():
             pref.push(feats_pin, lens_pin)
         f, l = pref.pop()
@@ -292,6 +297,9 @@ def run_ours(args):
         if e2e_left[0] > 0:
             pref.push(feats_pin, lens_pin)
         loss = fwd_bwd(f, l)
+        if mode == 1:
+            e2e_losses.append(float(loss))
+            return
         # device -> host read of the step's result, every step: an asynchronous copy into pinned memory whose value
         # the host picks up one step later (the last one in e2e_finish, still inside the timed region), so the read
         # never drains the launch queue -- the reference's trainer keeps its loss on the device for the same reason

@@ -202,4 +202,21 @@ __device__ __forceinline__ int scan_to_nat(int dir, int s, int len) {
   return (dir == 1 && s < len) ? (len - 1 - s) : s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// host: per-launch driver queries cached (the host needs ~13 ms to enqueue one encoder step of ~650 launches, so a
+// few microseconds per launch in cudaFuncSetAttribute / occupancy queries are a measurable share of it)
+// ---------------------------------------------------------------------------------------------
+inline cudaError_t hnb_set_max_smem(const void* fn, int bytes) {
+  struct E { const void* fn; int dev; int bytes; };
+  static E tab[128];
+  static int n = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < n; ++i)
+    if (tab[i].fn == fn && tab[i].dev == dev && tab[i].bytes >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && n < 128) tab[n++] = E{fn, dev, bytes};
+  return e;
+}
+
 }  // namespace hnb

@@ -623,7 +623,7 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   cfg.attrs = attr; cfg.numAttrs = 1;
 #define LAUNCH(TA, TB, BN_, CL_)                                                                                     \
   do {                                                                                                               \
-    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_kernel<TA, TB, BN_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)gemm_bf16_kernel<TA, TB, BN_, CL_>, \
                                        GemmCfg<BN_>::SMEM));                                                         \
     cfg.dynamicSmemBytes = GemmCfg<BN_>::SMEM;                                                                       \
     HNB_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<TA, TB, BN_, CL_>, tmA, tmB, p));                         \
@@ -636,7 +636,7 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   } while (0)
 #define LAUNCH_PAIR(TA, TB)                                                                                          \
   do {                                                                                                               \
-    HNB_CUDA_CALL(cudaFuncSetAttribute(gemm_bf16_pair_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)gemm_bf16_pair_kernel<TA, TB>, \
                                        PAIR_SMEM));                                                                  \
     cfg.dynamicSmemBytes = PAIR_SMEM;                                                                                \
     HNB_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<TA, TB>, tmA, tmB, p));                              \

@@ -473,11 +473,22 @@ extern "C" int hnb_layernorm_fwd(const void* x, int x_dtype, const float* gamma,
 // grid-stride kernels: exactly one wave of resident CTAs (a partial second wave would cost a full one)
 template <typename K>
 static int norm_grid(K kernel, long long rows, size_t smem) {
-  int dev = 0, sms = 148, occ = 0;
+  // (device, kernel, smem) -> resident CTAs: the occupancy query is a driver call per launch otherwise
+  struct E { const void* fn; size_t smem; int dev, cap; };
+  static E tab[64];
+  static int n = 0;
+  int dev = 0, cap = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NORM_WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 2;
-  const int g = cdiv(rows, NORM_WARPS), cap = sms * occ;
+  for (int i = 0; i < n && !cap; ++i)
+    if (tab[i].fn == (const void*)kernel && tab[i].smem == smem && tab[i].dev == dev) cap = tab[i].cap;
+  if (!cap) {
+    int sms = 148, occ = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NORM_WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 2;
+    cap = sms * occ;
+    if (n < 64) tab[n++] = E{(const void*)kernel, smem, dev, cap};
+  }
+  const int g = cdiv(rows, NORM_WARPS);
   return g < cap ? g : cap;
 }
 

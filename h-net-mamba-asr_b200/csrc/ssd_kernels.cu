@@ -584,8 +584,8 @@ static int ssd_fwd_impl(const T* xconv, const float* dt, const float* A_log, con
   float* decay = ws + ssd_states_floats(ndir, B, L, H);
   const size_t sm1 = (SQ * SN + SQ * SP + 2 * SQ) * sizeof(float);
   const size_t sm3 = (SQ * SN + SN * PADQ + SQ * SQ + SQ * SP + SN * SP + 2 * SQ) * sizeof(float);
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_chunk_state_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_chunk_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_chunk_state_kernel<T, 0>, (int)sm1));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_chunk_scan_kernel<T>, (int)sm3));
   dim3 grid(nc, ndir * B);
   ssd_chunk_state_kernel<T, 0><<<grid, ST, sm1, st>>>(xconv, C, xconv, C, di, dt, A_log, ndir, B, L, H, nc, states, decay);
   HNB_LAUNCH_CHECK("ssd_chunk_state");
@@ -628,8 +628,8 @@ static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt
   float* gstates = ws2;
   const size_t sm1 = (SQ * SN + SQ * SP + 2 * SQ) * sizeof(float);
   const size_t smb = (2 * SQ * SN + SN * PADQ + SQ * SQ + SQ * SP + 2 * SQ * SQ + 4 * SQ + 32) * sizeof(float);
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_chunk_state_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_chunk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_chunk_state_kernel<T, 1>, (int)sm1));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_chunk_kernel<T>, (int)smb));
   dim3 grid(nc, ndir * B);
   ssd_chunk_state_kernel<T, 1><<<grid, ST, sm1, st>>>(dy, di, xconv, C, di, dt, A_log, ndir, B, L, H, nc, gstates, nullptr);
   HNB_LAUNCH_CHECK("ssd_bwd_dstate");

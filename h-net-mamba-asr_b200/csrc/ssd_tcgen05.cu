@@ -1373,15 +1373,15 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   if (variant == 2 && !debug) {
     static const int per_sm = getenv("HNB_SSD_FWD2_PER_SM") ? atoi(getenv("HNB_SSD_FWD2_PER_SM")) : 2;   // diagnosis
     const int grid2 = items < per_sm * sm_count() ? items : per_sm * sm_count();
-    HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_fwd2_tc_kernel, F2_SMEM));
     ssd_fwd2_tc_kernel<<<grid2, F2_THREADS, F2_SMEM, (cudaStream_t)stream>>>(tm, p);
     HNB_LAUNCH_CHECK("ssd_fwd2_tc");
     return HNB_OK;
   }
   const int grid = items < sm_count() ? items : sm_count();
   if (debug) { cudaMalloc(&p.dbg, 64); cudaMemsetAsync(p.dbg, 0, 64, (cudaStream_t)stream); }
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_fwd_tc_kernel<FWD_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_fwd_tc_kernel<FWD_THREADS, false>, FWD_SMEM));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_fwd_tc_kernel<FWD_THREADS, true>, FWD_SMEM));
   if (debug) ssd_fwd_tc_kernel<FWD_THREADS, true><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
   else ssd_fwd_tc_kernel<FWD_THREADS, false><<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tm, p);
   HNB_LAUNCH_CHECK("ssd_fwd_tc");
@@ -1478,11 +1478,11 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
   if (debug) { cudaMalloc(&p.dbg, 128); cudaMemsetAsync(p.dbg, 0, 128, st); }
   const int sms = sm_count();
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dstate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D1_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel<BWD_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel<BWD_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dx_tc_kernel<BWD_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM));
-  HNB_CUDA_CALL(cudaFuncSetAttribute(ssd_bwd_dbc_tc_kernel<BWD_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dstate_tc_kernel, D1_SMEM));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dx_tc_kernel<BWD_THREADS, false>, D2_SMEM));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dbc_tc_kernel<BWD_THREADS, false>, D3_SMEM));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dx_tc_kernel<BWD_THREADS, true>, D2_SMEM));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dbc_tc_kernel<BWD_THREADS, true>, D3_SMEM));
   int items = ndir * B * H;
   ssd_bwd_dstate_tc_kernel<<<items < 2 * sms ? items : 2 * sms, D1_THREADS, D1_SMEM, st>>>(tmX, tmDY, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dstate_tc");

@@ -245,7 +245,7 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const
   size_t smem = 3 * (size_t)F * sizeof(float);
   const size_t red = (size_t)(PX > 1 ? PX - 1 : 0) * CG * 40 * sizeof(float);
   if (red > smem) smem = red;
-  HNB_CUDA_CALL(cudaFuncSetAttribute(sub_conv1_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4>, (int)smem));
   sub_conv1_bwd_kernel<4><<<blocks, CG * PX, smem, (cudaStream_t)stream>>>(feats, (const __nv_bfloat16*)a1,
       (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
   HNB_LAUNCH_CHECK("subsample_conv1_bwd");

@@ -79,8 +79,9 @@ class _Lib:
     def call(self, name: str, *args) -> None:
         """Call int hnb_<name>(...) with tensors turned into device pointers; raise on non-zero status."""
         conv = []
+        T = torch.Tensor
         for a in args:
-            if isinstance(a, torch.Tensor):
+            if type(a) is T or isinstance(a, T):                  # (exact-type test first: it is the common case)
                 if not a.is_cuda:
                     raise HnbError(f"hnb_{name}: got a {a.device} tensor; the hot path is CUDA-only")
                 if not a.is_contiguous():
@@ -126,7 +127,15 @@ def lib() -> _Lib:
     return _LIB
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream() -> int:
+    """cudaStream_t of torch's current stream on the current device.  The raw getter is one C call; building a
+    torch.cuda.Stream object per kernel launch (device-index lookups, availability checks) cost 15 us of host time
+    per launch, 5 ms of the 15 ms the host needs to enqueue one encoder step."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
