@@ -11,14 +11,20 @@ One ``MambaBlock`` call is ONE autograd node:
 """
 from __future__ import annotations
 
+import ctypes
 import math
+import os
 
 import torch
 import torch.nn as nn
 
-from . import ops
-from ._lib import HnbError
+from . import _lib, ops
+from ._lib import HnbError, dtype_code, lib, stream
 from .hnet_chunk import _autocast_dtype
+
+# MambaBlock through the library's one-call-per-block composites (hnb_block_fwd / hnb_block_bwd).  "0" keeps the
+# per-kernel Python orchestration (_MixerFn), which is also what a profiled step uses: bench.py times every entry point.
+BLOCK_COMPOSITE = os.environ.get("HNB_BLOCK_COMPOSITE", "1") != "0"
 
 
 def _round_up(v: int, m: int) -> int:
@@ -204,6 +210,77 @@ class _MixerFn(torch.autograd.Function):
         return (dx2.view(B, L, d), None, dg, db, None, None, None, None, None, *pg)
 
 
+class _BlockFn(torch.autograd.Function):
+    """One MambaBlock = ONE host call forward and ONE backward (hnb_block_fwd / hnb_block_bwd): same kernels as
+    _MixerFn, sequenced inside the library in one workspace.  Host time per encoder step drops from ~13 ms to a few ms,
+    which is what keeps eight ranks sharing one host from becoming launch-bound."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, ln_w, ln_b, ndir, di, N, H, *params):
+        B, L, d = x.shape
+        adt = _autocast_dtype() or x.dtype
+        x2 = x.reshape(B * L, d)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        if not x2.is_cuda:
+            raise HnbError(f"MambaBlock: got a {x2.device} tensor; the hot path is CUDA-only")
+        if lengths is not None:
+            lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+        ps = [p_.detach() if p_.is_contiguous() else p_.detach().contiguous() for p_ in params]
+        for t in ps:
+            if t.dtype != torch.float32 or t.device != x2.device:
+                raise HnbError("mixer parameters must be fp32 masters on the input's device")
+        ptrs = (ctypes.c_void_p * len(ps))(*[t.data_ptr() for t in ps])
+        L_ = lib()
+        act, xdt, impl = dtype_code(adt), dtype_code(x2.dtype), ops.ssd_impl_for(adt)
+        ws = torch.empty(L_.raw("block_fwd_ws_bytes")(B, L, d, ndir, di, N, H, act), dtype=torch.uint8, device=x2.device)
+        out2 = torch.empty_like(x2)
+        ln_w32, ln_b32 = ln_w.detach().float().contiguous(), ln_b.detach().float().contiguous()
+        L_.call("block_fwd", x2, xdt, lengths, ln_w32, ln_b32, ctypes.addressof(ptrs), B, L, d, ndir, di, N, H, act, impl,
+                out2, ws, stream())
+        ctx.save_for_backward(x2, lengths, ln_w32, ws)
+        ctx.meta = (B, L, d, ndir, di, N, H, act, xdt, impl, x.dtype, [p_.dtype for p_ in params], ln_w.dtype)
+        return out2.view(B, L, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, lengths, ln_w32, ws = ctx.saved_tensors
+        B, L, d, ndir, di, N, H, act, xdt, impl, x_dtype, pdts, ln_dtype = ctx.meta
+        dout2 = dout.reshape(B * L, d)
+        dout2 = dout2 if dout2.is_contiguous() else dout2.contiguous()
+        dout2 = dout2 if dout2.dtype == x2.dtype else dout2.to(x2.dtype)
+        L_ = lib()
+        offs = (ctypes.c_longlong * 9)()
+        n = L_.raw("block_grad_floats")(B, L, d, ndir, di, N, H, ctypes.addressof(offs))
+        # ONE zero fill: the split-K weight gradients and every accumulated parameter gradient are views of this arena
+        arena = torch.zeros(n, dtype=torch.float32, device=x2.device)
+        scratch = torch.empty(L_.raw("block_bwd_ws_bytes")(B, L, d, ndir, di, N, H, act, impl), dtype=torch.uint8,
+                              device=x2.device)
+        dx2 = torch.empty_like(x2)
+        L_.call("block_bwd", dout2, x2, xdt, lengths, ln_w32, ws, B, L, d, ndir, di, N, H, act, impl, dx2, arena, scratch,
+                stream())
+        C, dip = di + 2 * N, 2 * di + 2 * N + H
+        dstride = _round_up(dip, 8)
+        o = list(offs)
+        dWout = arena[o[0]:o[0] + d * ndir * di].view(d, ndir * di)
+        dWin = arena[o[1]:o[1] + ndir * dstride * d].view(ndir * dstride, d)
+        cw = arena[o[2]:o[2] + ndir * C * 4].view(ndir, C, 1, 4)
+        cb = arena[o[3]:o[3] + ndir * C].view(ndir, C)
+        nw = arena[o[4]:o[4] + ndir * di].view(ndir, di)
+        dA = arena[o[5]:o[5] + ndir * H].view(ndir, H)
+        dD = arena[o[6]:o[6] + ndir * H].view(ndir, H)
+        dtb = arena[o[7]:o[7] + ndir * H].view(ndir, H)
+        ln = arena[o[8]:o[8] + 2 * d].view(2, d)
+        pg = []
+        for r in range(ndir):                    # _params() order: in_proj.w, conv1d.w, conv1d.b, dt_bias, A_log, D, norm.w, out_proj.w
+            g = (dWin[r * dstride: r * dstride + dip], cw[r], cb[r], dtb[r], dA[r], dD[r], nw[r],
+                 dWout[:, r * di:(r + 1) * di])
+            pg += [t if t.dtype == pdts[r * NP + i] else t.to(pdts[r * NP + i]) for i, t in enumerate(g)]
+        dg, db = ln[0], ln[1]
+        if ln_dtype != torch.float32:
+            dg, db = dg.to(ln_dtype), db.to(ln_dtype)
+        return (dx2.view(B, L, d), None, dg, db, None, None, None, None, *pg)
+
+
 class MambaBlock(nn.Module):
     """y = x + Mamba2_fwd(norm(x)) [+ reverse(Mamba2_bwd(reverse(norm(x))))]  (mamba_block.py:31-56)."""
 
@@ -222,6 +299,9 @@ class MambaBlock(nn.Module):
         m = self.fwd
         params = m._params() + (self.bwd._params() if self.bwd is not None else ())
         ndir = 2 if self.bwd is not None else 1
+        if BLOCK_COMPOSITE and _lib._PROFILE is None:
+            return _BlockFn.apply(x, lengths if ndir == 2 else None, self.norm.weight, self.norm.bias, ndir,
+                                  m.d_inner, m.d_state, m.nheads, *params)
         return _MixerFn.apply(x, lengths if ndir == 2 else None, self.norm.weight, self.norm.bias, ndir,
                               m.d_inner, m.d_state, m.nheads, True, *params)
 

@@ -195,6 +195,30 @@ int hnb_pack_mixer_params2(const float* in_w0, const float* out_w0, const float*
                            float* conv_w_o, float* conv_b_o, float* dt_bias_o, float* A_log_o, float* D_o,
                            float* norm_w_o, void* stream);
 
+/* ---- one Mamba block per host call ----------------------------------------------------------
+ * MambaBlock.forward / its backward (src/dcasr/models/mamba_block.py:50-56) as ONE call each: the composites run the
+ * entry points above back to back on `stream` inside one workspace whose layout the library owns.  Same arithmetic,
+ * same kernels; what they save is host time (a block was ~20 Python -> C round trips and a dozen allocations).
+ *   x [B*L, d] (x_dtype: the residual stream, fp32 or bf16), ln_w / ln_b [d] float, lengths [B] int32 or NULL,
+ *   params: HOST array of 8*ndir device pointers (fp32 masters), per direction in mamba_ssm order
+ *           in_proj.w, conv1d.w, conv1d.b, dt_bias, A_log, D, norm.w, out_proj.w
+ *   act_dtype: dtype of the activations / GEMM operands (bf16 under autocast); ssd_impl as in hnb_ssd_fwd
+ *   out [B*L, d] (x_dtype) = x + mixers(LayerNorm(x));  ws: hnb_block_fwd_ws_bytes() bytes, kept for the backward. */
+long long hnb_block_fwd_ws_bytes(int B, int L, int d, int ndir, int di, int N, int H, int act_dtype);
+int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths, const float* ln_w, const float* ln_b,
+                  const void* const* params, int B, int L, int d, int ndir, int di, int N, int H,
+                  int act_dtype, int ssd_impl, void* out, void* ws, void* stream);
+/* backward: dout [B*L, d] (x_dtype) -> dx [B*L, d] (x_dtype) and the parameter gradients, ACCUMULATED into the fp32
+ * arena `grads` of hnb_block_grad_floats() floats that the caller zero-fills.  offsets[9] (in floats) of that arena:
+ * dWout [d, ndir*di] | dWin [ndir*dstride, d] (direction r = rows [r*dstride, +2di+2N+H)) | dconv_w [ndir,C,4] |
+ * dconv_b [ndir,C] | dnorm_w [ndir,di] | dA_log | dD | ddt_bias [ndir,H] | LayerNorm dgamma, dbeta [2,d].
+ * scratch: hnb_block_bwd_ws_bytes() bytes, dead when the call returns. */
+long long hnb_block_bwd_ws_bytes(int B, int L, int d, int ndir, int di, int N, int H, int act_dtype, int ssd_impl);
+long long hnb_block_grad_floats(int B, int L, int d, int ndir, int di, int N, int H, long long* offsets);
+int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const int32_t* lengths, const float* ln_w,
+                  const void* ws, int B, int L, int d, int ndir, int di, int N, int H, int act_dtype,
+                  int ssd_impl, void* dx, float* grads, void* scratch, void* stream);
+
 /* ---- dense projections (in_proj / out_proj / router W_q,W_k / proj_in,out) ---------------- */
 /* C[M,N] = op(A) op(B) (+ bias[N]) (+ R[M,N]) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
  *   transA = 0: A is [M,K] row-major (lda >= K);  1: A is [K,M] row-major (lda >= M)
