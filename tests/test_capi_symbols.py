@@ -49,3 +49,23 @@ def test_calls_fail_loudly_without_a_gpu():
         ch.chunk(torch.randn(1, 8, 16))
     with pytest.raises(Exception):
         d.MambaBlock(64)(torch.randn(1, 8, 64))
+
+
+def test_block_composite_layout_queries():
+    """Size / layout queries of the one-call-per-block composites are pure host arithmetic (no GPU needed): workspaces
+    are non-empty and grow with the batch, the gradient arena's offsets are increasing and 16-byte aligned."""
+    import ctypes
+    from dcasr_b200._lib import lib
+    L_ = lib()
+    B, L, d, ndir, di, N, H = 4, 398, 384, 2, 768, 128, 12
+    f1 = L_.raw("block_fwd_ws_bytes")(B, L, d, ndir, di, N, H, 1)
+    f2 = L_.raw("block_fwd_ws_bytes")(2 * B, L, d, ndir, di, N, H, 1)
+    b1 = L_.raw("block_bwd_ws_bytes")(B, L, d, ndir, di, N, H, 1, 1)
+    assert 0 < f1 < f2 and b1 > 0 and f1 % 256 == 0
+    offs = (ctypes.c_longlong * 9)()
+    n = L_.raw("block_grad_floats")(B, L, d, ndir, di, N, H, ctypes.addressof(offs))
+    o = list(offs)
+    dstride = (2 * di + 2 * N + H + 7) // 8 * 8
+    assert o[0] == 0 and o[1] == d * ndir * di and o[2] == o[1] + ndir * dstride * d
+    assert all(a < b for a, b in zip(o, o[1:])) and all(v % 4 == 0 for v in o[:3])
+    assert n == o[8] + 2 * d

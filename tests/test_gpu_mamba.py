@@ -496,3 +496,40 @@ def test_conv_bwd_adds_two_dbc_parts():
     assert rel_err(dz2, dz1) < 2e-3
     for a, b in zip(g2, g1):
         assert rel_err(a, b) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_block_composite_equals_per_kernel_path(dtype):
+    """hnb_block_fwd / hnb_block_bwd (one host call per block) run the same kernels as the per-kernel orchestration:
+    outputs, input gradients and every parameter gradient agree (bit-identical up to the order of fp32 atomic sums)."""
+    import dcasr_b200 as dd
+    from dcasr_b200 import mamba_block as mb
+    torch.manual_seed(11)
+    d, B, L = 256, 5, 300
+    blk = dd.MambaBlock(d).to(DEV)
+    x = torch.randn(B, L, d, device=DEV)
+    lens = torch.tensor([300, 211, 7, 300, 128], device=DEV)
+    w = torch.randn(B, L, d, device=DEV)
+    res = []
+    for composite in (True, False):
+        old = mb.BLOCK_COMPOSITE
+        mb.BLOCK_COMPOSITE = composite
+        try:
+            for p in blk.parameters():
+                p.grad = None
+            xg = x.clone().requires_grad_(True)
+            if dtype == torch.bfloat16:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    y = blk(xg, lens)
+            else:
+                y = blk(xg, lens)
+            (y.float() * w).sum().backward()
+            torch.cuda.synchronize()
+            res.append((y.detach().clone(), xg.grad.clone(), {k: p.grad.clone() for k, p in blk.named_parameters()}))
+        finally:
+            mb.BLOCK_COMPOSITE = old
+    (y1, g1, p1), (y0, g0, p0) = res
+    assert torch.equal(y1, y0)
+    assert rel_err(g1, g0) < 1e-5
+    for k in p0:
+        assert rel_err(p1[k], p0[k]) < 1e-4, k
