@@ -16,10 +16,11 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .fixed_pool import FixedPoolChunker
 from .hnet_chunk import DynamicChunker, _autocast_dtype
 from .mamba_block import MambaStack
 
-_CHUNKERS = {"dynamic": DynamicChunker}
+_CHUNKERS = {"dynamic": DynamicChunker, "fixed": FixedPoolChunker}
 
 
 def register_chunker(name: str, cls) -> None:
@@ -209,8 +210,8 @@ class DCASREncoder(nn.Module):
 
     @staticmethod
     def _dechunk_add(chunker, z, co, resid):
-        if isinstance(chunker, DynamicChunker):
-            return chunker.dechunk(z, co, residual=resid)        # fused gather + STE + residual
+        if isinstance(chunker, (DynamicChunker, FixedPoolChunker)):
+            return chunker.dechunk(z, co, residual=resid)        # fused gather (+ STE) + residual
         return resid + chunker.dechunk(z, co)
 
     def _forward_A(self, x_enc, mask, lengths, l32) -> EncoderOutput:

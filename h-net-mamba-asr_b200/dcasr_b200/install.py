@@ -30,9 +30,11 @@ def install(patch_dcasr: bool = True) -> None:
     for name in ("ChunkOutput", "RoutingModule", "DynamicChunker", "ratio_loss"):
         setattr(ref_chunk, name, getattr(hnet_chunk, name))
         setattr(ref_models, name, getattr(hnet_chunk, name))
-    try:
-        from dcasr.models.fixed_pool import FixedPoolChunker
-        encoder.register_chunker("fixed", FixedPoolChunker)    # the reference's own pure-torch control
+    try:                                                        # `chunker: fixed` resolves to the CUDA FixedPoolChunker too
+        import dcasr.models.fixed_pool as ref_fp
+        from . import fixed_pool
+        ref_fp.FixedPoolChunker = fixed_pool.FixedPoolChunker
+        ref_models.FixedPoolChunker = fixed_pool.FixedPoolChunker
     except Exception:
         pass
     import dcasr.models.mamba_block as ref_mb

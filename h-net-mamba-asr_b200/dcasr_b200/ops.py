@@ -333,3 +333,25 @@ def bias_relu_bwd(dout2d, out2d):
     lib().call("bias_relu_bwd", dout2d, out2d, dpre, db, rows, C, stream())
     return dpre, db
 
+
+
+# ------------------------------------------------------------------------------------------------
+# FixedPoolChunker
+# ------------------------------------------------------------------------------------------------
+def window_reduce(x, mask_u8, M, stride, normalize, z_dtype, want_cnt=True):
+    """x [B,L,D] -> z [B,M,D] (sum or masked mean over fixed windows), cnt [B,M] float (valid frames per window)."""
+    B, L, D = x.shape
+    z = _empty((B, M, D), z_dtype, x)
+    cnt = _empty((B, M), torch.float32, x) if want_cnt else None
+    lib().call("window_reduce", x, dtype_code(x.dtype), mask_u8, B, L, D, M, int(stride), int(bool(normalize)), z,
+               dtype_code(z_dtype), cnt, stream())
+    return z, cnt
+
+
+def window_broadcast(z, mask_u8, cnt, resid, L, stride, out_dtype):
+    """z [B,M,D] -> out [B,L,D]: out[b,t] = m[b,t] / max(cnt[b,w],1) * z[b,w(t)] (+ resid), w(t) = min(t//stride, M-1)."""
+    B, M, D = z.shape
+    out = _empty((B, L, D), out_dtype, z)
+    lib().call("window_broadcast", z, dtype_code(z.dtype), mask_u8, cnt, resid, B, L, D, M, int(stride), out,
+               dtype_code(out_dtype), stream())
+    return out

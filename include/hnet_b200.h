@@ -108,6 +108,18 @@ int hnb_upsample_bwd(const void* dy, int y_dtype, const void* zbar, int z_dtype,
 int hnb_masked_sums(const void* p, const void* b, int pb_dtype, const uint8_t* mask, long long n,
                     float* partial, void* stream);
 
+/* ---- FixedPoolChunker (src/dcasr/models/fixed_pool.py:54-106): the fixed-stride control of the learned chunker ----
+ * Window of frame t: w(t) = min(t / stride, M-1) (the reference clamps a padded tail into the last window, :80-83).
+ * reduce: z[b,j] = sum over the frames of window j of m[b,t] x[b,t], divided by max(cnt[b,j],1) when `normalize`
+ *   (chunk(): masked mean, :84-89; normalize = 0 and mask = NULL give the backward of dechunk()).
+ *   mask [B,L] uint8 or NULL (all frames); cnt [B,M] float (valid frames per window) or NULL. */
+int hnb_window_reduce(const void* x, int x_dtype, const uint8_t* mask, int B, int L, int D, int M, int stride,
+                      int normalize, void* z, int z_dtype, float* cnt, void* stream);
+/* broadcast: out[b,t] = m[b,t] / max(cnt[b,w],1) * z[b, w(t)] (+ resid[b,t])
+ *   (dechunk(): gather, :96-104, with mask = cnt = NULL; with both it is the backward of the masked mean). */
+int hnb_window_broadcast(const void* z, int z_dtype, const uint8_t* mask, const float* cnt, const void* resid,
+                         int B, int L, int D, int M, int stride, void* out, int out_dtype, void* stream);
+
 /* ---- Mamba-2 block ----------------------------------------------------------------------- */
 
 /* nn.LayerNorm (src/dcasr/models/mamba_block.py:51,73). mean/rstd [rows] float are saved for backward. */

@@ -174,3 +174,50 @@ def test_full_size_properties(B, L, D, N):
         zb[:, t] = prev
     ref = torch.gather(zb, 1, co.membership[..., None].expand(B, L, D))
     assert rel_err(y, ref) < 1e-5
+
+
+FIXED = sorted(p for p in glob.glob(os.path.join(GOLDEN, "fixed_*.npz")) if "identity" not in p)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("path", FIXED, ids=[os.path.basename(p)[:-4] for p in FIXED])
+def test_fixed_pool_matches_reference_golden(path, dtype):
+    """CUDA FixedPoolChunker (hnb_window_reduce / hnb_window_broadcast) against the reference's own outputs and
+    autograd gradients: integer / boolean fields bit-exact, values 1e-6 in fp32 and bf16 rounding in bf16."""
+    import dcasr_b200 as dd
+    g = np.load(path)
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    x = torch.from_numpy(g["x"]).to(DEV, dtype).requires_grad_(True)
+    z_proc = torch.from_numpy(g["z_proc"]).to(DEV, dtype).requires_grad_(True)
+    mask = torch.from_numpy(g["mask"]).to(DEV) if "mask" in g else None
+    ch = dd.FixedPoolChunker(x.shape[-1], N=int(g["N"]))
+    co = ch.chunk(x, mask)
+    assert torch.equal(co.membership.cpu(), torch.from_numpy(g["membership"])) and co.membership.dtype == torch.int64
+    assert torch.equal(co.z_mask.cpu(), torch.from_numpy(g["z_mask"])) and co.z_mask.dtype == torch.bool
+    assert torch.equal(co.b.float().cpu(), torch.from_numpy(g["b"])) and torch.equal(co.p, co.b)
+    assert rel_err(co.z.float().cpu(), torch.from_numpy(g["z"])) < max(tol, 2e-7)
+    assert abs(float(co.kept_fraction) - float(g["kept_fraction"])) < 1e-6 and float(co.ratio_loss) == 0.0
+    out = ch.dechunk(z_proc, co)
+    assert torch.equal(out.float().cpu(), torch.from_numpy(g["z_proc"]).to(dtype).float()[
+        torch.arange(out.shape[0])[:, None], torch.from_numpy(g["membership"])])       # a pure gather: bit exact
+    w, v = torch.from_numpy(g["w"]).to(DEV), torch.from_numpy(g["v"]).to(DEV)
+    ((out.float() * w).sum() + (co.z.float() * v).sum()).backward()
+    assert rel_err(x.grad.float().cpu(), torch.from_numpy(g["dx"])) < max(tol, 1e-6)
+    assert rel_err(z_proc.grad.float().cpu(), torch.from_numpy(g["dz_proc"])) < max(tol, 1e-6)
+    # the encoder's fused form: residual added in the same pass
+    r = torch.randn_like(out)
+    assert rel_err(ch.dechunk(z_proc, co, residual=r).float(), (r + out).float()) < max(tol, 1e-6)
+
+
+def test_encoder_with_fixed_chunker_runs_and_backpropagates():
+    """`chunker: fixed` through the whole Type A encoder (bf16 autocast): finite features, a gradient on every parameter."""
+    import dcasr_b200 as dd
+    torch.manual_seed(3)
+    enc = dd.DCASREncoder(n_mels=80, d_outer=128, d_main=128, n_enc=1, n_main=1, n_dec=1, arch_type="A", N=2,
+                          chunker="fixed").to(DEV)
+    feats, lens = torch.randn(3, 330, 80, device=DEV), torch.tensor([330, 250, 61], device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o = enc(feats, lens)
+    (o.features.float().pow(2).mean() + 0.03 * o.ratio_loss).backward()
+    assert torch.isfinite(o.features).all() and abs(float(o.kept_fractions[0]) - 0.5) < 0.02
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in enc.parameters())
