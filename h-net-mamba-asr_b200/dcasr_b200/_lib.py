@@ -77,18 +77,35 @@ class _Lib:
         return self.fn["hnb_" + name]
 
     def call(self, name: str, *args) -> None:
-        """Call int hnb_<name>(...) with tensors turned into device pointers; raise on non-zero status."""
+        """Call int hnb_<name>(...) with tensors turned into device pointers; raise on non-zero status.  The stream
+        argument (``stream()``) resolves to torch's current stream on the device of the call's first tensor, and the
+        call runs with that device current: a model on "cuda:1" in a process whose current device is 0 works."""
         conv = []
         T = torch.Tensor
+        dev, spos = -1, -1
         for a in args:
             if type(a) is T or isinstance(a, T):                  # (exact-type test first: it is the common case)
                 if not a.is_cuda:
                     raise HnbError(f"hnb_{name}: got a {a.device} tensor; the hot path is CUDA-only")
                 if not a.is_contiguous():
                     raise HnbError(f"hnb_{name}: tensor argument must be contiguous")
+                if dev < 0:
+                    dev = a.device.index
                 conv.append(a.data_ptr())
+            elif a is _CURRENT:
+                spos = len(conv)
+                conv.append(0)
             else:
                 conv.append(a)
+        cur = torch.cuda.current_device()
+        if dev >= 0 and dev != cur:                               # rare: tensors on another device than the current one
+            with torch.cuda.device(dev):
+                return self._run(name, conv, spos, dev, args)
+        return self._run(name, conv, spos, cur, args)
+
+    def _run(self, name, conv, spos, dev, args) -> None:
+        if spos >= 0:
+            conv[spos] = _raw_stream(dev) if _raw_stream is not None else torch.cuda.current_stream(dev).cuda_stream
         prof = _PROFILE
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -127,16 +144,25 @@ def lib() -> _Lib:
     return _LIB
 
 
+class _CurrentStream:
+    """Placeholder for "torch's current stream on the device of this call's tensors"; resolved inside _Lib.call.
+    Handed straight to a ctypes function (``lib().raw(...)``) it converts to the current device's current stream."""
+    __slots__ = ()
+
+    @property
+    def _as_parameter_(self):
+        dev = torch.cuda.current_device()
+        return ctypes.c_void_p(_raw_stream(dev) if _raw_stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+
+
+_CURRENT = _CurrentStream()
+# One C call; building a torch.cuda.Stream object per kernel launch (device-index lookups, availability checks) cost
+# 15 us of host time per launch, 5 ms of the 15 ms the host needed to enqueue one encoder step.
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
-def stream() -> int:
-    """cudaStream_t of torch's current stream on the current device.  The raw getter is one C call; building a
-    torch.cuda.Stream object per kernel launch (device-index lookups, availability checks) cost 15 us of host time
-    per launch, 5 ms of the 15 ms the host needs to enqueue one encoder step."""
-    if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
-    return torch.cuda.current_stream().cuda_stream
+def stream() -> _CurrentStream:
+    return _CURRENT
 
 
 def launch_count() -> int:

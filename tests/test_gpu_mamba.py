@@ -533,3 +533,28 @@ def test_block_composite_equals_per_kernel_path(dtype):
     assert rel_err(g1, g0) < 1e-5
     for k in p0:
         assert rel_err(p1[k], p0[k]) < 1e-4, k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_a_non_current_device():
+    """A model on "cuda:1" in a process whose current device is 0 (the reference's device-agnostic contract,
+    SURVEY.md §8b): kernels run on cuda:1's current stream and give what cuda:0 gives."""
+    import dcasr_b200 as dd
+    torch.manual_seed(9)
+    kw = dict(n_mels=80, d_outer=128, d_main=128, n_enc=1, n_main=1, n_dec=1, arch_type="A", N=2)
+    enc0 = dd.DCASREncoder(**kw).to("cuda:0")
+    with torch.no_grad():
+        enc0.chunk.router.W_k.weight.copy_(torch.randn(128, 128, device="cuda:0") / 128 ** 0.5)
+    enc1 = dd.DCASREncoder(**kw).to("cuda:1")
+    enc1.load_state_dict(enc0.state_dict())
+    feats, lens = torch.randn(2, 300, 80), torch.tensor([300, 201])
+    assert torch.cuda.current_device() == 0
+    outs = []
+    for enc, dev in ((enc0, "cuda:0"), (enc1, "cuda:1")):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o = enc(feats.to(dev), lens.to(dev))
+        (o.features.float().pow(2).mean() + 0.03 * o.ratio_loss).backward()
+        torch.cuda.synchronize(dev)
+        assert o.features.device == torch.device(dev)
+        outs.append((o.features.float().cpu(), enc.enc.layers[0].fwd.in_proj.weight.grad.float().cpu()))
+    assert rel_err(outs[1][0], outs[0][0]) < 1e-5 and rel_err(outs[1][1], outs[0][1]) < 1e-4
