@@ -39,6 +39,11 @@ class GradAllReducer:
             self.buckets.append(cur)
         self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device)
                      for b in self.buckets]
+        # persistent views of the flat buffers, shaped like their parameters: a step copies gradients in and out with
+        # one multi-tensor launch per bucket and no per-parameter tensor ops on the host (a reshape + a cast going in
+        # and a view coming out per parameter were ~1000 small host ops, ~1.5 ms, per step of the 330-parameter encoder)
+        self.views = [[v.view_as(p) for p, v in zip(b, flat.split([p.numel() for p in b]))]
+                      for b, flat in zip(self.buckets, self.flat)]
         self.works = [None] * len(self.buckets)
         self.pending = [len(b) for b in self.buckets]
         self.overlap = overlap and dist.is_initialized() and dist.get_world_size() > 1
@@ -48,11 +53,17 @@ class GradAllReducer:
                 p.register_post_accumulate_grad_hook(lambda q, i=where[id(p)]: self._ready(i))
 
     def _launch(self, i: int) -> None:
-        b, flat = self.buckets[i], self.flat[i]
-        views = flat.split([p.numel() for p in b])
-        torch._foreach_copy_(list(views), [p.grad.reshape(-1).float() if p.grad is not None
-                                           else torch.zeros_like(v) for p, v in zip(b, views)])
-        self.works[i] = dist.all_reduce(flat, async_op=True)
+        b, views = self.buckets[i], self.views[i]
+        if all(p.grad is not None for p in b):
+            torch._foreach_copy_(views, [p.grad for p in b])
+        else:                                                    # a parameter that got no gradient contributes zeros
+            have = [(v, p.grad) for p, v in zip(b, views) if p.grad is not None]
+            for p, v in zip(b, views):
+                if p.grad is None:
+                    v.zero_()
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        self.works[i] = dist.all_reduce(self.flat[i], async_op=True)
 
     def _ready(self, i: int) -> None:
         self.pending[i] -= 1
@@ -69,11 +80,10 @@ class GradAllReducer:
         for i, (b, flat) in enumerate(zip(self.buckets, self.flat)):
             self.works[i].wait()
             flat.div_(world)
-            views = flat.split([p.numel() for p in b])
-            for p, v in zip(b, views):
+            for p in b:
                 if p.grad is None:
                     p.grad = torch.empty_like(p)
-            torch._foreach_copy_([p.grad for p in b], [v.view_as(p) for p, v in zip(b, views)])   # one launch per bucket
+            torch._foreach_copy_([p.grad for p in b], self.views[i])   # one launch per bucket
             self.works[i] = None
             self.pending[i] = len(b)
 
