@@ -56,62 +56,55 @@ class _BroadcastFn(torch.autograd.Function):
         return dz, (dout if has_resid else None), None, None
 
 
+def _passthrough(x: torch.Tensor, mask: torch.Tensor | None) -> ChunkOutput:
+    """Stride 1: every frame is its own window.  Field for field what DynamicChunker returns at N = 1
+    (fixed_pool.py:56-67): z is x itself, p = b = the mask as floats, membership = frame index."""
+    B, L, _ = x.shape
+    valid = x.new_ones(B, L) if mask is None else mask.to(x.dtype)
+    index = torch.arange(L, device=x.device).repeat(B, 1)
+    z_mask = torch.ones(B, L, dtype=torch.bool, device=x.device) if mask is None else mask
+    return ChunkOutput(z=x, z_mask=z_mask, p=valid, b=valid, membership=index, ratio_loss=x.new_zeros(()),
+                       kept_fraction=x.new_ones(()))
+
+
 class FixedPoolChunker(nn.Module):
-    """Fixed-stride masked mean pooling to rate 1/N (no learned boundaries; fixed_pool.py:31-110)."""
+    """Masked mean over windows of ``stride`` frames, rate 1/N, nothing learned (fixed_pool.py:31-110)."""
 
     def __init__(self, d_model: int, N=1, ema_smoothing: bool = True):
         super().__init__()
-        n = float(N)
-        stride = int(round(n))
-        if abs(n - stride) > 1e-6:
-            raise ValueError(
-                f"FixedPoolChunker needs an integer stride; got N={N!r}. Fixed-stride "
-                "pooling has no fractional window — Type B fixed-pool is only defined at "
-                "perfect-square N (so √N is an integer).")
+        stride = int(round(float(N)))
+        if abs(float(N) - stride) > 1e-6:               # Type B passes sqrt(N): only perfect squares have a window
+            raise ValueError(f"FixedPoolChunker: the stride must be an integer, got N={N!r}")
         if stride < 1:
-            raise ValueError(f"FixedPoolChunker stride must be >= 1, got {stride}")
-        self.d_model = d_model
-        self.stride = stride
-        self.N = stride
-        self.identity = (stride == 1)
-        self.ema_smoothing = ema_smoothing      # interface parity: fixed pooling has no probability signal to smooth with
+            raise ValueError(f"FixedPoolChunker: the stride must be at least 1, got {stride}")
+        self.d_model, self.stride, self.N = d_model, stride, stride
+        self.identity = stride == 1
+        self.ema_smoothing = ema_smoothing              # accepted for interface parity; there is no probability to smooth with
 
     def chunk(self, x: torch.Tensor, mask: torch.Tensor | None = None) -> ChunkOutput:
-        B, L, D = x.shape
+        if self.identity:
+            return _passthrough(x, mask)
+        B, L, _ = x.shape
         s = self.stride
-        if self.identity:                       # exact passthrough, field for field DynamicChunker's N = 1 (:56-67)
-            ones = x.new_ones(B, L)
-            memb = torch.arange(L, device=x.device).unsqueeze(0).expand(B, L).clone()
-            if mask is not None:
-                ones = ones * mask.to(x.dtype)
-            return ChunkOutput(z=x, z_mask=(mask if mask is not None else x.new_ones(B, L, dtype=torch.bool)),
-                               p=ones, b=ones, membership=memb, ratio_loss=x.new_zeros(()),
-                               kept_fraction=x.new_ones(()))
-        if mask is not None:
-            lengths = mask.sum(dim=1)
-            m = mask.to(x.dtype)
-        else:
-            lengths = torch.full((B,), L, device=x.device, dtype=torch.long)
-            m = x.new_ones(B, L)
-        nwin = ((lengths + s - 1) // s).clamp_min(1)
-        M = int(nwin.max().item())              # the one host sync of the stage (sizes z), as in the reference (:78)
-        pos = torch.arange(L, device=x.device)
-        memb = (pos // s).clamp(max=M - 1).unsqueeze(0).expand(B, L)
+        n_valid = mask.sum(dim=1) if mask is not None else torch.full((B,), L, device=x.device, dtype=torch.long)
+        windows = torch.div(n_valid + (s - 1), s, rounding_mode="floor").clamp_min(1)     # per row (:76)
+        M = int(windows.max().item())                   # the one host sync of the stage: it sizes z (:77)
+        t = torch.arange(L, device=x.device)
+        membership = torch.div(t, s, rounding_mode="floor").clamp(max=M - 1).unsqueeze(0).expand(B, L)   # (:80-83)
         z, cnt = _PoolFn.apply(x, _mask_u8(mask), M, s)
-        z_mask = cnt > 0
-        b = (pos % s == 0).to(x.dtype).unsqueeze(0).expand(B, L) * m
-        kept = nwin.sum().float() / lengths.sum().clamp_min(1).float()
-        return ChunkOutput(z=z, z_mask=z_mask, p=b, b=b, membership=memb, ratio_loss=x.new_zeros(()),
+        starts = (t % s == 0).to(x.dtype).unsqueeze(0).expand(B, L)                       # window starts (:91)
+        b = starts if mask is None else starts * mask.to(x.dtype)
+        kept = windows.sum().float() / n_valid.sum().clamp_min(1).float()                 # (:92)
+        return ChunkOutput(z=z, z_mask=cnt > 0, p=b, b=b, membership=membership, ratio_loss=x.new_zeros(()),
                            kept_fraction=kept)
 
     def dechunk(self, z_proc: torch.Tensor, co: ChunkOutput, residual: torch.Tensor | None = None) -> torch.Tensor:
-        """Broadcast each processed window vector back over its fine frames (identity at N = 1).  ``residual`` (an
-        extension used by the encoder) is added in the same pass.  The window of a frame is recomputed from its
-        position, min(t // stride, M-1): exactly ``co.membership`` as chunk() of this class builds it."""
+        """Every frame takes its window's processed vector (fixed_pool.py:96-104); ``residual`` (an extension the
+        encoder uses) is added in the same pass.  The window of a frame is recomputed from its position,
+        min(t // stride, M-1): exactly ``co.membership`` as chunk() of this class builds it."""
         if self.identity:
             return z_proc if residual is None else residual + z_proc
-        L = co.membership.shape[1]
-        return _BroadcastFn.apply(z_proc, residual, L, self.stride)
+        return _BroadcastFn.apply(z_proc, residual, co.membership.shape[1], self.stride)
 
     def forward(self, x, mask=None):
         return self.chunk(x, mask)
