@@ -69,3 +69,24 @@ def test_block_composite_layout_queries():
     assert o[0] == 0 and o[1] == d * ndir * di and o[2] == o[1] + ndir * dstride * d
     assert all(a < b for a, b in zip(o, o[1:])) and all(v % 4 == 0 for v in o[:3])
     assert n == o[8] + 2 * d
+
+
+def test_host_side_cost_models_are_sane():
+    """The library's launch-shaping heuristics are pure host arithmetic (they fall back to 148 SMs without a GPU):
+    dB/dC head groups are 1 or 2 and divide H, the CUDA-core path always asks for one part, split-K hints are >= 1
+    and never exceed the number of 64-wide k-blocks, and the SSD workspace grows with the problem."""
+    from dcasr_b200._lib import lib
+    L_ = lib()
+    parts = L_.raw("ssd_dbc_parts")
+    for (ndir, B, L, H) in ((2, 40, 398, 12), (2, 40, 196, 16), (2, 2, 1498, 24), (1, 1, 7, 3), (2, 3, 150, 5)):
+        p1 = parts(ndir, B, L, H, 1)
+        assert p1 in (1, 2) and H % p1 == 0, (ndir, B, L, H, p1)
+        assert parts(ndir, B, L, H, 0) == 1
+    assert parts(2, 40, 196, 16, 1) == 2            # the main stack at the headline batch: 160 items are 1.1 waves of 148 SMs
+    hint = L_.raw("gemm_splitk_hint")
+    for (M, N, K) in ((3616, 384, 15920), (384, 1536, 15920), (4640, 512, 7840), (128, 128, 64), (8, 8, 8)):
+        sk = hint(M, N, K)
+        assert 1 <= sk <= max(1, (K + 63) // 64), (M, N, K, sk)
+    assert hint(3616, 384, 15920) > 1               # weight gradients (K = tokens) are split
+    ws = L_.raw("ssd_ws_bytes")
+    assert 0 < ws(2, 4, 398, 768, 128, 12) < ws(2, 8, 398, 768, 128, 12) < ws(2, 8, 1498, 768, 128, 12)
