@@ -110,6 +110,31 @@ class _Subsample(nn.Module):
         return x, (((lengths - 1) // 2 - 1) // 2).clamp_min(0)
 
 
+class FixedPoolChunkerRef(nn.Module):
+    """The reference's fixed-stride control (src/dcasr/models/fixed_pool.py:31-110) behind the chunker interface the
+    encoder uses; the arithmetic is oracle/fixed_pool_ref.py."""
+
+    def __init__(self, d_model, N=1, ema_smoothing=True):
+        super().__init__()
+        self.stride = int(round(float(N)))
+        if abs(float(N) - self.stride) > 1e-6 or self.stride < 1:
+            raise ValueError(f"fixed-stride pooling needs an integer stride >= 1, got N={N!r}")
+
+    def chunk(self, x, mask=None):
+        from . import fixed_pool_ref as fp
+        if self.stride == 1:                                       # identity passthrough (:56-67)
+            B, L, _ = x.shape
+            ones = x.new_ones(B, L) if mask is None else mask.to(x.dtype)
+            return fp.FixedChunkRef(z=x, z_mask=torch.ones(B, L, dtype=torch.bool) if mask is None else mask, p=ones,
+                                    b=ones, membership=torch.arange(L).repeat(B, 1), ratio_loss=x.new_zeros(()),
+                                    kept_fraction=x.new_ones(()), cnt=ones)
+        return fp.chunk_ref(x, self.stride, mask)
+
+    def dechunk(self, z_proc, co):
+        from . import fixed_pool_ref as fp
+        return z_proc if self.stride == 1 else fp.dechunk_ref(z_proc, co.membership)
+
+
 @dataclass
 class EncoderOutRef:
     features: torch.Tensor
@@ -126,23 +151,24 @@ class EncoderRef(nn.Module):
         super().__init__()
         if arch_type not in ("A", "B"):
             raise ValueError(f"arch_type must be 'A' or 'B', got {arch_type!r}")
-        if chunker != "dynamic":
-            raise ValueError("oracle restates the dynamic chunker only")
+        if chunker not in ("dynamic", "fixed"):
+            raise ValueError(f"unknown chunker {chunker!r}")                 # src/dcasr/models/encoder.py:35-36
+        mk = DynamicChunkerRef if chunker == "dynamic" else FixedPoolChunkerRef
         self.arch_type = arch_type
         self.subsample = _Subsample(n_mels, d_outer)
         self.enc = MambaStackRef(n_enc, d_outer, bidirectional)
         self.dec = MambaStackRef(n_dec, d_outer, bidirectional)
         if arch_type == "A":
-            self.chunk = DynamicChunkerRef(d_outer, N, hnet_ema)
+            self.chunk = mk(d_outer, N, hnet_ema)
             self.proj_in = nn.Linear(d_outer, d_main)
             self.main = MambaStackRef(n_main, d_main, bidirectional)
             self.proj_out = nn.Linear(d_main, d_outer)
         else:
             nb = math.sqrt(N)
-            self.chunk1 = DynamicChunkerRef(d_outer, nb, hnet_ema)
+            self.chunk1 = mk(d_outer, nb, hnet_ema)
             self.proj1_in = nn.Linear(d_outer, d_main)
             self.mid = MambaStackRef(n_mid, d_main, bidirectional)
-            self.chunk2 = DynamicChunkerRef(d_main, nb, hnet_ema)
+            self.chunk2 = mk(d_main, nb, hnet_ema)
             self.main = MambaStackRef(n_main, d_main, bidirectional)
             self.mid_dec = MambaStackRef(n_mid, d_main, bidirectional)
             self.proj1_out = nn.Linear(d_main, d_outer)

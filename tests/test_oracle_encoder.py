@@ -58,3 +58,32 @@ def test_encoder_oracle_matches_reference(path):
     for k in g.files:
         if k.startswith("g_"):
             assert rel_err(sd[k[2:]].grad, torch.from_numpy(g[k])) < 2e-3, k
+
+
+ENC_FIXED = sorted(glob.glob(os.path.join(GOLDEN, "encfixed_*.npz")))
+
+
+@pytest.mark.parametrize("path", ENC_FIXED, ids=[os.path.basename(p)[:-4] for p in ENC_FIXED])
+def test_encoder_oracle_with_fixed_chunker_matches_reference(path):
+    """`chunker: fixed` (src/dcasr/models/encoder.py:30-37, fixed_pool.py): the oracle's assembly against the reference's
+    own DCASREncoder run with its FixedPoolChunker (tests/golden/make_golden_fixed.py)."""
+    g = np.load(path)
+    enc = EncoderRef(n_mels=80, d_outer=64, d_main=128, n_enc=1, n_main=1, n_dec=1, n_mid=1,
+                     arch_type=str(g["arch"]), N=int(g["N"]), chunker="fixed")
+    fill_weights(enc, int(g["seed"]))
+    out = enc(torch.from_numpy(g["feats"]), torch.from_numpy(g["feat_lengths"]))
+    assert torch.equal(out.lengths, torch.from_numpy(g["lengths"])) and float(out.ratio_loss) == 0.0
+    i = 0
+    while f"p{i}" in g:
+        p, b = out.boundaries[i]
+        assert torch.equal(p, torch.from_numpy(g[f"p{i}"])) and torch.equal(b, torch.from_numpy(g[f"b{i}"]))
+        assert rel_err(out.chunk_embeddings[i], torch.from_numpy(g[f"z{i}"])) < 1e-5
+        assert max_err(out.kept_fractions[i], torch.from_numpy(g[f"kept{i}"])) < 1e-7
+        i += 1
+    mask = (torch.arange(out.features.shape[1])[None] < out.lengths[:, None]).unsqueeze(-1)
+    assert rel_err(out.features * mask, torch.from_numpy(g["features"]) * mask) < 1e-4
+    ((out.features * torch.from_numpy(g["w"]) * mask).sum() + 0.03 * out.ratio_loss).backward()
+    sd = dict(enc.named_parameters())
+    for k in g.files:
+        if k.startswith("g_"):
+            assert rel_err(sd[k[2:]].grad, torch.from_numpy(g[k])) < 2e-3, k
