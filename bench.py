@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: encoder frames/sec, fwd+bwd, Type A Small N=2 (BASELINE.json), on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--seconds S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload W] [--mode train|decode] [--N n]
 
 A step = one DCASREncoder forward + backward (loss = mean(features^2) + 0.03*ratio_loss)
 over one synthetic batch of 80-dim log-mel (B utterances x 16 s; 40 = the reference's per-GPU
@@ -10,6 +10,8 @@ batch_bins=64000 budget), bf16 autocast, random-init weights.  A frame = one val
 N > 1 (torchrun): the utterance batch is sharded (weak scaling), gradients are all-reduced over NCCL
 inside the timed step, time = max over ranks.
 --impl reference times the CPU restatement of the reference path (oracle/, kind "port") on host cores.
+--workload selects the other BASELINE.json configurations (B_small_N4, A_large_N3_60s, ragged); --mode decode times the
+fp32 no_grad forward.  After the timed region utterance 0 goes through the CPU oracle: the line's `parity` object.
 """
 from __future__ import annotations
 
@@ -32,6 +34,16 @@ import torch  # noqa: E402
 METRIC = "encoder frames/sec fwd+bwd, Type A Small N=2"
 UNIT = "frames/s"
 SMALL = dict(n_mels=80, d_outer=384, d_main=512, n_enc=4, n_main=12, n_dec=4, arch_type="A", N=2)
+# BASELINE.json configs: [1] the headline (default), [2] Type B N=4, [3] Large Type A N=3 on 60 s, [4] ragged 2-35 s batches
+WORKLOADS = {
+    "A_small_N2": dict(kw=SMALL, seconds=16.0, batch=40, what="Type A Small N=2"),
+    "B_small_N4": dict(kw=dict(n_mels=80, d_outer=384, d_main=512, n_enc=4, n_main=12, n_dec=4, n_mid=4, arch_type="B", N=4),
+                       seconds=16.0, batch=40, what="Type B Small N=4 (two sqrt(N)=2 chunk stages)"),
+    "A_large_N3_60s": dict(kw=dict(n_mels=80, d_outer=512, d_main=768, n_enc=6, n_main=18, n_dec=6, arch_type="A", N=3),
+                           seconds=60.0, batch=10, what="Type A Large N=3, 60 s utterances (docs/experimental_plan.md:123)"),
+    "ragged": dict(kw=SMALL, seconds=None, batch=None, what="Type A Small, ragged 2-35 s batches formed by the reference's bucketing rule"),
+}
+BATCH_BINS = 64000          # padded 100 Hz frames per GPU batch (reference configs/typeA_small_N2.yaml:71)
 
 
 def n_frames_100hz(seconds: float) -> int:
@@ -108,24 +120,101 @@ def synth_batch(B: int, seconds: float, seed: int):
     return torch.randn(B, T, 80, generator=g), torch.full((B,), T, dtype=torch.int64)
 
 
+def bucket_batches(lengths, max_frames):
+    """Length-bucketed batches under a padded-frame budget: sort by length, then greedily extend the current batch while
+    (count + 1) * longest <= max_frames -- the rule of the reference's DistributedBucketBatchSampler
+    (src/dcasr/data/librispeech.py:174-187), restated."""
+    order = sorted(range(len(lengths)), key=lambda i: lengths[i])
+    out, cur, longest = [], [], 0
+    for i in order:
+        cand = max(longest, lengths[i])
+        if cur and (len(cur) + 1) * cand > max_frames:
+            out.append(cur)
+            cur, longest = [i], lengths[i]
+        else:
+            cur.append(i)
+            longest = cand
+    if cur:
+        out.append(cur)
+    return out
+
+
+def ragged_batches(rank: int, n_utts: int = 4000, n_pick: int = 12):
+    """BASELINE config 5: durations 35 * Beta(2.2, 4.0) clipped to [2, 35] s (LibriSpeech-like, mean ~12.4 s), bucketed
+    with the reference's rule under batch_bins = 64000; every rank gets its own `n_pick` batches, evenly spread over
+    the sorted batch list (so short- and long-utterance batches are both in the sample).  -> [(feats, lens)], stats."""
+    g = torch.Generator().manual_seed(1234)
+    # (torch.distributions has no generator argument: draw Beta(a, b) = Ga / (Ga + Gb) from seeded Gamma variates)
+    ga = torch._standard_gamma(torch.full((n_utts,), 2.2), generator=g)
+    gb = torch._standard_gamma(torch.full((n_utts,), 4.0), generator=g)
+    dur = (35.0 * ga / (ga + gb)).clamp(2.0, 35.0)
+    lens = [n_frames_100hz(float(d)) for d in dur]
+    batches = bucket_batches(lens, BATCH_BINS)
+    idx = [int(round(k * (len(batches) - 1) / (n_pick - 1))) for k in range(n_pick)]
+    idx = [(i + rank) % len(batches) for i in idx]
+    out = []
+    for bi in idx:
+        ls = torch.tensor([lens[i] for i in batches[bi]], dtype=torch.int64)
+        gg = torch.Generator().manual_seed(100 + bi)
+        f = torch.randn(len(ls), int(ls.max()), 80, generator=gg)
+        for r, n in enumerate(ls.tolist()):
+            f[r, n:] = 0.0
+        out.append((f, ls))
+    valid = sum(int(sub_len_t(l).sum()) for _, l in out)
+    padded = sum(f.shape[0] * sub_len(f.shape[1]) for f, _ in out)
+    return out, {"utterance_pool": n_utts, "mean_seconds": round(float(dur.mean()), 2), "batches_in_pool": len(batches),
+                 "batches_sampled": n_pick, "batch_shapes": [[f.shape[0], f.shape[1]] for f, _ in out],
+                 "valid_frames": valid, "padded_frames": padded, "padding_share": round(1 - valid / padded, 4)}
+
+
+def sub_len_t(t):
+    return (((t - 1) // 2 - 1) // 2).clamp_min(0)
+
+
+def set_routers(enc, keep_N):
+    """Untrained identity routers keep ~0.3 % of the frames (the main stack would run on M ~ 1).  The metric's config is the
+    TRAINED operating point, keep fraction ~ 1/N per stage: W_k = shift I + seeded Gaussian / sqrt(d) puts
+    cos(q_t, k_{t-1}) ~ N(c, 1/d); shift 0 -> ~0.5, 0.12 -> ~1/3, 0.2 -> ~1/4 (SURVEY.md §8d, config 5 note)."""
+    shift = {1: 0.0, 2: 0.0, 3: 0.12, 4: 0.2}.get(int(round(keep_N)), 0.0)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for name in ("chunk", "chunk1", "chunk2"):
+            ch = getattr(enc, name, None)
+            if ch is not None and getattr(ch, "router", None) is not None:
+                d = ch.router.W_k.weight.shape[0]
+                w = shift * torch.eye(d) + torch.randn(d, d, generator=g) / d ** 0.5
+                ch.router.W_k.weight.copy_(w.to(ch.router.W_k.weight.device))
+
+
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the CPU restatement of the reference path, fwd+bwd, on host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(batch: int, seconds: float):
+def metric_name(workload: str, mode: str) -> str:
+    if workload == "A_small_N2" and mode == "train":
+        return METRIC
+    what = {"A_small_N2": "Type A Small N=2", "B_small_N4": "Type B Small N=4", "A_large_N3_60s": "Type A Large N=3 60 s",
+            "ragged": "Type A Small ragged 2-35 s"}[workload]
+    return f"encoder frames/sec {'fwd+bwd' if mode == 'train' else 'fwd (fp32 decode)'}, {what}"
+
+
+def cpu_reference_step_fn(kw, batch: int, seconds: float, keep_N, mode: str = "train"):
+    """One step of the CPU restatement of the reference path (oracle/encoder_ref.py: the reference's encoder.py /
+    mamba_block.py / hnet_chunk.py restated as vectorised torch code + the Mamba2 restatement), fp32, all host threads."""
     from oracle.encoder_ref import EncoderRef
     torch.manual_seed(1)
-    enc = EncoderRef(**SMALL)
-    with torch.no_grad():                                  # same keep-fraction ~0.5 operating point as the GPU arm
-        g = torch.Generator().manual_seed(7)
-        enc.chunk.router.W_k.weight.copy_(torch.randn(384, 384, generator=g) / 384 ** 0.5)
+    enc = EncoderRef(**kw)
+    set_routers(enc, keep_N)                                # same keep-fraction operating point as the GPU arm
     feats, lens = synth_batch(batch, seconds, 1)
 
     def step():
+        if mode != "train":
+            with torch.no_grad():
+                return float(enc(feats, lens).features.float().pow(2).mean())
         enc.zero_grad(set_to_none=True)
         out = enc(feats, lens)
         loss = out.features.float().pow(2).mean() + 0.03 * out.ratio_loss
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step, batch * sub_len(feats.shape[1])
 
@@ -135,7 +224,10 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
-    step, frames = cpu_reference_step_fn(1, args.seconds)
+    wl = WORKLOADS[args.workload]
+    kw = dict(wl["kw"]); kw["N"] = args.N if args.N else kw["N"]
+    seconds = args.seconds or wl["seconds"] or 12.4      # ragged: one utterance of the distribution's mean length
+    step, frames = cpu_reference_step_fn(kw, 1, seconds, kw["N"] if kw["arch_type"] == "A" else kw["N"] ** 0.5, args.mode)
     for _ in range(max(1, min(args.warmup, 1))):
         step()
     t0 = time.perf_counter()
@@ -143,12 +235,14 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = frames * args.steps / dt
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Type A Small N=2 encoder fwd+bwd, 1 x {args.seconds:g} s utterance per step (bounded CPU sample)"},
+    what = "fwd+bwd" if args.mode == "train" else "fwd (no_grad)"
+    line = {"metric": metric_name(args.workload, args.mode), "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl['what']} encoder {what}, 1 x {seconds:g} s utterance per step (bounded CPU sample)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{args.steps} steps x 1 utterance x {args.seconds:g} s, oracle/encoder_ref.py"},
+                             "sample": f"{args.steps} steps x 1 utterance x {seconds:g} s, oracle/encoder_ref.py (vectorised "
+                                       f"torch restatement of the reference modules; Mamba-2 arithmetic as chunk-64 einsums)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -226,6 +320,42 @@ def profile_step(step, pk):
 
 
 # ---------------------------------------------------------------------------------------------------
+def parity_check(enc, kw, feats1, lens1, dev, mode):
+    """After the timed region: utterance 0 of the bench batch through the CPU oracle (fp32) and through the product, once
+    in fp32 (exact kernels; features at north_star's 1e-3, boundaries bit-exact) and once as timed (bf16 autocast; loss
+    against the fp32 oracle, boundary decisions compared outside the bf16 band)."""
+    from oracle.encoder_ref import EncoderRef
+    ref = EncoderRef(**kw)
+    ref.load_state_dict({k: v.detach().float().cpu() for k, v in enc.state_dict().items()})
+    with torch.no_grad():
+        r = ref(feats1, lens1)
+        loss_r = float(r.features.pow(2).mean() + 0.03 * r.ratio_loss)
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        o32 = enc(feats1.to(dev), lens1.to(dev))
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ob = enc(feats1.to(dev), lens1.to(dev))
+        loss_b = float(ob.features.float().pow(2).mean() + 0.03 * ob.ratio_loss)
+    den = float(r.features.double().norm())
+    same32 = all(torch.equal(b.cpu(), br) for (_, b), (_, br) in zip(o32.boundaries, r.boundaries))
+    margin = min(float((p[p > 0] - 0.5).abs().min()) for p, _ in r.boundaries) if r.boundaries else None
+    out = {"oracle": "oracle/encoder_ref.py fp32 on host, utterance 0 of the batch, forward",
+           "fp32_boundaries_equal": same32, "oracle_min_abs_p_minus_half": margin,
+           "fp32_feature_rel_err": (float((o32.features.cpu().double() - r.features.double()).norm()) / den) if same32 else None,
+           "bf16_loss": loss_b, "oracle_loss": loss_r, "bf16_loss_rel_err": abs(loss_b - loss_r) / abs(loss_r)}
+    bad = 0
+    for (pb, bb), (pr, br) in zip(ob.boundaries, r.boundaries):
+        if pb.shape == pr.shape:
+            outside = (pr - 0.5).abs() > 2e-2
+            bad += int((bb.cpu()[outside] != br[outside]).sum())
+        else:
+            bad = None
+            break
+    out["bf16_boundary_mismatches_outside_2e-2_band"] = bad
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import dcasr_b200 as dd
@@ -240,41 +370,68 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    wl = WORKLOADS[args.workload]
+    kw = dict(wl["kw"])
+    if args.N:
+        kw["N"] = args.N
+    train = args.mode == "train"
+    ragged = args.workload == "ragged"
     torch.manual_seed(1)
-    torch.backends.cudnn.benchmark = True           # ConvSubsampling4 is library code: let cuDNN pick its kernels
-    enc = dd.DCASREncoder(**SMALL).to(dev)
-    with torch.no_grad():
-        # Untrained identity routers keep ~0.3 % of the frames (the main stack would run on M ~ 1).  The metric's
-        # config is the TRAINED operating point, keep-fraction ~ 1/N = 0.5, so W_k is set to a seeded random matrix:
-        # cos(q_t, k_{t-1}) is then ~N(0, 1/D) and half of the frames cross p >= 0.5 (SURVEY.md §8d, config 5 note).
-        g = torch.Generator().manual_seed(7)
-        enc.chunk.router.W_k.weight.copy_(torch.randn(384, 384, generator=g) / 384 ** 0.5)
+    torch.backends.cudnn.benchmark = not ragged     # ConvSubsampling4 is library code: let cuDNN pick its kernels (fixed shapes only)
+    enc = dd.DCASREncoder(**kw).to(dev)
+    set_routers(enc, kw["N"] if kw["arch_type"] == "A" else kw["N"] ** 0.5)
     if world > 1:                                   # identical replicas, as DDP's initial broadcast would make them
         for p in enc.parameters():
             dist.broadcast(p.data, 0)
     params = [p for p in enc.parameters()]
     from dcasr_b200.distributed import GradAllReducer
-    reducer = GradAllReducer(params, bucket_mb=32.0, overlap=True) if world > 1 else None
-    feats_h, lens_h = synth_batch(args.batch, args.seconds, 1 + rank)      # each rank its own shard of utterances
-    feats_pin, lens_pin = feats_h.pin_memory(), lens_h.pin_memory()
-    feats_d, lens_d = feats_h.to(dev), lens_h.to(dev)
-    frames_per_step = args.batch * sub_len(feats_h.shape[1]) * world
-    kept = [0.0]
+    reducer = GradAllReducer(params, bucket_mb=32.0, overlap=True) if (world > 1 and train) else None
+    # ---- the batches: one fixed-length batch (each rank its own shard of utterances), or a cycle of ragged batches
+    if ragged:
+        host_batches, ragged_stats = ragged_batches(rank)
+    else:
+        batch = args.batch or wl["batch"]
+        seconds = args.seconds or wl["seconds"]
+        host_batches, ragged_stats = [synth_batch(batch, seconds, 1 + rank)], None
+    pinned = [(f.pin_memory(), l.pin_memory()) for f, l in host_batches]
+    resident = [(f.to(dev), l.to(dev)) for f, l in host_batches]
+    frames_of = [int(sub_len_t(l).sum()) for _, l in host_batches]
+    nb = len(host_batches)
+    kept_log, exposed = [], []
+    cursor = {"resident": 0, "e2e": 0, "hot": 0}
+
+    def loss_of(out, lens_sub):
+        if ragged:                                  # masked mean: padded frames carry no loss (as CTC / the ratio loss do)
+            m = (torch.arange(out.features.shape[1], device=dev)[None, :] < lens_sub[:, None]).unsqueeze(-1)
+            return (out.features.float().pow(2) * m).sum() / (m.sum() * out.features.shape[2]) + 0.03 * out.ratio_loss
+        return out.features.float().pow(2).mean() + 0.03 * out.ratio_loss
 
     def fwd_bwd(feats, lens):
+        if not train:                               # decode: fp32, no_grad forward (reference tasks/decode_task.py:123-151)
+            with torch.no_grad():
+                out = enc(feats, lens)
+                kept_log.append(out.kept_fractions)
+                return out.features.float().pow(2).mean()
         for p in params:
             p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = enc(feats, lens)
-        loss = out.features.float().pow(2).mean() + 0.03 * out.ratio_loss
+        loss = loss_of(out, out.lengths)
         loss.backward()
         if reducer is not None:                     # the one exchange of the path: gradient all-reduce (DDP semantics)
-            reducer()
-        kept[0] = out.kept_fractions[0]
+            if len(exposed) < 64:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); reducer(); e1.record()
+                exposed.append((e0, e1))
+            else:
+                reducer()
+        kept_log.append(out.kept_fractions)
         return loss
 
     def step_resident():
-        return fwd_bwd(feats_d, lens_d)
+        i = cursor["resident"] % nb
+        cursor["resident"] += 1
+        return fwd_bwd(*resident[i])
 
     from dcasr_b200.distributed import HostBatchPrefetcher
     pref = HostBatchPrefetcher(dev)
@@ -282,24 +439,21 @@ def run_ours(args):
     loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(4)]
     e2e_pending, e2e_losses, e2e_seq, e2e_wall = [], [], [0], []
 
+    def e2e_push():
+        i = cursor["e2e"] % nb
+        cursor["e2e"] += 1
+        pref.push(*pinned[i])
+
     def step_e2e():
         # every step copies its own batch from pinned host memory (exactly one H2D copy per step, all of them inside
         # the timed region); the copy for step i+1 is started on a side stream before step i's kernels are launched
-        mode = int(os.environ.get("HNB_BENCH_E2E_MODE", "2"))     # diagnosis: 0 same-stream copy + blocking read, 1 prefetch + blocking read
-        if mode == 0:
-            f, l = feats_pin.to(dev, non_blocking=True), lens_pin.to(dev, non_blocking=True)
-            e2e_losses.append(float(fwd_bwd(f, l)))
-            return
         if pref.empty():
-            pref.push(feats_pin, lens_pin)
+            e2e_push()
         f, l = pref.pop()
         e2e_left[0] -= 1
         if e2e_left[0] > 0:
-            pref.push(feats_pin, lens_pin)
+            e2e_push()
         loss = fwd_bwd(f, l)
-        if mode == 1:
-            e2e_losses.append(float(loss))
-            return
         # device -> host read of the step's result, every step: an asynchronous copy into pinned memory that the host
         # picks up as soon as it has landed (polled once per step, never waited for; whatever is still in flight is
         # drained in e2e_finish, inside the timed region), so the read never drains the launch queue -- the reference's
@@ -322,16 +476,22 @@ def run_ours(args):
             ev0.synchronize()
             e2e_losses.append(float(s0))
 
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        xsub_d, lsub_d = enc.subsample(feats_d, lens_d)
-    xsub_d = xsub_d.detach()
+    hot_inputs = []
+    if train:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for f, l in resident:
+                xs, ls = enc.subsample(f, l)
+                hot_inputs.append((xs.detach(), ls))
 
     def step_hot_path():                            # the path north_star names: everything after ConvSubsampling4
+        i = cursor["hot"] % nb
+        cursor["hot"] += 1
+        xs, ls = hot_inputs[i]
         for p in params:
             p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = enc.forward_hot_path(xsub_d, lsub_d)
-        loss = out.features.float().pow(2).mean() + 0.03 * out.ratio_loss
+            out = enc.forward_hot_path(xs, ls)
+        loss = loss_of(out, ls)
         loss.backward()
         if reducer is not None:
             reducer()
@@ -359,48 +519,69 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / 1e3, wall, dd.launch_count()
 
-    for _ in range(max(args.warmup, 3)):
+    steps = args.steps if not ragged else max(args.steps, nb) // nb * nb      # ragged: whole cycles over the sampled batches
+    warm = max(args.warmup, 3) if not ragged else max(args.warmup, nb)        # ragged: every batch shape once before timing
+    frames_timed = lambda k0: sum(frames_of[(k0 + i) % nb] for i in range(steps)) * world      # noqa: E731
+    for _ in range(warm):
         step_resident()
+    del exposed[:], kept_log[:]
+    k0 = cursor["resident"]
     with ClockSampler(local) as cs:
-        sec, wall, launches = timed(step_resident, args.steps)
+        sec, wall, launches = timed(step_resident, steps)
     clocks = cs.summary()
+    frames_value = frames_timed(k0)
+    exposed_ms = [a.elapsed_time(b) for a, b in exposed]
+    kept = [[round(float(v), 4) for v in ks] for ks in kept_log[:nb]]
     import gc
     e2e_left[0] = 3
     for _ in range(3):
         step_e2e()
     e2e_finish()
     gc.collect()
-    e2e_left[0] = args.steps
+    e2e_left[0] = steps
     del e2e_losses[:], e2e_wall[:]
-    sec_e2e, _, _ = timed(step_e2e, args.steps, finish=e2e_finish)
-    assert len(e2e_losses) == args.steps and all(math.isfinite(v) for v in e2e_losses), e2e_losses
+    cursor["e2e"] = 0
+    sec_e2e, _, _ = timed(step_e2e, steps, finish=e2e_finish)
+    assert len(e2e_losses) == steps and all(math.isfinite(v) for v in e2e_losses), e2e_losses
+    frames_e2e = frames_timed(0)
+    if train:
+        for _ in range(2 if not ragged else nb):
+            step_hot_path()
+        kh = cursor["hot"]
+        sec_hot, _, launches_hot = timed(step_hot_path, steps)
+        frames_hot = frames_timed(kh)
 
-    for _ in range(2):
-        step_hot_path()
-    sec_hot, _, launches_hot = timed(step_hot_path, args.steps)
-
-    value = frames_per_step * args.steps / sec
-    e2e_v = frames_per_step * args.steps / sec_e2e
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"Type A Small N=2 DCASREncoder fwd+bwd, {args.batch} x {args.seconds:g} s utterances per GPU "
-                                   f"(L0={sub_len(feats_h.shape[1])} frames each), bf16 autocast, random-init weights",
-                       "frames_per_step": frames_per_step, "kept_fraction": round(float(kept[0]), 4),
+    f0, l0 = host_batches[0]
+    value = frames_value / sec
+    e2e_v = frames_e2e / sec_e2e
+    h2d = sum(f.numel() * 4 + l.numel() * 8 for f, l in host_batches) / nb * world
+    shape = (f"{f0.shape[0]} x {(args.seconds or wl['seconds']):g} s utterances per GPU (L0={sub_len(f0.shape[1])} frames each)"
+             if not ragged else f"{nb} ragged batches per GPU cycled (2-35 s, batch_bins {BATCH_BINS})")
+    line = {"metric": metric_name(args.workload, args.mode), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if train else "f32", "data": "synthetic",
+            "config": {"workload": f"{wl['what']}{'' if not args.N else f' (N={args.N})'} DCASREncoder "
+                                   f"{'fwd+bwd, bf16 autocast' if train else 'forward, fp32 no_grad (decode)'}, {shape}, random-init weights",
+                       "frames_per_step": frames_value / steps, "kept_fraction": kept[0] if kept else None,
                        "includes_conv_subsample": "yes (cuDNN/cuBLAS via torch; outside the hand-written hot path)",
                        "optimizer": "none (metric is encoder fwd+bwd); N>1 adds the NCCL gradient all-reduce",
                        "l2": "no flush: the step's working set (saved activations, several GB) is far larger than the 126 MB L2",
                        "parallelism": f"dp{world} (utterance batch sharded, replicas)"},
-            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": (feats_h.numel() * 4 + lens_h.numel() * 8) * world,
-                    "d2h_bytes_per_step": 4 * world,
-                    "host_ms_between_steps": [round(1e3 * (b - a), 2) for a, b in zip(e2e_wall, e2e_wall[1:])],
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * world,
+                    "host_ms_between_steps": [round(1e3 * (b - a), 2) for a, b in zip(e2e_wall, e2e_wall[1:])][:16],
                     "how": "per step: H2D of that step's pinned batch (side stream, started one step ahead) and an async "
                            "D2H copy of its loss into pinned memory, picked up by the host when it has landed (all of "
                            "them before the closing event)"},
-            "hot_path": {"value": frames_per_step * args.steps / sec_hot, "unit": UNIT, "ms_per_step": 1e3 * sec_hot / args.steps,
-                         "what": "forward_hot_path + backward from the subsampled features (ConvSubsampling4 excluded)",
-                         "gpu_launches": launches_hot},
             "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3)}
+    if train:
+        line["hot_path"] = {"value": frames_hot / sec_hot, "unit": UNIT, "ms_per_step": 1e3 * sec_hot / steps,
+                            "what": "forward_hot_path + backward from the subsampled features (ConvSubsampling4 excluded)",
+                            "gpu_launches": launches_hot}
+    if ragged:
+        line["config"]["ragged"] = ragged_stats
+        line["config"]["kept_fraction_per_batch"] = kept
+    if exposed_ms:
+        line["allreduce_exposed_ms"] = round(sum(exposed_ms) / len(exposed_ms), 3)
     # the profiled step contains the gradient all-reduce when world > 1: EVERY rank must run it
     pk, pk_src = peaks()
     table, total = profile_step(step_resident, pk)
@@ -408,20 +589,31 @@ def run_ours(args):
         top = next((r for r in table if "frac" in r), None)
         if top:
             traffic = None      # DRAM read+write bytes per call of this entry point, from the committed ncu pass
-            try:
-                tj = json.load(open(os.path.join(REPO, "profiles", "r01_traffic.json")))
-                traffic = round(tj["entries"][top["kernel"]]["dram_bytes_per_call"])
-            except Exception:
-                pass
+            import glob
+            for tf in sorted(glob.glob(os.path.join(REPO, "profiles", "r*_traffic.json")), reverse=True):
+                try:
+                    tj = json.load(open(tf))
+                    if tj.get("workload", "A_small_N2") == args.workload and args.mode == "train":
+                        traffic = round(tj["entries"][top["kernel"]]["dram_bytes_per_call"])
+                        break
+                except Exception:
+                    pass
             line["roofline"] = {"kernel": "hnb_" + top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
                                 "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
                                 "algorithmic_bytes_per_call": top.get("bytes_per_call"),
                                 "peak_source": pk_src + (" (sustained)" if top["bound"] == "tensor" else ""),
                                 "share_of_step": top["share"], "launches_per_step": top["launches"]}
         line["kernel_table"] = table[:12]
+        line["kernel_ms_sum"] = round(total, 3)
+        if world == 1 and not args.no_parity:
+            try:
+                line["parity"] = parity_check(enc, kw, f0[:1, : int(l0[0])].contiguous(), l0[:1], dev, args.mode)
+            except Exception as e:            # a parity failure must be visible in the line, never hide the measurement
+                line["parity"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
-            step, frames = cpu_reference_step_fn(1, args.seconds)
+            secs = args.seconds or wl["seconds"] or 12.4
+            step, frames = cpu_reference_step_fn(kw, 1, secs, kw["N"] if kw["arch_type"] == "A" else kw["N"] ** 0.5, args.mode)
             step()
             t0 = time.perf_counter()
             n = 0
@@ -429,8 +621,8 @@ def run_ours(args):
                 step(); n += 1
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": frames * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{n} steps x 1 utterance x {args.seconds:g} s fwd+bwd, oracle/encoder_ref.py "
-                                              f"(fp32, {os.cpu_count()} host cpus)"}
+                                    "sample": f"{n} steps x 1 utterance x {secs:g} s {'fwd+bwd' if train else 'fwd'}, oracle/encoder_ref.py "
+                                              f"(vectorised torch restatement of the reference modules, fp32, {os.cpu_count()} host cpus)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -442,10 +634,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=40, help="utterances per GPU (40 x 16 s = batch_bins 64000)")
-    ap.add_argument("--seconds", type=float, default=16.0)
+    ap.add_argument("--workload", default="A_small_N2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config: A_small_N2 (headline, default), B_small_N4, A_large_N3_60s, ragged")
+    ap.add_argument("--mode", default="train", choices=["train", "decode"],
+                    help="train: fwd+bwd under bf16 autocast (the metric); decode: fp32 no_grad forward")
+    ap.add_argument("--N", type=float, default=0, help="override the compression ratio (ragged sweep: 1, 2, 3, 4)")
+    ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: batch_bins 64000 / frames per utterance)")
+    ap.add_argument("--seconds", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench oracle check of utterance 0")
     args = ap.parse_args()
+    if args.N and args.N == int(args.N):
+        args.N = int(args.N)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -65,7 +65,7 @@ size_t bwd_layout(const Dims& m, int parts, size_t* off) {
   return o;
 }
 
-// gradient arena (fp32, zeroed by the caller): dWout [d, ndir*di] | dWin [ndir*dstride, d] | conv_w | conv_b | norm_w |
+// gradient arena (fp32): dWout [ndir][d, di] | dWin [ndir*dstride, d] | conv_w | conv_b | norm_w |
 // dA_log | dD | ddt_bias | LayerNorm dgamma, dbeta
 enum { A_WOUT, A_WIN, A_CW, A_CB, A_NW, A_DA, A_DD, A_DTB, A_LN, A_COUNT };
 size_t arena_layout(const Dims& m, size_t* off) {      // in floats
@@ -178,7 +178,7 @@ extern "C" int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths,
 
 extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const int32_t* lengths, const float* ln_w,
                              const void* ws, int B, int L, int d, int ndir, int di, int N, int H, int act_dtype,
-                             int ssd_impl, void* dx, float* grads, void* scratch, void* stream) {
+                             int ssd_impl, void* dx, float* grads, int zero_grads, void* scratch, void* stream) {
   const Dims m{B, L, d, ndir, di, N, H, act_dtype};
   HNB_TRY(check_dims("block_bwd", m, x_dtype));
   HNB_CHECK_ARG(dout && x && ln_w && ws && dx && grads && scratch, "block_bwd: null pointer");
@@ -204,6 +204,7 @@ extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const
   void* dBC = sc + so[S_DBC]; float* ddt = reinterpret_cast<float*>(sc + so[S_DDT]); void* ws2 = sc + so[S_WS2];
   void* dh2 = sc + so[S_DH2];
   cudaStream_t st = (cudaStream_t)stream;
+  if (zero_grads) HNB_CUDA_CALL(cudaMemsetAsync(grads, 0, arena_layout(m, ao) * sizeof(float), st));
 
   // gradient of the block output in the activation dtype (the residual stream may be fp32 under bf16 autocast)
   const void* da = dout;
@@ -220,8 +221,20 @@ extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const
   const int bf = act_dtype == HNB_BF16;
   HNB_TRY(gemm(act_dtype, da, d, 0, Wout, (long long)ndir * di, 1, (int)T, ndir * di, d, nullptr, 0, dyn, (long long)ndir * di,
                act_dtype, 1, stream));                                                        // d ynorm
-  HNB_TRY(gemm(act_dtype, da, d, 1, yn, (long long)ndir * di, 1, d, ndir * di, (int)T, nullptr, 0, grads + ao[A_WOUT],
-               (long long)ndir * di, HNB_F32, bf ? hnb_gemm_splitk_hint(d, ndir * di, (int)T) : 1, stream));   // dWout
+  // dWout of both directions from ONE GEMM, each direction's [d, di] matrix contiguous (column-blocked C): the parameter's
+  // .grad can then alias the arena instead of being a strided copy of it
+  if (bf && (ndir == 1 || di % 32 == 0)) {
+    HNB_TRY(hnb_gemm_bf16_ex(da, d, 1, yn, (long long)ndir * di, 1, d, ndir * di, (int)T, nullptr, nullptr, 0, grads + ao[A_WOUT],
+                             di, HNB_F32, hnb_gemm_splitk_hint(d, ndir * di, (int)T), ndir > 1 ? di : 0, (long long)d * di,
+                             stream));
+  } else {
+    for (int r = 0; r < ndir; ++r) {
+      const size_t a = esz(act_dtype);
+      const void* yn_r = static_cast<const uint8_t*>(yn) + (size_t)r * di * a;
+      HNB_TRY(gemm(act_dtype, da, d, 1, yn_r, (long long)ndir * di, 1, d, di, (int)T, nullptr, 0,
+                   grads + ao[A_WOUT] + (long long)r * d * di, di, HNB_F32, bf ? hnb_gemm_splitk_hint(d, di, (int)T) : 1, stream));
+    }
+  }
   if (dstride != dip) {                                       // pad columns of dzxbcdt feed the two GEMMs below
     const size_t a = esz(act_dtype);
     HNB_CUDA_CALL(cudaMemset2DAsync(static_cast<uint8_t*>(dzx) + (size_t)dip * a, (size_t)dstride * a, 0,

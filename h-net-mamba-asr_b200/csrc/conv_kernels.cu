@@ -120,7 +120,7 @@ conv_fwd_kernel(const T* __restrict__ zx, long long ldz, long long dstride, cons
   const int dir = blockIdx.z / B, bi = blockIdx.z % B;
   const int C = di + 2 * N;
   const long long T_ = (long long)B * L;
-  const int len = lengths ? lengths[bi] : L;
+  const int len = lengths ? min(max(lengths[bi], 0), L) : L;   // clamped like reverse_sequences (mamba_block.py:26)
   const long long xoff = (long long)dir * dstride + di;
   const long long doff = (long long)dir * dstride + di + C;
   const T* rowbase = zx + (long long)bi * L * ldz;
@@ -216,7 +216,7 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
   const int dir = blockIdx.z / B, bi = blockIdx.z % B;
   const int C = di + 2 * N;
   const long long T_ = (long long)B * L;
-  const int len = lengths ? lengths[bi] : L;
+  const int len = lengths ? min(max(lengths[bi], 0), L) : L;   // clamped like reverse_sequences (mamba_block.py:26)
   const long long xoff = (long long)dir * dstride + di;
   const long long doff = (long long)dir * dstride + di + C;
   const T* rowbase = zx + (long long)bi * L * ldz;

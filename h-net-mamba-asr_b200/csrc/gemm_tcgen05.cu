@@ -86,6 +86,14 @@ struct GemmParams {
   long long ldc;
   int c_is_f32;
   int atomic;
+  int cblk;                   // > 0: C is stored as N / cblk separate [M, cblk] matrices (fp32 outputs; cblk % 32 == 0)
+  long long cblk_stride;      // elements between those matrices
+  // element offset of (row, col0) in C; a 32-column block never straddles two column blocks
+  __device__ __forceinline__ long long c_off(int row, int col0) const {
+    if (cblk <= 0) return (long long)row * ldc + col0;
+    const int blk = col0 / cblk;
+    return blk * cblk_stride + (long long)row * ldc + (col0 - blk * cblk);
+  }
 };
 
 // Epilogue of one accumulator tile for one warp: TMEM lane quarter at `t_addr`, output row `row`, the warp's column
@@ -130,7 +138,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ad
           }
         }
         if (p.atomic) {
-          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+          float* c = reinterpret_cast<float*>(p.C) + p.c_off(row, col0);
           if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -139,7 +147,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ad
             for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(c + j, v[j]);
           }
         } else if (p.c_is_f32) {
-          float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+          float* c = reinterpret_cast<float*>(p.C) + p.c_off(row, col0);
           const float* r = p.R ? reinterpret_cast<const float*>(p.R) + (long long)row * p.ldr + col0 : nullptr;
           if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (!r || (reinterpret_cast<uintptr_t>(r) & 31) == 0)) {
             if (r) {
@@ -566,10 +574,29 @@ extern "C" int hnb_gemm_splitk_hint(int M, int N, int K) {
   return best;
 }
 
+// Which kernel hnb_gemm_bf16 runs for this problem: 0 = single-CTA tiles, 1 = 2-CTA multicast, 2 = CTA-pair (cta_group::2).
+extern "C" int hnb_gemm_bf16_path(int M, int N, int K, int splitk) {
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  static const int cl_env = getenv("HNB_GEMM_CLUSTER") ? atoi(getenv("HNB_GEMM_CLUSTER")) : 3;
+  const int BN = gemm_tile_n(N), kb_total = cdiv(K, BK);
+  const int sk_req = splitk < 1 ? 1 : (splitk > kb_total ? kb_total : splitk);
+  const int per_req = cdiv(kb_total, sk_req);
+  if (gemm_use_pair(M, N, BN, per_req, cdiv(kb_total, per_req))) return 2;
+  return (cl_env == 2 && cdiv(M, BM) >= 4 && BN != 192) ? 1 : 0;
+}
+
 extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const void* B, long long ldb, int transB, int M,
                              int N, int K, const float* bias, const void* R, long long ldr, void* C, long long ldc,
                              int c_dtype, int splitk, void* stream) {
+  return hnb_gemm_bf16_ex(A, lda, transA, B, ldb, transB, M, N, K, bias, R, ldr, C, ldc, c_dtype, splitk, 0, 0, stream);
+}
+
+extern "C" int hnb_gemm_bf16_ex(const void* A, long long lda, int transA, const void* B, long long ldb, int transB, int M,
+                                int N, int K, const float* bias, const void* R, long long ldr, void* C, long long ldc,
+                                int c_dtype, int splitk, int c_col_block, long long c_block_stride, void* stream) {
   HNB_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_bf16: bad arguments");
+  HNB_CHECK_ARG(c_col_block == 0 || (c_col_block > 0 && c_col_block % 32 == 0 && N % c_col_block == 0 && c_dtype == HNB_F32 && !R),
+                "gemm_bf16: column-blocked C needs fp32 C, no residual, a block width that is a multiple of 32 and divides N");
   HNB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
   HNB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                 "gemm_bf16: operands must be 16-byte aligned");
@@ -611,6 +638,7 @@ extern "C" int hnb_gemm_bf16(const void* A, long long lda, int transA, const voi
   p.bias = bias; p.R = R; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.c_is_f32 = (c_dtype == HNB_F32);
   p.atomic = p.splitk > 1;
+  p.cblk = c_col_block; p.cblk_stride = c_block_stride;
   const int n_items = p.groups_m * p.tiles_n * p.splitk;
   const int sms = gemm_sm_count();
   const int grid = CL * (n_items < sms / CL ? n_items : sms / CL);

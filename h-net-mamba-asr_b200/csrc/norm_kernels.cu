@@ -241,7 +241,7 @@ gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long lo
   const int dir = (int)(idx / T_);
   const long long tok = idx % T_;
   const int bi = (int)(tok / L), t = (int)(tok % L);
-  const int len = lengths ? lengths[bi] : L;
+  const int len = lengths ? min(max(lengths[bi], 0), L) : L;   // clamped like reverse_sequences (mamba_block.py:26)
   const int s = scan_to_nat(dir, t, len);                           // the map is an involution
   const T* yr = y + ((long long)dir * T_ + (long long)bi * L + s) * di;
   const T* zr = zx + tok * ldz + (long long)dir * dstride;
@@ -299,7 +299,7 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
     for (int i = 0; i < VN; ++i) aw[k][i] = 0.f;
   for (long long tok = (long long)blockIdx.x * NORM_WARPS + wi; tok < T_; tok += (long long)gridDim.x * NORM_WARPS) {
     const int bi = (int)(tok / L), t = (int)(tok % L);
-    const int len = lengths ? lengths[bi] : L;
+    const int len = lengths ? min(max(lengths[bi], 0), L) : L;   // clamped like reverse_sequences (mamba_block.py:26)
     const int s = scan_to_nat(dir, t, len);
     const long long yoff = ((long long)dir * T_ + (long long)bi * L + s) * di;
     const T* zr = zx + tok * ldz + (long long)dir * dstride;

@@ -260,6 +260,9 @@ class DynamicChunker(nn.Module):
             B, L = co.membership.shape
             bb = co.b.contiguous()
             _, counts = ops.boundary_scan(bb, B, L)
+            if int(counts.max()) > z_proc.shape[1]:         # the reference's gather raises here too (index out of range)
+                raise IndexError(f"dechunk: z_proc holds {z_proc.shape[1]} chunks per row but the boundaries define "
+                                 f"{int(counts.max())}")
             _, _, P, starts = ops.compact_rows(co.p.detach().reshape(B, L, 1).contiguous(), co.p.detach().contiguous(),
                                                bb, co.membership.contiguous(), counts, z_proc.shape[1])
         return _DechunkFn.apply(z_proc, co.p, residual, co.b, co.membership, P, starts, counts,

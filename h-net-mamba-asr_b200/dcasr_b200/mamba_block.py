@@ -251,17 +251,18 @@ class _BlockFn(torch.autograd.Function):
         L_ = lib()
         offs = (ctypes.c_longlong * 9)()
         n = L_.raw("block_grad_floats")(B, L, d, ndir, di, N, H, ctypes.addressof(offs))
-        # ONE zero fill: the split-K weight gradients and every accumulated parameter gradient are views of this arena
-        arena = torch.zeros(n, dtype=torch.float32, device=x2.device)
+        # the split-K weight gradients and every accumulated parameter gradient are views of this arena; the call clears it
+        # on its own stream (no fill kernel, no extra host round trip)
+        arena = torch.empty(n, dtype=torch.float32, device=x2.device)
         scratch = torch.empty(L_.raw("block_bwd_ws_bytes")(B, L, d, ndir, di, N, H, act, impl), dtype=torch.uint8,
                               device=x2.device)
         dx2 = torch.empty_like(x2)
-        L_.call("block_bwd", dout2, x2, xdt, lengths, ln_w32, ws, B, L, d, ndir, di, N, H, act, impl, dx2, arena, scratch,
+        L_.call("block_bwd", dout2, x2, xdt, lengths, ln_w32, ws, B, L, d, ndir, di, N, H, act, impl, dx2, arena, 1, scratch,
                 stream())
         C, dip = di + 2 * N, 2 * di + 2 * N + H
         dstride = _round_up(dip, 8)
         o = list(offs)
-        dWout = arena[o[0]:o[0] + d * ndir * di].view(d, ndir * di)
+        dWout = arena[o[0]:o[0] + d * ndir * di].view(ndir, d, di)       # one contiguous [d, di] matrix per direction
         dWin = arena[o[1]:o[1] + ndir * dstride * d].view(ndir * dstride, d)
         cw = arena[o[2]:o[2] + ndir * C * 4].view(ndir, C, 1, 4)
         cb = arena[o[3]:o[3] + ndir * C].view(ndir, C)
@@ -273,7 +274,7 @@ class _BlockFn(torch.autograd.Function):
         pg = []
         for r in range(ndir):                    # _params() order: in_proj.w, conv1d.w, conv1d.b, dt_bias, A_log, D, norm.w, out_proj.w
             g = (dWin[r * dstride: r * dstride + dip], cw[r], cb[r], dtb[r], dA[r], dD[r], nw[r],
-                 dWout[:, r * di:(r + 1) * di])
+                 dWout[r])
             pg += [t if t.dtype == pdts[r * NP + i] else t.to(pdts[r * NP + i]) for i, t in enumerate(g)]
         dg, db = ln[0], ln[1]
         if ln_dtype != torch.float32:

@@ -220,16 +220,17 @@ long long hnb_block_fwd_ws_bytes(int B, int L, int d, int ndir, int di, int N, i
 int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths, const float* ln_w, const float* ln_b,
                   const void* const* params, int B, int L, int d, int ndir, int di, int N, int H,
                   int act_dtype, int ssd_impl, void* out, void* ws, void* stream);
-/* backward: dout [B*L, d] (x_dtype) -> dx [B*L, d] (x_dtype) and the parameter gradients, ACCUMULATED into the fp32
- * arena `grads` of hnb_block_grad_floats() floats that the caller zero-fills.  offsets[9] (in floats) of that arena:
- * dWout [d, ndir*di] | dWin [ndir*dstride, d] (direction r = rows [r*dstride, +2di+2N+H)) | dconv_w [ndir,C,4] |
+/* backward: dout [B*L, d] (x_dtype) -> dx [B*L, d] (x_dtype) and the parameter gradients, written into the fp32 arena
+ * `grads` of hnb_block_grad_floats() floats (zero_grads != 0: the call clears the arena first on `stream`; 0: it
+ * ACCUMULATES into what the caller left there).  offsets[9] (in floats) of that arena:
+ * dWout [ndir][d, di] (one contiguous matrix per direction) | dWin [ndir*dstride, d] (direction r = rows [r*dstride, +2di+2N+H)) | dconv_w [ndir,C,4] |
  * dconv_b [ndir,C] | dnorm_w [ndir,di] | dA_log | dD | ddt_bias [ndir,H] | LayerNorm dgamma, dbeta [2,d].
  * scratch: hnb_block_bwd_ws_bytes() bytes, dead when the call returns. */
 long long hnb_block_bwd_ws_bytes(int B, int L, int d, int ndir, int di, int N, int H, int act_dtype, int ssd_impl);
 long long hnb_block_grad_floats(int B, int L, int d, int ndir, int di, int N, int H, long long* offsets);
 int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const int32_t* lengths, const float* ln_w,
                   const void* ws, int B, int L, int d, int ndir, int di, int N, int H, int act_dtype,
-                  int ssd_impl, void* dx, float* grads, void* scratch, void* stream);
+                  int ssd_impl, void* dx, float* grads, int zero_grads, void* scratch, void* stream);
 
 /* ---- dense projections (in_proj / out_proj / router W_q,W_k / proj_in,out) ---------------- */
 /* C[M,N] = op(A) op(B) (+ bias[N]) (+ R[M,N]) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
@@ -242,10 +243,22 @@ int hnb_gemm_bf16(const void* A, long long lda, int transA, const void* B, long 
                   int M, int N, int K, const float* bias, const void* R, long long ldr,
                   void* C, long long ldc, int c_dtype, int splitk, void* stream);
 
+/* The same with a column-blocked C: c_col_block > 0 stores C as N / c_col_block separate row-major [M, c_col_block]
+ * matrices (row stride ldc), c_block_stride elements apart -- the out-projection weight gradient of BOTH directions comes
+ * out of one GEMM as two contiguous [d, d_inner] matrices (mamba_ssm out_proj.weight layout, mamba_block.py:45-47).
+ * fp32 C only, no residual, c_col_block % 32 == 0. */
+int hnb_gemm_bf16_ex(const void* A, long long lda, int transA, const void* B, long long ldb, int transB,
+                     int M, int N, int K, const float* bias, const void* R, long long ldr,
+                     void* C, long long ldc, int c_dtype, int splitk, int c_col_block, long long c_block_stride,
+                     void* stream);
+
 /* Recommended split-K factor for hnb_gemm_bf16 on this (M, N, K): fills whole waves of the tile grid the library will
  * use.  > 1 means: zero-fill an fp32 C and pass the value as `splitk`.  (Weight gradients of the reference's
  * nn.Linear layers, src/dcasr/models/mamba_block.py:45-47 via mamba_ssm; K = tokens.) */
 int hnb_gemm_splitk_hint(int M, int N, int K);
+/* Which kernel hnb_gemm_bf16 picks for (M, N, K, splitk): 0 = single-CTA tiles, 1 = 2-CTA multicast of B,
+ * 2 = CTA-pair tiles (tcgen05.mma.cta_group::2).  Test / diagnosis aid: the choice is a cost model, not an argument. */
+int hnb_gemm_bf16_path(int M, int N, int K, int splitk);
 /* exact fp32 GEMM on CUDA cores (decode / fp32 parity path), same operand conventions */
 int hnb_gemm_f32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
                  int M, int N, int K, const float* bias, const float* R, long long ldr,

@@ -83,15 +83,15 @@ class DynamicChunkerRef(nn.Module):
             ones = x.new_ones(Bsz, L)
             if mask is not None:
                 ones = ones * mask.to(x.dtype)
-            return hnet_ref.ChunkRef(x, mask if mask is not None else torch.ones(Bsz, L, dtype=torch.bool),
-                                     ones, ones, torch.arange(L).expand(Bsz, L).clone(),
+            return hnet_ref.ChunkRef(x, mask if mask is not None else torch.ones(Bsz, L, dtype=torch.bool, device=x.device),
+                                     ones, ones, torch.arange(L, device=x.device).expand(Bsz, L).clone(),
                                      x.new_zeros(()), x.new_ones(()))
-        return hnet_ref.chunk_ref(x, self.router.W_q.weight, self.router.W_k.weight, self.N, mask)
+        return hnet_ref.chunk_vec(x, self.router.W_q.weight, self.router.W_k.weight, self.N, mask)
 
     def dechunk(self, z_proc, co):
         if self.identity:
             return z_proc
-        return hnet_ref.dechunk_ref(z_proc, co, self.ema_smoothing)
+        return hnet_ref.dechunk_vec(z_proc, co, self.ema_smoothing)
 
 
 class _Subsample(nn.Module):
@@ -179,7 +179,7 @@ class EncoderRef(nn.Module):
 
     def forward_from_subsampled(self, x, lengths):
         """The hot path proper: everything after ConvSubsampling4."""
-        mask = torch.arange(x.shape[1])[None, :] < lengths[:, None]
+        mask = torch.arange(x.shape[1], device=x.device)[None, :] < lengths[:, None]
         x_enc = self.enc(x, lengths)
         if self.arch_type == "A":
             co = self.chunk.chunk(x_enc, mask)

@@ -64,6 +64,28 @@ def test_gemm_bf16_vs_torch(ta, tb, M, N, K):
         assert rel_err(c3, ref) < 5e-5
 
 
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,sk", [(620, 512, 1024, 1), (1150, 768, 2048, 2), (640, 256, 4640, 1)])
+def test_gemm_bf16_cta_pair_path(ta, tb, M, N, K, sk):
+    """The cta_group::2 pair kernel directly (ADVICE r1): 256-wide tiles, an ODD number of row tiles (the last cluster's
+    second CTA owns no rows), >= 12 k-blocks per item, all four operand layouts, with and without split-K; the test
+    asserts that the library's cost model really picks the pair kernel for these shapes."""
+    from dcasr_b200 import ops
+    from dcasr_b200._lib import lib
+    assert lib().raw("gemm_bf16_path")(M, N, K, sk) == 2, "shape no longer routed to the CTA-pair kernel"
+    torch.manual_seed(0)
+    a = torch.randn((K, M) if ta else (M, K), device=DEV, dtype=torch.bfloat16)
+    b = torch.randn((K, N) if tb else (N, K), device=DEV, dtype=torch.bfloat16)
+    ref = (a.double().t() if ta else a.double()) @ (b.double() if tb else b.double().t())
+    c = ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb), out_dtype=torch.float32, splitk=sk)
+    assert rel_err(c, ref) < 5e-5
+    if sk == 1:
+        bias = torch.randn(N, device=DEV)
+        r = torch.randn(M, N, device=DEV, dtype=torch.bfloat16)
+        c2 = ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb), bias=bias, residual=r)
+        assert rel_err(c2, ref + bias + r.float()) < 5e-3
+
+
 def test_gemm_f32_vs_torch():
     from dcasr_b200 import ops
     torch.manual_seed(0)
@@ -332,9 +354,13 @@ def test_encoder_matches_reference_golden_fp32(path):
 
 
 @pytest.mark.parametrize("arch,N", [("A", 2), ("B", 4)])
-def test_encoder_bf16_autocast_vs_fp32_oracle(arch, N):
-    """Training precision: bf16 autocast on the CUDA path against the fp32 CPU oracle, 2e-2 relative."""
+def test_encoder_bf16_autocast_vs_fp32_oracle(arch, N, monkeypatch):
+    """Training precision at toy depth: bf16 autocast on the CUDA path against the FP32 CPU oracle (information about the
+    absolute error of the bf16 path; the bf16-vs-bf16 comparison at north_star's 2e-2 is
+    tests/test_gpu_baseline_configs.py::test_full_size_hot_path_bf16_vs_bf16_oracle_on_gpu).  Boundary decisions inside
+    the bf16 band are teacher-forced to the oracle's (tests/_util.py:force_in_band_boundaries): no skip."""
     import dcasr_b200 as dd
+    from _util import force_in_band_boundaries
     from oracle.encoder_ref import EncoderRef
     kw = dict(n_mels=80, d_outer=128, d_main=256, n_enc=2, n_main=2, n_dec=2, n_mid=1, arch_type=arch, N=N)
     ref = EncoderRef(**kw)
@@ -349,15 +375,13 @@ def test_encoder_bf16_autocast_vs_fp32_oracle(arch, N):
     x = x + 1.5 * torch.roll(x, 1, 1) * (torch.rand(B, L, 1) > 0.5)
     xr = x.clone().requires_grad_(True)
     o_ref = ref.forward_from_subsampled(xr, lengths)
+    forced = force_in_band_boundaries(monkeypatch, o_ref.boundaries, 2e-2)   # bf16 q,k: the reference's own bf16 path moves p by ~1e-2
     xg = x.to(DEV).requires_grad_(True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         o = enc.forward_hot_path(xg, lengths.to(DEV))
     assert o.features.dtype == torch.float32 and o.boundaries[0][0].dtype == torch.float32
-    p_ref, b_ref = o_ref.boundaries[0]
-    safe = (p_ref - 0.5).abs() > 2e-2          # bf16 q,k: the reference's own bf16 path moves p by ~1e-2
-    assert torch.equal(o.boundaries[0][1].cpu()[safe], b_ref[safe])
-    if not all(torch.equal(bg.cpu(), br) for (_, bg), (_, br) in zip(o.boundaries, o_ref.boundaries)):
-        pytest.skip("a boundary flipped inside the bf16 band: activations are not comparable frame by frame")
+    print("in-band boundary decisions forced per stage:", forced)
+    assert all(torch.equal(bg.cpu(), br) for (_, bg), (_, br) in zip(o.boundaries, o_ref.boundaries))
     mask = (torch.arange(L)[None] < lengths[:, None]).unsqueeze(-1)
     ferr = rel_err(o.features.cpu() * mask, o_ref.features * mask)
     print("bf16 feature rel err vs fp32 oracle:", ferr)
@@ -373,7 +397,7 @@ def test_encoder_bf16_autocast_vs_fp32_oracle(arch, N):
     big = [e for e in errs if e[2] >= 64]            # weight matrices, norm/conv vectors
     small = [e for e in errs if e[2] < 64]           # per-head scalars (A_log, D, dt_bias): sums with cancellation
     print("worst bf16 grad rel err: tensors", max(big), " per-head scalars", max(small))
-    assert max(big)[0] < 6e-2, max(big)     # medians are ~2.7e-2 (precision)
+    assert max(big)[0] < 6e-2, max(big)     # vs FP32 truth; medians are ~2.7e-2 (precision)
     assert max(small)[0] < 0.25, max(small)
 
 

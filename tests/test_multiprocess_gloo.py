@@ -32,6 +32,24 @@ def _worker(rank, world, port, out):
     st(X[idx]).pow(2).sum().backward()                          # a second step must reuse the buckets cleanly
     red()
     torch.save({k: p.grad.clone() for k, p in st.named_parameters()}, os.path.join(out, f"g{rank}.pt"))
+    # gradient accumulation (reference trainer accum_grad = 2): the first micro-batch under no_sync(), as with DDP
+    st.zero_grad(set_to_none=True)
+    half = len(idx) // 2 or 1
+    with red.no_sync():
+        st(X[idx[:half]]).pow(2).sum().backward()
+    st(X[idx[half:]] if len(idx) > half else X[idx]).pow(2).sum().backward()
+    red()
+    torch.save({k: p.grad.clone() for k, p in st.named_parameters()}, os.path.join(out, f"acc{rank}.pt"))
+    # a second backward WITHOUT no_sync() while buckets are in flight must raise, not publish partial sums
+    st.zero_grad(set_to_none=True)
+    st(X[idx]).pow(2).sum().backward()
+    try:
+        st(X[idx]).pow(2).sum().backward()
+        err = ""
+    except RuntimeError as e:
+        err = str(e)
+    red()                                                        # drains the collectives launched by the first pass
+    torch.save(err, os.path.join(out, f"err{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,6 +74,21 @@ def test_sharded_gradients_equal_mean_of_shards(tmp_path):
         acc = gr if acc is None else {k: acc[k] + gr[k] for k in gr}
     for k in g0:
         assert torch.allclose(g0[k], acc[k] / world, rtol=1e-5, atol=1e-6), k
+
+
+def test_accumulated_micro_batches_and_double_backward_guard(tmp_path):
+    """accum_grad = 2 through no_sync() gives the mean over ranks of the SUM over micro-batches (what DDP gives), and a
+    second un-guarded backward is refused (it used to all-reduce a partial sum silently)."""
+    world, port = 2, 29533
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a0, a1 = torch.load(tmp_path / "acc0.pt"), torch.load(tmp_path / "acc1.pt")
+    g0 = torch.load(tmp_path / "g0.pt")
+    for k in a0:
+        assert torch.equal(a0[k], a1[k]), k
+        # x -> sum of squares is additive over utterances: two micro-batches that partition the shard give the shard's gradient
+        assert torch.allclose(a0[k], g0[k], rtol=1e-4, atol=1e-5), k
+    for r in range(world):
+        assert "no_sync" in torch.load(tmp_path / f"err{r}.pt")
 
 
 def test_shard_indices_cover_and_balance():

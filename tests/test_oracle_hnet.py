@@ -18,14 +18,20 @@ def _t(a, grad=False):
     return t.requires_grad_(True) if grad else t
 
 
+FORMS = {"per_frame": (hnet_ref.chunk_ref, hnet_ref.dechunk_ref, hnet_ref.ema_ref),
+         "vectorised": (hnet_ref.chunk_vec, hnet_ref.dechunk_vec, hnet_ref.ema_vec)}
+
+
+@pytest.mark.parametrize("form", sorted(FORMS))
 @pytest.mark.parametrize("path", HNET, ids=[os.path.basename(p)[:-4] for p in HNET])
-def test_hnet_oracle_matches_reference(path):
+def test_hnet_oracle_matches_reference(path, form):
+    chunk_fn, dechunk_fn, _ = FORMS[form]
     g = np.load(path)
     x, Wq, Wk = _t(g["x"], True), _t(g["Wq"], True), _t(g["Wk"], True)
     mask = _t(g["mask"]) if "mask" in g else None
     N = float(g["N"])
     N = int(N) if N == int(N) else N
-    co = hnet_ref.chunk_ref(x, Wq, Wk, N, mask)
+    co = chunk_fn(x, Wq, Wk, N, mask)
     p_ref, b_ref = _t(g["p"]), _t(g["b"])
     assert max_err(co.p, p_ref) < 1e-6
     safe = (p_ref - 0.5).abs() > 1e-4                       # north_star: exact outside the band
@@ -38,7 +44,7 @@ def test_hnet_oracle_matches_reference(path):
     assert max_err(co.ratio_loss, _t(g["ratio_loss"])) < 1e-6
     assert max_err(co.kept_fraction, _t(g["kept_fraction"])) < 1e-7
     z_proc = _t(g["z_proc"], True)
-    y = hnet_ref.dechunk_ref(z_proc, co, bool(g["ema"]))
+    y = dechunk_fn(z_proc, co, bool(g["ema"]))
     assert max_err(y, _t(g["y"])) < 2e-5
     loss = (y * _t(g["w"])).sum() + (co.z * _t(g["wz"])).sum() + 0.03 * co.ratio_loss
     loss.backward()
@@ -47,11 +53,12 @@ def test_hnet_oracle_matches_reference(path):
         assert max_err(t.grad, ref) < 1e-4 * max(1.0, ref.abs().max().item()), name
 
 
+@pytest.mark.parametrize("form", sorted(FORMS))
 @pytest.mark.parametrize("path", EMA, ids=[os.path.basename(p)[:-4] for p in EMA])
-def test_ema_oracle_matches_reference(path):
+def test_ema_oracle_matches_reference(path, form):
     g = np.load(path)
     x, p = _t(g["x"], True), _t(g["p"], True)
-    out = hnet_ref.ema_ref(x, p)
+    out = FORMS[form][2](x, p)
     assert max_err(out, _t(g["out"])) < 1e-5
     (out * _t(g["w"])).sum().backward()
     assert max_err(x.grad, _t(g["gx"])) < 1e-4
@@ -63,6 +70,6 @@ def test_ema_oracle_matches_reference(path):
 
 def test_ema_single_frame_and_identity_edge():
     x = torch.randn(2, 1, 4)
-    assert torch.equal(hnet_ref.ema_ref(x, torch.ones(2, 1)), x)
+    assert torch.equal(hnet_ref.ema_ref(x, torch.ones(2, 1)), x) and torch.equal(hnet_ref.ema_vec(x, torch.ones(2, 1)), x)
     p, b = hnet_ref.router_ref(torch.ones(1, 9, 6), torch.eye(6), torch.eye(6))
     assert p[0, 0] == 1 and torch.allclose(p[0, 1:], torch.zeros(8), atol=1e-6) and b[0, 1:].sum() == 0
