@@ -16,6 +16,12 @@ this file restates its *published* forward:
 Parameter names / shapes / ``_no_weight_decay`` tags equal the upstream module so
 reference checkpoints load (dimension formulas: src/dcasr/eval/efficiency.py:49-57).
 
+Under CUDA autocast (the reference's training precision, src/dcasr/training/trainer.py:187-190) the upstream conv1d /
+SSD / gated-norm kernels are opaque custom ops: autocast decides the dtype of what goes IN (bf16 zxbcdt from the bf16
+in_proj GEMM) and they return that dtype, computing in fp32 inside.  `forward` therefore runs those three stages with
+autocast disabled on the bf16-rounded tensors and rounds their results back (conv output, y, normed y) -- autocast must
+not be left to cast the einsums of this restatement, which would add roundings the reference's path does not have.
+
 PARITY UNPINNED by the reference (no numeric vectors exist for this path); see
 ``oracle/__init__.py``.  Cross-checks live in tests/test_oracle_mamba2.py.
 """
@@ -146,18 +152,20 @@ class Mamba2Ref(nn.Module):
     def forward(self, u: torch.Tensor) -> torch.Tensor:
         Bsz, L, _ = u.shape
         di, N, H, P = self.d_inner, self.d_state, self.nheads, self.headdim
-        zxbcdt = self.in_proj(u)
-        z, xBC, dt = torch.split(zxbcdt, [di, di + 2 * N, H], dim=-1)
-        xBC = causal_conv1d_silu(xBC, self.conv1d.weight, self.conv1d.bias)
-        x, Bm, Cm = torch.split(xBC, [di, N, N], dim=-1)
-        cd = torch.promote_types(u.dtype, torch.float32)          # scan math in >= fp32
-        dtp = F.softplus(dt.to(cd) + self.dt_bias.to(cd))
-        A = -torch.exp(self.A_log.to(cd))
-        xh = x.to(cd).reshape(Bsz, L, H, P)
-        if self.mode == "sequential":
-            y = ssd_sequential(xh, dtp, A, Bm.to(cd), Cm.to(cd), self.D.to(cd))
-        else:
-            y = ssd_chunked(xh, dtp, A, Bm.to(cd), Cm.to(cd), self.D.to(cd), self.chunk_size)
-        y = y.reshape(Bsz, L, di)
-        y = gated_rmsnorm(y, z.to(cd), self.norm.weight.to(cd), self.norm.eps).to(u.dtype)
+        zxbcdt = self.in_proj(u)                                  # bf16 under autocast
+        act = zxbcdt.dtype
+        cd = torch.promote_types(act, torch.float32)              # kernel-internal math in >= fp32
+        with torch.autocast(u.device.type, enabled=False):
+            z, xBC, dt = torch.split(zxbcdt, [di, di + 2 * N, H], dim=-1)
+            xBC = causal_conv1d_silu(xBC.to(cd), self.conv1d.weight.to(cd), self.conv1d.bias.to(cd)).to(act)
+            x, Bm, Cm = torch.split(xBC, [di, N, N], dim=-1)
+            dtp = F.softplus(dt.to(cd) + self.dt_bias.to(cd))
+            A = -torch.exp(self.A_log.to(cd))
+            xh = x.to(cd).reshape(Bsz, L, H, P)
+            if self.mode == "sequential":
+                y = ssd_sequential(xh, dtp, A, Bm.to(cd), Cm.to(cd), self.D.to(cd))
+            else:
+                y = ssd_chunked(xh, dtp, A, Bm.to(cd), Cm.to(cd), self.D.to(cd), self.chunk_size)
+            y = y.reshape(Bsz, L, di).to(act)
+            y = gated_rmsnorm(y.to(cd), z.to(cd), self.norm.weight.to(cd), self.norm.eps).to(act)
         return self.out_proj(y)
