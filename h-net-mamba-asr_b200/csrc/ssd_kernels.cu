@@ -569,11 +569,11 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
                    int di, int N, int H, void* y, void* states, void* stream, int variant);
 int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
                    const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
-                   void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, void* stream);
-int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H);
+                   void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, void* stream, int variant);
+int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H, int variant);
 
 extern "C" int hnb_ssd_dbc_parts(int ndir, int B, int L, int H, int impl) {
-  return impl == 1 ? hnb_ssd_dbc_parts_tc(ndir, B, L, H) : 1;
+  return (impl == 1 || impl == 3) ? hnb_ssd_dbc_parts_tc(ndir, B, L, H, impl == 3 ? 1 : 0) : 1;
 }
 
 template <typename T>
@@ -604,7 +604,7 @@ extern "C" int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const 
   int rc = ssd_check("ssd_fwd", ndir, B, L, di, N, H);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1 || impl == 2) {                       // 2: the one-CTA-per-SM forward kernel (same outputs, kept under test)
+  if (impl == 1 || impl == 2 || impl == 3) {          // 2: the one-CTA-per-SM forward kernel (same outputs, kept under test); 3: as 1
     HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_fwd: the tcgen05 path takes bf16 activations");
     return hnb_ssd_fwd_tc(xconv, dt, A_log, Dskip, ndir, B, L, di, N, H, y, states, stream, impl == 2 ? 1 : 0);
   }
@@ -652,10 +652,10 @@ extern "C" int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int
   int rc = ssd_check("ssd_bwd", ndir, B, L, di, N, H);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1) {
+  if (impl == 1 || impl == 3) {                        // 1: fused dx + dB/dC kernel; 3: the three-kernel backward (kept under test)
     HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_bwd: the tcgen05 path takes bf16 activations");
     return hnb_ssd_bwd_tc(dy, xconv, y, dt, A_log, Dskip, states, ndir, B, L, di, N, H, dxc, dBC, dbc_parts, ddt, dA_log,
-                          dD, ws2, stream);
+                          dD, ws2, stream, impl == 3 ? 1 : 0);
   }
   HNB_CHECK_ARG(dbc_parts == 1, "ssd_bwd: the CUDA-core path writes one dBC part");
   if (dtype == HNB_BF16)

@@ -669,6 +669,8 @@ ssd_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
 struct BwdParams {
   const float* dt; const float* A_log; const float* Dskip;
   const float* tables;           // [ndir*B, H, nc, TAB_FLOATS]  (built by the forward)
+  const __nv_bfloat16* xconv;    // [ndir*B*L, di + 2N]  (fused kernel: x and dY rows re-read for epilogue B, L2 hits)
+  const __nv_bfloat16* dy;       // [ndir*B*L, di]
   __nv_bfloat16* gstates;        // [ndir*B, H, nc, 128, 64]
   __nv_bfloat16* dxc;            // [ndir*B*L, di]
   __nv_bfloat16* dBC;            // [HG][ndir*B*L, 2N]: one partial sum per head group (summed by the conv backward)
@@ -1317,6 +1319,461 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
+
+// ---- 2 + 3 fused: dx / ddt / dA / dD AND dB / dC in ONE pass over (row, chunk [, head group]) ---------------------
+// The two kernels above read x | B | C, dY, the chunk states, the state gradients and the tables twice, compute
+// R = dY X^T twice and the decay matrix L twice (498 MB of DRAM traffic for 147 MB of algorithmic bytes, two latency
+// chains per head).  Here a work item loads C | B once, then per head X, dY, S_in, Gst and the tables once:
+//     G = C B^T, R = dY X^T                               (TMEM 256..383, 384..511)
+//     epilogue A: one pass over the lower triangle builds BOTH score tiles from one decay evaluation:
+//         K = G o L  -> smem (bf16),   W = R o L o dt -> smem (bf16),   row sums of W o G
+//         dYs = e^{cs} dY, Xw = w X  -> TMEM as bf16 A operands (448..479, 480..511): no scaled copies in shared memory
+//     du1 = K^T dY, du2 = B Gst, Yo = C S_in              (TMEM 256..319, 320..383, 384..447: G and R are dead)
+//     epilogue B (dx, ddt terms) takes these into registers, and only THEN
+//     dC += W B + dYs S_in^T,  dB += W^T C + Xw Gst^T     (TMEM 0..127, 128..255, accumulated over the item's heads)
+// are put on the tensor pipe: tcgen05.ld / tcgen05.st queue behind in-flight MMAs (measured: with the accumulation issued
+// early, epilogue B's three TMEM loads took 2.5 k cycles), so the accumulation runs while epilogue B computes and while
+// the next head-step's G, R are being set up.  G is recomputed per head (8 MMAs on an otherwise idle pipe) so that its
+// TMEM columns can be reused.
+// Who issues: an issuing thread stalls on the tensor queue (60 MMAs = ~3.5 k cycles per head-step).  In the first
+// version of this kernel that stall sat on everybody's critical path (15.3 k cycles per head-step: no faster than the two
+// kernels it replaces); a 17th, issue-only warp rounds the CTA up to 20 warps' worth of registers (96 per thread, 840 B
+// of spills).  So two lanes of two LIGHT compute warps (TMEM lane quarter 0: one 32 x 32 block of the triangular score
+// tile instead of four) issue, each at a point where its warp would be waiting for the tensor pipe anyway: lane 0 of
+// warp 8 issues every TMA copy, G | R and the du / Yo group; lane 0 of warp 4 issues the accumulation group.
+// Shared memory: 12 tiles (192 KB) + tables + partial sums.
+constexpr int DF_OFF_C = 0, DF_OFF_B = 2 * HALF, DF_OFF_X = 4 * HALF, DF_OFF_DY = 5 * HALF, DF_OFF_S = 6 * HALF,
+              DF_OFF_G = 7 * HALF, DF_OFF_K = 8 * HALF, DF_OFF_W = 10 * HALF, DF_OFF_TAB = 12 * HALF;
+constexpr int DF_OFF_EXTRA = DF_OFF_TAB + 2 * TAB_BYTES;
+constexpr int DF_OFF_BAR = DF_OFF_EXTRA + 2 * EXTRA_FLOATS * 4;
+constexpr int DF_SMEM = DF_OFF_BAR + 128 + 1024;
+constexpr int DF_THREADS = BWD_THREADS;
+static_assert(DF_SMEM <= 232448, "fused SSD backward: shared memory");
+static_assert(DF_OFF_EXTRA % 16 == 0 && DF_OFF_BAR % 8 == 0, "fused SSD backward: alignment");
+
+template <bool DBG>
+__global__ void __launch_bounds__(DF_THREADS, 1)
+ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                        const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
+                        const BwdParams p) {
+  constexpr int NT = BWD_THREADS, NCG = NT / 128;
+  static_assert(NCG == 4, "the balanced score-tile split assumes 16 compute warps");
+  constexpr uint32_t TM_DC = 0, TM_DB = 128, TM_G = 256, TM_R = 384, TM_DU1 = 256, TM_DU2 = 320, TM_YO = 384,
+                     TM_DYS = 448, TM_XW = 480;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
+  uint8_t* sC = base + DF_OFF_C; uint8_t* sB = base + DF_OFF_B; uint8_t* sX = base + DF_OFF_X;
+  uint8_t* sdY = base + DF_OFF_DY; uint8_t* sS = base + DF_OFF_S; uint8_t* sG = base + DF_OFF_G;
+  uint8_t* sK = base + DF_OFF_K; uint8_t* sW = base + DF_OFF_W;
+  float* tabs = reinterpret_cast<float*>(base + DF_OFF_TAB);
+  float* xtra = reinterpret_cast<float*>(base + DF_OFF_EXTRA);
+  uint64_t* bar_cb = reinterpret_cast<uint64_t*>(base + DF_OFF_BAR);
+  uint64_t* bar_x = bar_cb + 1;     // TMA: X of the head-step has landed
+  uint64_t* bar_dy = bar_cb + 2;    // TMA: dY + tables
+  uint64_t* bar_sg = bar_cb + 3;    // TMA: S_in + Gst
+  uint64_t* bar_gr = bar_cb + 4;    // MMA: G, R retired
+  uint64_t* bar_du1 = bar_cb + 5;   // MMA: du1 retired (dY tile free)
+  uint64_t* bar_du = bar_cb + 6;    // MMA: du1, du2, Yo retired
+  uint64_t* bar_acc = bar_cb + 7;   // MMA: dC / dB accumulation of the head-step retired
+  uint64_t* bar_kw = bar_cb + 8;    // 16 compute warps: K, W, dYs, Xw written; X tile and G, R consumed
+  uint64_t* bar_ldb = bar_cb + 9;   // 16 compute warps: epilogue B holds du1, du2, Yo in registers
+  uint64_t* bar_out = bar_cb + 10;  // 16 compute warps: dB | dC of the item have left TMEM
+  uint64_t* bar_2b = bar_cb + 11;   // the accumulation group is on the tensor pipe: the next G | R may be queued behind it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_cb + 12);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, cg = (warp >> 2) & 3, row = lq * 32 + lane;
+  if (tid == 0) {
+    umma::prefetch_tmap(&tmX); umma::prefetch_tmap(&tmDY); umma::prefetch_tmap(&tmS); umma::prefetch_tmap(&tmG);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) umma::mbar_init(bar_cb + i, 1);
+    umma::mbar_init(bar_kw, NT / 32); umma::mbar_init(bar_ldb, NT / 32); umma::mbar_init(bar_out, NT / 32);
+    umma::mbar_init(bar_2b, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < 4 * HALF / 16; i += DF_THREADS) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);   // sK | sW: finite padding rows
+  umma::fence_async_smem();
+  umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc, HG = p.HG, Hh = H / HG, n_items = p.ndirB * nc * HG;
+
+  const bool isA = tid == 8 * 32;                                      // TMA, G | R, du1 | du2 | Yo
+  const bool isB = tid == 4 * 32;                                      // dC | dB accumulation
+  constexpr uint32_t i_kk128 = umma::make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t i_km128 = umma::make_idesc_bf16(128, 128, 0, 1);
+  constexpr uint32_t i_mm128 = umma::make_idesc_bf16(128, 128, 1, 1);
+  constexpr uint32_t i_km64 = umma::make_idesc_bf16(128, 64, 0, 1);
+  constexpr uint32_t i_mm64 = umma::make_idesc_bf16(128, 64, 1, 1);
+  auto load_cb = [&](int item) {
+    int db, c; p.chunk_of(p.dHG.div(item), db, c);
+    umma::mbar_expect_tx(bar_cb, 4 * HALF);
+    umma::tma_load_3d(sC, &tmX, bar_cb, di + TN, c * TQ, db);
+    umma::tma_load_3d(sC + HALF, &tmX, bar_cb, di + TN + 64, c * TQ, db);
+    umma::tma_load_3d(sB, &tmX, bar_cb, di, c * TQ, db);
+    umma::tma_load_3d(sB + HALF, &tmX, bar_cb, di + 64, c * TQ, db);
+  };
+  auto load_x = [&](int item, int hh) {
+    int bs, hg, db, c; p.dHG.divmod(item, bs, hg); p.chunk_of(bs, db, c);
+    umma::mbar_expect_tx(bar_x, HALF);
+    umma::tma_load_3d(sX, &tmX, bar_x, (hg * Hh + hh) * TP, c * TQ, db);
+  };
+  auto load_dy = [&](int item, int hh, int buf) {
+    int bs, hg, db, c; p.dHG.divmod(item, bs, hg); p.chunk_of(bs, db, c);
+    const int h = hg * Hh + hh;
+    const int srow = ((db * H + h) * nc) + c;
+    umma::mbar_expect_tx(bar_dy, HALF + TAB_BYTES);
+    umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)srow * TAB_FLOATS, TAB_BYTES, bar_dy);
+    umma::tma_load_3d(sdY, &tmDY, bar_dy, h * TP, c * TQ, db);
+  };
+  auto load_sg = [&](int item, int hh) {
+    int bs, hg, db, c; p.dHG.divmod(item, bs, hg); p.chunk_of(bs, db, c);
+    const int srow = (((db * H + hg * Hh + hh) * nc) + c) * TN;
+    umma::mbar_expect_tx(bar_sg, 2 * HALF);
+    umma::tma_load_2d(sS, &tmS, bar_sg, 0, srow);
+    umma::tma_load_2d(sG, &tmG, bar_sg, 0, srow);
+  };
+  if (isA && blockIdx.x < n_items) { load_cb(blockIdx.x); load_x(blockIdx.x, 0); load_dy(blockIdx.x, 0, 0); load_sg(blockIdx.x, 0); }
+  {
+    uint32_t iseq = 0, seq = 0;                                        // item / head-step sequence numbers of this CTA
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
+      int bs, hg, db, c; p.dHG.divmod(it, bs, hg); p.chunk_of(bs, db, c);
+      const int dir = p.dB.div(db);
+      const int q0 = c * TQ, qv = min(TQ, L - q0);
+      const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;           // row blocks / k-steps that hold valid frames
+      const long long row0 = (long long)db * L + q0;
+      for (int hh = 0; hh < Hh; ++hh, ++seq) {
+        const int h = hg * Hh + hh;
+        const uint32_t par = seq & 1;
+        int nit = it, nh = hh + 1;                                     // the head-step after this one
+        if (nh == Hh) { nit = it + gridDim.x; nh = 0; }
+        const float* tab = tabs + (seq & 1) * TAB_FLOATS;
+        const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
+        const float* s_eq = tab + 4 * TQ;
+        float* s_dcsA = xtra + (seq & 1) * EXTRA_FLOATS;              // [4][128]  d cs_t, row sums of W o G (epilogue A)
+        float* s_dcsB = s_dcsA + 4 * TQ;                              // [4][128]  d cs_q, column and state terms (epilogue B)
+        float* s_ddtx = s_dcsB + 4 * TQ;                              // [4][128]  <du_q, x_q>
+        float* s_pdot = s_ddtx + 4 * TQ;                              // [NT] <Gst, S_in>   (per thread, summed by the tail warp)
+        float* s_psc = s_pdot + NT;                                   // [NT] d cs_last from the chunk state
+        float* s_pdd = s_psc + NT;                                    // [NT] dD
+        const float A = -__expf(p.A_log[dir * H + h]);
+        const float Dh = p.Dskip[dir * H + h];
+        const bool tmr = DBG && p.dbg && blockIdx.x == 0 && qv == TQ && (tid == 0 || tid == NT - 31);
+        long long* dbg = p.dbg + (tid == 0 ? 0 : 16);
+        const long long tk0 = HNB_CLK();
+        if (isA) {
+          if (hh == 0) {
+            if (seq > 0) {                                             // C, B, S, Gst are free once the last accumulation retired
+              umma::mbar_wait(bar_acc, par ^ 1);
+              load_cb(it); load_sg(it, 0);
+            }
+            umma::mbar_wait(bar_cb, iseq & 1);
+          }
+          umma::mbar_wait(bar_x, par); umma::mbar_wait(bar_dy, par);
+          if (seq > 0) umma::mbar_wait(bar_2b, par ^ 1);               // G | R must enter the pipe BEHIND the last accumulation group
+          umma::tc_fence_after();
+          // ---- group 1: G = C B^T, R = dY X^T.  They overwrite du1 | du2 | Yo (in registers since bar_ldb of the last
+          //      head-step) and dYs | Xw (operands of the accumulation issued before them: the pipe runs in order)
+  #pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+            umma::mma_bf16_ss(tmem + TM_G, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024), i_kk128, kb > 0);
+          }
+  #pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+            umma::mma_bf16_ss(tmem + TM_R, umma::make_smem_desc(umma::smem_u32(sdY) + kb * 32, 16, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), i_kk128, kb > 0);
+          umma::mma_commit(bar_gr);
+          if (hh > 0) {                                                // same item: S, Gst of this head once the last accumulation retired
+            umma::mbar_wait(bar_acc, par ^ 1);
+            load_sg(it, hh);
+          }
+        }
+        umma::mbar_wait(bar_x, par); umma::mbar_wait(bar_dy, par);     // X, dY and the tables are visible to this thread
+        if (seq > 0) umma::mbar_wait(bar_acc, par ^ 1);                // the previous head-step no longer reads sK / sW
+        umma::mbar_wait(bar_gr, par);
+        umma::tc_fence_after();
+        const long long tk1 = HNB_CLK();
+        // ---- epilogue A (thread = row t, 8 of every 32 columns): K and W from ONE decay evaluation
+        const bool live = (row >> 5) < nblk;                           // (warp-uniform) padding rows: sK / sW rows stay finite (zeroed once)
+        if (!live) {
+          s_dcsA[cg * TQ + row] = 0.f;
+        } else {
+          const int t = row, I = t >> 5;
+          float acc = 0.f;
+          const float cs_t = tab[t], e_ref = I > 0 ? __expf(cs_t - tab[32 * I - 1]) : 0.f;
+          // two passes of two column blocks: 32 instead of 64 live accumulator values per thread (the kernel is at
+          // its 128-register ceiling; spills cost L2 round trips here -- with 227 KB of shared memory there is hardly any L1)
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            float g[2][8], r[2][8];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+              if (2 * kh + kk <= I) {
+                umma::tmem_ld8(t_lane + TM_G + (uint32_t)(32 * (2 * kh + kk) + 8 * cg), g[kk]);
+                umma::tmem_ld8(t_lane + TM_R + (uint32_t)(32 * (2 * kh + kk) + 8 * cg), r[kk]);
+              }
+            if (2 * kh <= I) umma::tmem_ld_wait();
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const int k = 2 * kh + kk, s0 = 32 * k + 8 * cg;
+              const uint32_t so = kh * HALF + swz(t, 4 * kk + cg);
+              if (k <= I) {
+                float l[8], d8[8];
+                decay8(l, t, I, k, s0, cs_t, e_ref, tab);
+                load8(d8, s_dt + s0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  g[kk][j] *= l[j];                                    // K
+                  const float rd = r[kk][j] * d8[j];
+                  r[kk][j] = rd * l[j];                                // W
+                  // the row sums must use K exactly as the tensor core will see it (bf16): the column sums come out of
+                  // du1 = K^T dY, and the two cancel in the cumulative sum -- any rounding asymmetry would survive
+                  acc += rd * __bfloat162float(__float2bfloat16_rn(g[kk][j]));
+                }
+                *reinterpret_cast<uint4*>(sK + so) = pack8(g[kk]);
+                *reinterpret_cast<uint4*>(sW + so) = pack8(r[kk]);
+              } else {
+                *reinterpret_cast<uint4*>(sK + so) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(sW + so) = make_uint4(0, 0, 0, 0);
+              }
+            }
+          }
+          s_dcsA[cg * TQ + t] = acc;
+        }
+        // The TMEM copies below overwrite R columns 64 + 8 cg .. +7 and 96 + 8 cg .. +7 of this warp's lane quarter: exactly
+        // the strips of column blocks 2 and 3 that THIS warp has just read (or never reads) -- program order suffices.
+        // scaled copies as TMEM operands: dYs = e^{cs_t} dY, Xw = w_q X  (bf16 pairs, A operands of the K = 64 MMAs),
+        // from this thread's 16 columns of its x and dY rows
+        {
+          const float ecs_t = s_ecs[row], w_q = s_w[row];
+          uint32_t pk[8];
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            unpack8(*reinterpret_cast<const uint4*>(sdY + swz(row, 2 * cg + k)), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] *= ecs_t;
+            const uint4 q4 = pack8(v);
+            pk[4 * k] = q4.x; pk[4 * k + 1] = q4.y; pk[4 * k + 2] = q4.z; pk[4 * k + 3] = q4.w;
+          }
+          umma::tmem_st8(t_lane + TM_DYS + (uint32_t)(8 * cg), pk);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            unpack8(*reinterpret_cast<const uint4*>(sX + swz(row, 2 * cg + k)), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] *= w_q;
+            const uint4 q4 = pack8(v);
+            pk[4 * k] = q4.x; pk[4 * k + 1] = q4.y; pk[4 * k + 2] = q4.z; pk[4 * k + 3] = q4.w;
+          }
+          umma::tmem_st8(t_lane + TM_XW + (uint32_t)(8 * cg), pk);
+          umma::tmem_st_wait();
+        }
+        const long long tk2 = HNB_CLK();
+        umma::fence_async_smem(); umma::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bar_kw);                      // K, W, dYs, Xw written; G, R, X consumed
+        if (isA) {                                                     // ---- MMA group 2a: what epilogue B needs
+          umma::mbar_wait(bar_kw, par);
+          umma::tc_fence_after();
+          umma::mbar_wait(bar_sg, par);
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb)                               // du1 = K^T dY   (k = time: valid frames only)
+            if (kb < nkb)
+              umma::mma_bf16_ss(tmem + TM_DU1, umma::make_smem_desc(umma::smem_u32(sK) + kb * 2048, HALF, 1024),
+                                umma::make_smem_desc(umma::smem_u32(sdY) + kb * 2048, 1024, 1024), i_mm64, kb > 0);
+          umma::mma_commit(bar_du1);
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {                             // du2 = B Gst
+            const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+            umma::mma_bf16_ss(tmem + TM_DU2, umma::make_smem_desc(umma::smem_u32(sB) + o, 16, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sG) + kb * 2048, 1024, 1024), i_km64, kb > 0);
+          }
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {                             // Yo = C S_in (unscaled)
+            const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+            umma::mma_bf16_ss(tmem + TM_YO, umma::make_smem_desc(umma::smem_u32(sC) + o, 16, 1024),
+                              umma::make_smem_desc(umma::smem_u32(sS) + kb * 2048, 1024, 1024), i_km64, kb > 0);
+          }
+          umma::mma_commit(bar_du);
+        }
+        // while the second MMA group runs: the decay term e^{cs_last} <Gst, S_in>
+        umma::mbar_wait(bar_sg, par);
+        {
+          float dot = 0.f;
+          for (int i = tid; i < TQ * 8; i += NT) {                     // same swizzle on both tiles: elementwise product
+            float a[8], b[8];
+            unpack8(reinterpret_cast<const uint4*>(sS)[i], a);
+            unpack8(reinterpret_cast<const uint4*>(sG)[i], b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dot += a[k] * b[k];
+          }
+          s_pdot[tid] = dot;                                           // scaled by e^{cs_last} in the tail
+        }
+        const long long tk3 = HNB_CLK();
+        umma::mbar_wait(bar_du, par);
+        umma::tc_fence_after();
+        const long long tk4 = HNB_CLK();
+        // ---- epilogue B (thread = row q, 16 of the 64 columns): dx, and the remaining d cs terms
+        const int q = row;
+        float d1[16], d2[16], yo[16];
+        uint4 xr4[2], dr4[2];                                          // this thread's 16 columns of its x and dY rows
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          xr4[k] = *reinterpret_cast<const uint4*>(sX + swz(row, 2 * cg + k));
+          dr4[k] = *reinterpret_cast<const uint4*>(sdY + swz(row, 2 * cg + k));
+        }
+        if (live) {
+          umma::tmem_ld16(t_lane + TM_DU1 + 16u * cg, d1);
+          umma::tmem_ld16(t_lane + TM_DU2 + 16u * cg, d2);
+          umma::tmem_ld16(t_lane + TM_YO + 16u * cg, yo);
+          umma::tmem_ld_wait();
+        }
+        umma::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bar_ldb);                     // the accumulation (and the next G, R) may go on the pipe
+        if (isA && nit < n_items) {                                    // X, dY tiles are free: du1 retired, every thread holds its rows
+          umma::mbar_wait(bar_ldb, par);
+          load_x(nit, nh); load_dy(nit, nh, (seq & 1) ^ 1);
+        }
+        if (isB) {                                                     // ---- MMA group 2b: accumulate dC, dB over the item's heads
+          umma::mbar_wait(bar_ldb, par);
+          if (hh == 0 && iseq > 0) umma::mbar_wait(bar_out, (iseq - 1) & 1);   // the last item's dB | dC have left TMEM
+          umma::tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {                             // dC += W B        (k = time q: valid frames only)
+            const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
+            if (kb < nkb)
+              umma::mma_bf16_ss(tmem + TM_DC, umma::make_smem_desc(umma::smem_u32(sW) + o, 16, 1024),
+                                umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024), i_km128, (hh > 0 || kb > 0));
+          }
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)                               // dC += (e^{cs} dY) S_in^T
+            umma::mma_bf16_ts(tmem + TM_DC, tmem + TM_DYS + 8 * kb,
+                              umma::make_smem_desc(umma::smem_u32(sS) + kb * 32, 16, 1024), i_kk128, 1u);
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb)                               // dB += W^T C      (k = time t: valid frames only)
+            if (kb < nkb)
+              umma::mma_bf16_ss(tmem + TM_DB, umma::make_smem_desc(umma::smem_u32(sW) + kb * 2048, HALF, 1024),
+                                umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024), i_mm128, (hh > 0 || kb > 0));
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)                               // dB += (w X) Gst^T
+            umma::mma_bf16_ts(tmem + TM_DB, tmem + TM_XW + 8 * kb,
+                              umma::make_smem_desc(umma::smem_u32(sG) + kb * 32, 16, 1024), i_kk128, 1u);
+          umma::mma_commit(bar_acc);
+          umma::mbar_arrive(bar_2b);
+        }
+        const long long tk5 = HNB_CLK();
+        if (!live) {
+          s_dcsB[cg * TQ + q] = 0.f; s_ddtx[cg * TQ + q] = 0.f;
+          s_psc[tid] = 0.f; s_pdd[tid] = 0.f;
+        } else {
+          const float eq = s_eq[q], dtq = s_dt[q];
+          float col = 0.f, sc = 0.f, dux = 0.f, dd = 0.f, yd = 0.f;
+          float o[16], xv[16], dv[16];
+          unpack8(xr4[0], xv); unpack8(xr4[1], xv + 8);
+          unpack8(dr4[0], dv); unpack8(dr4[1], dv + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float du = d1[j] + eq * d2[j];
+            o[j] = dtq * du + Dh * dv[j];
+            col += d1[j] * xv[j];
+            sc += d2[j] * xv[j];
+            dux += du * xv[j];
+            dd += dv[j] * xv[j];
+            yd += dv[j] * yo[j];
+          }
+          if (q < qv) {
+            __nv_bfloat16* og = p.dxc + (row0 + q) * di + h * TP + 16 * cg;
+            *reinterpret_cast<uint4*>(og) = pack8(o);
+            *reinterpret_cast<uint4*>(og + 8) = pack8(o + 8);
+          }
+          col *= dtq; sc *= dtq * eq;
+          s_dcsB[cg * TQ + q] = s_ecs[q] * yd - (col + sc);            // + e^{cs_t} <dY_t, (C S_in)_t>: the state path's row term
+          s_ddtx[cg * TQ + q] = dux;
+          s_psc[tid] = sc; s_pdd[tid] = dd;
+        }
+        const long long tk6 = HNB_CLK();
+        // partial sums of the head-step complete: only the tail warp waits for everybody, the others go on
+        if (warp == 4 * (NCG - 1)) named_sync(1, NT);
+        else asm volatile("bar.arrive 1, %0;" ::"r"(NT) : "memory");
+        if (tmr) {
+          const long long tk7 = HNB_CLK();
+          dbg[0] += tk1 - tk0; dbg[1] += tk2 - tk1; dbg[2] += tk3 - tk2; dbg[3] += tk4 - tk3; dbg[4] += tk5 - tk4;
+          dbg[5] += tk6 - tk5; dbg[6] += tk7 - tk6; dbg[9] += 1;
+        }
+        // ---- reverse inclusive cumsum of d cs over the chunk -> ddt, dA_log: ONE warp (lane l owns frames 4l..4l+3);
+        //      every other warp goes on to the next head-step
+        if (warp == 4 * (NCG - 1)) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f}, ddx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int gI = 0; gI < NCG; ++gI) {
+            const float4 a = *reinterpret_cast<const float4*>(s_dcsA + gI * TQ + 4 * lane);
+            const float4 b = *reinterpret_cast<const float4*>(s_dcsB + gI * TQ + 4 * lane);
+            const float4 d = *reinterpret_cast<const float4*>(s_ddtx + gI * TQ + 4 * lane);
+            v[0] += a.x + b.x; v[1] += a.y + b.y; v[2] += a.z + b.z; v[3] += a.w + b.w;
+            ddx[0] += d.x; ddx[1] += d.y; ddx[2] += d.z; ddx[3] += d.w;
+          }
+          float extra = 0.f, dd = 0.f;
+          {
+            const float ecl = s_ecs[TQ - 1];
+#pragma unroll
+            for (int k = 0; k < NT / 128; ++k) {
+              const float4 a = *reinterpret_cast<const float4*>(s_pdot + 128 * k + 4 * lane);
+              const float4 b = *reinterpret_cast<const float4*>(s_psc + 128 * k + 4 * lane);
+              const float4 c4 = *reinterpret_cast<const float4*>(s_pdd + 128 * k + 4 * lane);
+              extra += ecl * (a.x + a.y + a.z + a.w) + (b.x + b.y + b.z + b.w);
+              dd += c4.x + c4.y + c4.z + c4.w;
+            }
+          }
+          extra = warp_sum(extra); dd = warp_sum(dd);
+          if (lane == 31) v[3] += extra;                               // d cs of the chunk's last frame
+          v[2] += v[3]; v[1] += v[2]; v[0] += v[1];                    // suffix sums inside the lane
+          float suf = v[0];
+#pragma unroll
+          for (int o2 = 1; o2 < 32; o2 <<= 1) { const float u = __shfl_down_sync(0xffffffffu, suf, o2); if (lane + o2 < 32) suf += u; }
+          const float later = suf - v[0];                              // everything after this lane's frames
+          const float4 dt4 = *reinterpret_cast<const float4*>(s_dt + 4 * lane);
+          const float dtv[4] = {dt4.x, dt4.y, dt4.z, dt4.w};
+          float accA = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int tt = 4 * lane + k;
+            const float sv = v[k] + later;
+            accA += sv * dtv[k];
+            if (tt < qv) p.ddt[(row0 + tt) * H + h] = sv * A + ddx[k];
+          }
+          accA = warp_sum(accA);
+          if (lane == 0) { atomicAdd(p.dA_log + dir * H + h, accA * A); atomicAdd(p.dD + dir * H + h, dd); }
+        }
+      }
+      // ---- write dB | dC of this item (bf16, like the rest of the activation gradients)
+      umma::mbar_wait(bar_acc, (seq - 1) & 1);
+      umma::tc_fence_after();
+      {
+        const int t = row;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {                          // 0: dB, 1: dC
+          float v[32];
+          umma::tmem_ld32(t_lane + (part == 0 ? TM_DB : TM_DC) + 32u * cg, v);
+          umma::tmem_ld_wait();
+          if (t < qv) {
+            __nv_bfloat16* og = p.dBC + hg * p.dbc_part_stride + (row0 + t) * (2 * TN) + part * TN + 32 * cg;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(og + 8 * k) = pack8(v + 8 * k);
+          }
+        }
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(bar_out);                       // the next item's accumulation may overwrite dC | dB
+    }
+  }
+  umma::tc_fence_before(); __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 }  // namespace hnb
 
@@ -1402,7 +1859,13 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
 // first CTA carries the largest item of every round: its load is the makespan.  Cost unit: one head-step of a full
 // chunk; a partly filled chunk costs its fixed latency plus the trimmed share.  A second part costs the convolution
 // backward one extra read of dB | dC (about two head-steps' worth of time).
-int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H) {
+// variant 0: the fused backward kernel (an item carries ALL per-head work of its heads); 1: the three-kernel backward.
+static bool ssd_bwd_legacy_env() {
+  static const bool legacy = getenv("HNB_SSD_BWD") && atoi(getenv("HNB_SSD_BWD")) == 3;   // 3 = round-1 three-kernel backward
+  return legacy;
+}
+int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H, int variant) {
+  if (ssd_bwd_legacy_env()) variant = 1;
   const int sms = sm_count(), nc = cdiv(L, TQ), rem = L - (nc - 1) * TQ;
   const int nfull = ndir * B * (rem == TQ ? nc : nc - 1), npart = ndir * B * nc - nfull;
   int best = 1;
@@ -1410,7 +1873,9 @@ int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H) {
   for (int hg = 1; hg <= 2; ++hg) {
     if (H % hg) continue;
     const double full = H / hg + 0.6, part = (0.45 + 0.55 * rem / TQ) * (H / hg) + 0.6;
-    double cost = 2.0 * (hg - 1);
+    // a second part costs the convolution backward one extra read of dB | dC: ~2 head-steps of the dB/dC kernel alone,
+    // ~1 of the (longer) fused head-step
+    double cost = (variant == 0 ? 1.0 : 2.0) * (hg - 1);
     for (long long i = 0; i < (long long)(nfull + npart) * hg; i += sms) cost += i < (long long)nfull * hg ? full : part;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = hg; }
   }
@@ -1438,8 +1903,9 @@ static int dx_heads_per_item(int ndirB, int L, int H, int sms) {
 
 int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float* dt, const float* A_log,
                    const float* Dskip, const void* states, int ndir, int B, int L, int di, int N, int H, void* dxc,
-                   void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, void* stream) {
+                   void* dBC, int dbc_parts, float* ddt, float* dA_log, float* dD, void* ws2, void* stream, int variant) {
   (void)y;
+  if (ssd_bwd_legacy_env()) variant = 1;
   HNB_CHECK_ARG(N == TN && di == H * TP, "ssd_bwd(tcgen05): built for d_state=128, headdim=64");
   const int C = di + 2 * N, nc = cdiv(L, TQ);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1460,6 +1926,7 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   }
   BwdParams p;
   p.dt = dt; p.A_log = A_log; p.Dskip = Dskip; p.gstates = (__nv_bfloat16*)ws2; p.dxc = (__nv_bfloat16*)dxc;
+  p.xconv = (const __nv_bfloat16*)xconv; p.dy = (const __nv_bfloat16*)dy;
   p.dBC = (__nv_bfloat16*)dBC; p.ddt = ddt; p.dA_log = dA_log; p.dD = dD;
   HNB_CHECK_ARG((dbc_parts == 1 || dbc_parts == 2) && H % dbc_parts == 0, "ssd_bwd(tcgen05): dbc_parts must be 1 or 2 and divide H");
   p.HG = dbc_parts; p.dbc_part_stride = (long long)ndir * B * L * 2 * N;
@@ -1476,7 +1943,7 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   p.tables = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.dbg = nullptr;
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
-  if (debug) { cudaMalloc(&p.dbg, 128); cudaMemsetAsync(p.dbg, 0, 128, st); }
+  if (debug) { cudaMalloc(&p.dbg, 256); cudaMemsetAsync(p.dbg, 0, 256, st); }
   const int sms = sm_count();
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dstate_tc_kernel, D1_SMEM));
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dx_tc_kernel<BWD_THREADS, false>, D2_SMEM));
@@ -1486,6 +1953,29 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   int items = ndir * B * H;
   ssd_bwd_dstate_tc_kernel<<<items < 2 * sms ? items : 2 * sms, D1_THREADS, D1_SMEM, st>>>(tmX, tmDY, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dstate_tc");
+  if (variant == 0) {                                   // dx / ddt / dA / dD and dB / dC in one pass
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_fused_tc_kernel<false>, DF_SMEM));
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_fused_tc_kernel<true>, DF_SMEM));
+    items = ndir * B * nc * dbc_parts;
+    if (debug) ssd_bwd_fused_tc_kernel<true><<<items < sms ? items : sms, DF_THREADS, DF_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+    else ssd_bwd_fused_tc_kernel<false><<<items < sms ? items : sms, DF_THREADS, DF_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+    HNB_LAUNCH_CHECK("ssd_bwd_fused_tc");
+    if (debug) {
+      long long h[32];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, p.dbg, 256, cudaMemcpyDeviceToHost);
+      cudaFree(p.dbg);
+      for (int w = 0; w < 2; ++w) {
+        const long long* d = h + 16 * w;
+        const double n = d[9] > 0 ? (double)d[9] : 1.0;
+        fprintf(stderr, "[ssd_bwd_fused CTA0 %s] full head-steps %lld | cycles: loads + G,R wait %.0f | epi A + TMEM copies %.0f | dot %.0f | "
+                "du wait %.0f | epi B loads %.0f | epi B %.0f | step barrier %.0f | sum %.0f\n", w == 0 ? "warp 0 (light rows)" : "warp 15 (heavy rows)",
+                d[9], d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n, d[5] / n, d[6] / n,
+                (d[0] + d[1] + d[2] + d[3] + d[4] + d[5] + d[6]) / n);
+      }
+    }
+    return HNB_OK;
+  }
   items = ndir * B * nc * (H / p.dxHh);
   if (debug) ssd_bwd_dx_tc_kernel<BWD_THREADS, true><<<items < sms ? items : sms, BWD_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
   else ssd_bwd_dx_tc_kernel<BWD_THREADS, false><<<items < sms ? items : sms, BWD_THREADS, D2_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);

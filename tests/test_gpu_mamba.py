@@ -220,7 +220,8 @@ def test_ssd_tcgen05_forward_vs_exact(ndir, B, L, H, impl):
         assert rel_err(s1, s2) < 1e-2 and rel_err(y1, y2) < 1e-2
 
 
-def test_ssd_tcgen05_kernels_repeatable():
+@pytest.mark.parametrize("impl", [1, 3], ids=["fused_bwd", "three_kernel_bwd"])
+def test_ssd_tcgen05_kernels_repeatable(impl):
     """Five runs on the same inputs give bit-identical activations and activation gradients: an unsynchronised read
     of a tile still in flight, or a TMEM column reused too early, shows up as run-to-run noise long before it breaks a
     1e-2 tolerance.  (dA_log / dD are fp32 atomic sums over work items and are compared with a tolerance.)"""
@@ -230,8 +231,8 @@ def test_ssd_tcgen05_kernels_repeatable():
     dy = (torch.randn(ndir, B * L, di, device=DEV) * 0.5).to(torch.bfloat16)
     ref = None
     for _ in range(5):
-        y, ws = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1)
-        dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, impl=1)
+        y, ws = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=impl)
+        dxc, dBC, ddt, dA, dD = ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, impl=impl)
         torch.cuda.synchronize()
         cur = (y.clone(), dxc.clone(), dBC.clone(), ddt.clone(), dA.clone(), dD.clone())
         if ref is None:
@@ -242,17 +243,19 @@ def test_ssd_tcgen05_kernels_repeatable():
         assert rel_err(cur[4], ref[4]) < 1e-5 and rel_err(cur[5], ref[5]) < 1e-5
 
 
+@pytest.mark.parametrize("impl", [1, 3], ids=["fused_bwd", "three_kernel_bwd"])
 @pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 700, 16), (1, 5, 77, 4), (2, 40, 196, 16),
-                                       (1, 3, 17, 2), (2, 2, 129, 4)])
-def test_ssd_tcgen05_backward_vs_exact(ndir, B, L, H):
-    """tcgen05 SSD backward (3 kernels) against the fp32 CUDA-core backward on identical bf16 inputs."""
+                                       (1, 3, 17, 2), (2, 2, 129, 4), (2, 2, 1498, 24), (2, 7, 256, 12)])
+def test_ssd_tcgen05_backward_vs_exact(ndir, B, L, H, impl):
+    """tcgen05 SSD backward (impl 1: state-gradient pass + ONE fused dx | dB/dC kernel; impl 3: the three-kernel backward)
+    against the fp32 CUDA-core backward on identical bf16 inputs."""
     from dcasr_b200 import ops
     xconv, dt, A_log, Dk, di, N = _ssd_inputs(ndir, B, L, H, seed=1)
     dy = (torch.randn(ndir, B * L, di, device=DEV) * 0.5).to(torch.bfloat16)
     y0, ws0 = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=0)
-    y1, ws1 = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1)
+    y1, ws1 = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=impl)
     r0 = ops.ssd_bwd(dy, xconv, y0, dt, A_log, Dk, ws0, ndir, B, L, di, N, H, impl=0)
-    r1 = ops.ssd_bwd(dy, xconv, y1, dt, A_log, Dk, ws1, ndir, B, L, di, N, H, impl=1)
+    r1 = ops.ssd_bwd(dy, xconv, y1, dt, A_log, Dk, ws1, ndir, B, L, di, N, H, impl=impl)
     torch.cuda.synchronize()
     names = ("dxc", "dBC", "ddt", "dA_log", "dD")
     errs = {n: rel_err(a, b) for n, a, b in zip(names, r1, r0)}
