@@ -1340,7 +1340,13 @@ ssd_bwd_dbc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // kernels it replaces); a 17th, issue-only warp rounds the CTA up to 20 warps' worth of registers (96 per thread, 840 B
 // of spills).  So two lanes of two LIGHT compute warps (TMEM lane quarter 0: one 32 x 32 block of the triangular score
 // tile instead of four) issue, each at a point where its warp would be waiting for the tensor pipe anyway: lane 0 of
-// warp 8 issues every TMA copy, G | R and the du / Yo group; lane 0 of warp 4 issues the accumulation group.
+// warp 8 issues every TMA copy, G | R and the du / Yo group; lane 0 of warp 4 issues the accumulation group.  Measured
+// alternatives (cycles per full head-step at the outer-stack shape; this split: 10.2 k): one lane issuing everything
+// 13.5-14.2 k (its warp's own epilogues end up in series with 60 MMAs); a third lane for G | R 11.8 k; <Gst, S_in> by the
+// light warps only 12.1 k (the issuing warps ARE light warps: extra work on them delays the next MMA group); x / dY rows
+// kept in registers from epilogue A so that the tiles go back to TMA earlier 11.7 k; x / dY re-read from global memory
+// for epilogue B 13.5 k.  A head-step of a nearly empty last chunk (L = 398: 14 frames) still costs ~10 k cycles: the step
+// is a chain of five mbarrier hand-offs and three MMA groups whose latencies do not shrink with the frame count.
 // Shared memory: 12 tiles (192 KB) + tables + partial sums.
 constexpr int DF_OFF_C = 0, DF_OFF_B = 2 * HALF, DF_OFF_X = 4 * HALF, DF_OFF_DY = 5 * HALF, DF_OFF_S = 6 * HALF,
               DF_OFF_G = 7 * HALF, DF_OFF_K = 8 * HALF, DF_OFF_W = 10 * HALF, DF_OFF_TAB = 12 * HALF;
@@ -1758,10 +1764,14 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           float v[32];
           umma::tmem_ld32(t_lane + (part == 0 ? TM_DB : TM_DC) + 32u * cg, v);
           umma::tmem_ld_wait();
-          if (t < qv) {
+          if (t < qv) {                                                 // 64 contiguous bytes per thread: two full 32-byte sectors
             __nv_bfloat16* og = p.dBC + hg * p.dbc_part_stride + (row0 + t) * (2 * TN) + part * TN + 32 * cg;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(og + 8 * k) = pack8(v + 8 * k);
+            for (int k = 0; k < 2; ++k) {
+              const uint4 lo = pack8(v + 16 * k), hi = pack8(v + 16 * k + 8);
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(og + 16 * k), "r"(lo.x), "r"(lo.y),
+                           "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+            }
           }
         }
       }
