@@ -573,7 +573,7 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
 int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H, int variant);
 
 extern "C" int hnb_ssd_dbc_parts(int ndir, int B, int L, int H, int impl) {
-  return (impl == 1 || impl == 3) ? hnb_ssd_dbc_parts_tc(ndir, B, L, H, impl == 3 ? 1 : 0) : 1;
+  return (impl == 1 || impl == 3 || impl == 4 || impl == 5) ? hnb_ssd_dbc_parts_tc(ndir, B, L, H, impl == 3 ? 1 : 0) : 1;
 }
 
 template <typename T>
@@ -604,9 +604,10 @@ extern "C" int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const 
   int rc = ssd_check("ssd_fwd", ndir, B, L, di, N, H);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1 || impl == 2 || impl == 3) {          // 2: the one-CTA-per-SM forward kernel (same outputs, kept under test); 3: as 1
+  if (impl >= 1 && impl <= 5) {     // 1, 3: by shape; 2 / 4: the persistent one- / two-CTA-per-SM kernels; 5: states pass + scan
     HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_fwd: the tcgen05 path takes bf16 activations");
-    return hnb_ssd_fwd_tc(xconv, dt, A_log, Dskip, ndir, B, L, di, N, H, y, states, stream, impl == 2 ? 1 : 0);
+    return hnb_ssd_fwd_tc(xconv, dt, A_log, Dskip, ndir, B, L, di, N, H, y, states, stream,
+                          impl == 2 ? 1 : impl == 4 ? 2 : impl == 5 ? 3 : 0);
   }
   if (dtype == HNB_BF16)
     return ssd_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)xconv, dt, A_log, Dskip, ndir, B, L, di, H,
@@ -652,7 +653,7 @@ extern "C" int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int
   int rc = ssd_check("ssd_bwd", ndir, B, L, di, N, H);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1 || impl == 3) {                        // 1: fused dx + dB/dC kernel; 3: the three-kernel backward (kept under test)
+  if (impl == 1 || impl == 3 || impl == 4 || impl == 5) {   // 1, 4, 5: fused dx + dB/dC kernel; 3: the three-kernel backward (kept under test)
     HNB_CHECK_ARG(dtype == HNB_BF16, "ssd_bwd: the tcgen05 path takes bf16 activations");
     return hnb_ssd_bwd_tc(dy, xconv, y, dt, A_log, Dskip, states, ndir, B, L, di, N, H, dxc, dBC, dbc_parts, ddt, dA_log,
                           dD, ws2, stream, impl == 3 ? 1 : 0);

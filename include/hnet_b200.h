@@ -158,10 +158,12 @@ int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long long ldz, 
  *   h_t = exp(dt_t A) h_{t-1} + dt_t B_t (x) x_t ,  y_t = C_t . h_t + D x_t
  * xconv [ndir,B*L,C] holds x | B | C; dt [ndir,B*L,H]; A_log, Dskip [ndir,H] float.
  * y [ndir,B*L,di] (act dtype).  states: workspace of hnb_ssd_ws_bytes() bytes (per-chunk states,
- * kept for the backward).  impl: 0 = CUDA-core fp32 (exact, any dtype), 1 = tcgen05 (bf16 only; forward: two CTAs per
- * SM, score tile in TMEM; backward: state-gradient pass + ONE fused dx | dB/dC kernel), 2 = tcgen05 with the
+ * kept for the backward).  impl: 0 = CUDA-core fp32 (exact, any dtype), 1 = tcgen05 (bf16 only; forward kernel chosen by
+ * shape between 4 and 5; backward: state-gradient pass + ONE fused dx | dB/dC kernel), 2 = tcgen05 with the
  * one-CTA-per-SM forward kernel (forward only; same outputs), 3 = tcgen05 with the three-kernel backward of round 1
- * (state gradients, dx, dB/dC; same outputs, kept under test as the yard-stick of the fused kernel). */
+ * (state gradients, dx, dB/dC; same outputs, kept under test as the yard-stick of the fused kernel), 4 = as 1 with the
+ * persistent forward kernel per (row, head), two CTAs per SM, 5 = as 1 with the split forward (chunk-state pass, then a
+ * scan over every chunk of every row at once with the score tile shared by the heads; the faster one on long rows). */
 long long hnb_ssd_ws_bytes(int ndir, int B, int L, int di, int N, int H);
 int hnb_ssd_chunk(void);
 int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const float* A_log, const float* Dskip,

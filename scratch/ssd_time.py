@@ -27,8 +27,10 @@ for (B, L, H, tag) in shapes:
     A_log = torch.log(torch.rand(ndir, H, device=DEV) * 15 + 1); Dk = torch.randn(ndir, H, device=DEV)
     dy = (torch.randn(ndir, B * L, di, device=DEV) * 0.5).to(torch.bfloat16)
     y, ws = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1)
-    tf = timeit(lambda: ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=1))
-    res = [f"fwd {tf:.1f}"]
+    res = []
+    for fi in (5, 4):          # 5: split (states pass + scan), 4: persistent two-CTA kernel
+        tf = timeit(lambda: ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=fi))
+        res.append(f"fwd impl {fi} {tf:.1f}")
     for impl in (1, 3):
         parts = int(lib().raw("ssd_dbc_parts")(ndir, B, L, H, impl))
         tb = timeit(lambda: ops.ssd_bwd(dy, xconv, y, dt, A_log, Dk, ws, ndir, B, L, di, N, H, impl=impl, keep_parts=True))

@@ -199,12 +199,14 @@ def _ssd_inputs(ndir, B, L, H, seed=0):
     return xconv, dt, A_log, Dk, di, N
 
 
-@pytest.mark.parametrize("impl", [1, 2], ids=["two_cta_tmem_operand", "one_cta"])
+@pytest.mark.parametrize("impl", [5, 4, 2], ids=["split_states_scan", "persistent_two_cta", "persistent_one_cta"])
 @pytest.mark.parametrize("ndir,B,L,H", [(1, 2, 128, 2), (2, 3, 398, 12), (2, 2, 1498, 16), (1, 5, 77, 4), (2, 40, 196, 16),
-                                       (1, 2, 1, 2), (1, 3, 17, 2), (2, 2, 129, 4), (2, 1, 256, 1)])
+                                       (1, 2, 1, 2), (1, 3, 17, 2), (2, 2, 129, 4), (2, 1, 256, 1), (2, 40, 398, 12),
+                                       (1, 3, 640, 6), (2, 5, 300, 5)])
 def test_ssd_tcgen05_forward_vs_exact(ndir, B, L, H, impl):
-    """tcgen05/TMEM SSD forward (impl 1: two CTAs per SM, score tile as a TMEM operand; impl 2: one CTA per SM) against
-    the fp32 CUDA-core path (impl 0) on identical bf16 inputs; the chunk states saved for the backward must agree too."""
+    """tcgen05/TMEM SSD forward (impl 5: chunk-state pass + scan over every chunk at once, score tile shared by the heads;
+    impl 4: persistent kernel per (row, head), two CTAs per SM; impl 2: one CTA per SM) against the fp32 CUDA-core path
+    (impl 0) on identical bf16 inputs; the chunk states saved for the backward must agree too."""
     from dcasr_b200 import ops
     xconv, dt, A_log, Dk, di, N = _ssd_inputs(ndir, B, L, H)
     y0, _ = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=0)
@@ -213,14 +215,14 @@ def test_ssd_tcgen05_forward_vs_exact(ndir, B, L, H, impl):
     err = rel_err(y1, y0)
     print("ssd tcgen05 fwd rel err vs exact:", err)
     assert err < 1e-2        # bf16 rounding of M, S_in and w*x operands (the upstream kernels round the same tensors)
-    if impl == 1:            # both tensor-core kernels save the same chunk states (bf16) and tables for the backward
+    if impl != 2:            # every tensor-core kernel saves the same chunk states (bf16) and tables for the backward
         y2, ws2 = ops.ssd_fwd(xconv, dt, A_log, Dk, ndir, B, L, di, N, H, impl=2)
         nst = ndir * B * H * ((L + 127) // 128) * 128 * 64
         s1 = ws1.view(torch.bfloat16)[:nst].float(); s2 = ws2.view(torch.bfloat16)[:nst].float()
         assert rel_err(s1, s2) < 1e-2 and rel_err(y1, y2) < 1e-2
 
 
-@pytest.mark.parametrize("impl", [1, 3], ids=["fused_bwd", "three_kernel_bwd"])
+@pytest.mark.parametrize("impl", [1, 3, 5], ids=["fused_bwd", "three_kernel_bwd", "split_fwd"])
 def test_ssd_tcgen05_kernels_repeatable(impl):
     """Five runs on the same inputs give bit-identical activations and activation gradients: an unsynchronised read
     of a tile still in flight, or a TMEM column reused too early, shows up as run-to-run noise long before it breaks a
