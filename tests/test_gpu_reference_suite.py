@@ -1,0 +1,138 @@
+"""The reference's OWN tests and its OWN Trainer, executed against the dcasr_b200 drop-in on the GPU (VERDICT r1 missing
+#6 / #7; SURVEY.md §7 step 1 "the first gate", §8f #3).
+
+`oracle/stage_reference.py` (run by `__graft_entry__.build()` in the container that has /root/reference) installs the
+unmodified reference package under baseline/_ref/ and copies its hot-path test files to baseline/_ref/ref_tests/ with a
+conftest that calls `dcasr_b200.install()` before any reference module is imported.  baseline/_ref/ is git-ignored and
+travels to the GPU box with the snapshot; where it is absent these tests skip (and say so)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from _util import PKG_DIR, REPO
+
+REF_DST = os.path.join(REPO, "baseline", "_ref")
+REF_TESTS = os.path.join(REF_DST, "ref_tests")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="baseline/_ref not staged (needs /root/reference at build time)")]
+
+# Reference tests that exercise something OUTSIDE the drop-in's contract, each with the reason.  Everything else must pass.
+DESELECT = {
+    # fp64 gradcheck of the reference's own scatter_add implementation detail: the CUDA kernels are fp32 / bf16 (north_star:
+    # "fp32 or bf16"); the same mean-pool / broadcast gradients are checked in fp32 by tests/test_gpu_hnet.py::test_fixed_pool_*
+    "test_fixed_pool.py::test_meanpool_broadcast_gradcheck_fp64": "float64 activations are outside the kernels' dtype set",
+    # the same two properties in fp32 (zero gradient at saturated p asserted exactly; gradients against the sequential
+    # recurrence): tests/test_gpu_hnet.py::test_ema_* and the golden `ema_*` cases produced by the reference itself
+    "test_hnet_chunk.py::test_ema_gradient_correct_at_saturated_p": "float64 inputs",
+    "test_hnet_chunk.py::test_ema_gradcheck_fp64": "float64 inputs",
+}
+
+
+def _run_pytest(files, extra=()):
+    args = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-rfEs", "--no-header",
+            *[os.path.join(REF_TESTS, f) for f in files]]
+    for name in DESELECT:                              # node ids are relative to the rootdir (= cwd = REF_TESTS)
+        args += ["--deselect", name]
+    args += list(extra)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([REF_DST, PKG_DIR]))
+    return subprocess.run(args, capture_output=True, text=True, timeout=1500, cwd=REF_TESTS, env=env)
+
+
+def _counts(out):
+    m = re.search(r"(\d+) passed", out)
+    f = re.search(r"(\d+) failed", out)
+    e = re.search(r"(\d+) error", out)
+    return int(m.group(1)) if m else 0, int(f.group(1)) if f else 0, int(e.group(1)) if e else 0
+
+
+def test_reference_hot_path_tests_pass_on_the_drop_in():
+    """tests/test_hnet_chunk.py, test_mamba_block.py, test_encoder.py, test_fixed_pool.py of the reference, unmodified, with
+    `dcasr.models.*` and `mamba_ssm` resolved to the B200 classes."""
+    r = _run_pytest(["test_hnet_chunk.py", "test_mamba_block.py", "test_encoder.py", "test_fixed_pool.py"])
+    tail = r.stdout[-6000:] + r.stderr[-2000:]
+    print(tail)
+    p, f, e = _counts(r.stdout)
+    assert r.returncode == 0 and f == 0 and e == 0, tail
+    assert p >= 75, (p, tail)          # every collected case of the four files (parametrised) minus DESELECT
+
+
+def test_reference_model_and_heads_tests_pass_on_the_drop_in():
+    """The callers either side of the path: the reference's asr_task (build_model -> encoder + CTC / AED heads + HybridLoss,
+    forward + backward on CUDA), CTC head and loss tests, with the encoder replaced."""
+    r = _run_pytest(["test_asr_task.py", "test_ctc.py", "test_loss.py"])
+    tail = r.stdout[-6000:] + r.stderr[-2000:]
+    print(tail)
+    p, f, e = _counts(r.stdout)
+    assert r.returncode == 0 and f == 0 and e == 0, tail
+    assert p >= 20, (p, tail)
+
+
+TRAIN_CODE = r'''
+import json, os, sys, tempfile, pathlib
+sys.path.insert(0, %(tests)r)
+import conftest                                        # sys.path, stand-ins, dcasr_b200.install()
+import torch
+from dcasr.tasks.asr_task import build_model
+from dcasr.training.trainer import Trainer
+import dcasr_b200
+torch.manual_seed(0)
+cfg = {"encoder": "dcasr", "head": "ctc", "frontend_conf": {"n_mels": 80},
+       "encoder_conf": {"d_outer": 128, "d_main": 128, "n_enc": 1, "n_main": 2, "n_dec": 1, "arch_type": "A",
+                        "hnet": {"compression_N": 2}},
+       "model_conf": {"ctc_weight": 1.0, "aed_weight": 0.0, "hnet_ratio_beta": 0.03}}
+model = build_model(cfg, 60)
+assert type(model.encoder).__module__.startswith("dcasr_b200"), type(model.encoder)
+g = torch.Generator().manual_seed(1)
+def batch(B=4, T=400, U=8):
+    return {"feats": torch.randn(B, T, 80, generator=g), "feat_lens": torch.tensor([T, T - 40, T - 80, T - 120][:B]),
+            "tokens": torch.randint(0, 60, (B, U), generator=g), "token_lens": torch.full((B,), U), "ids": [f"u{i}" for i in range(B)]}
+loader = [batch() for _ in range(3)] * 4               # 12 steps over 3 distinct batches: the loss must go down
+tcfg = {"optim": "adamw", "optim_conf": {"lr": 2e-3, "router_lr_mult": 1.0}, "scheduler": "warmuplr",
+        "scheduler_conf": {"warmup_steps": 2}, "max_epoch": 1, "grad_clip": 5.0, "accum_grad": %(accum)d, "precision": "bf16",
+        "log_interval": 1, "valid_interval_epoch": 1, "keep_nbest_models": 1,
+        "best_model_criterion": [["valid", "loss", "min"]], "early_stopping": {"enable": False}}
+tmp = pathlib.Path(tempfile.mkdtemp())
+tr = Trainer(model, loader, tcfg, dev_loaders={"dev": loader[:2]}, device="cuda:0", ckpt_dir=tmp / "ckpts")
+p0 = {n: p.detach().clone() for n, p in tr.raw_model.named_parameters()}
+dcasr_b200.reset_launch_count()
+losses = []
+orig = tr.raw_model.forward
+def fwd(*a, **k):
+    loss, stats = orig(*a, **k)
+    if torch.is_grad_enabled():
+        losses.append(loss.detach())
+    return loss, stats
+tr.raw_model.forward = fwd
+tr.train()
+torch.cuda.synchronize()
+losses = [float(l) for l in losses]
+moved = sum(int(not torch.equal(p0[n], p.detach())) for n, p in tr.raw_model.named_parameters())
+ck = sorted(os.listdir(tmp / "ckpts"))
+sd = torch.load(tmp / "ckpts" / [c for c in ck if c.endswith(".pt")][0], map_location="cpu", weights_only=False)
+print("RESULT" + json.dumps({"steps": tr.global_step, "losses": losses, "moved": moved, "n_params": len(p0),
+                             "launches": dcasr_b200.launch_count(), "ckpt": ck,
+                             "ckpt_has_encoder": any(k.startswith("encoder.main.layers.0.fwd.A_log") for k in sd["model"])}))
+'''
+
+
+@pytest.mark.parametrize("accum", [1, 2])
+def test_reference_trainer_trains_the_drop_in(accum):
+    """The reference's Trainer (bf16 autocast, AdamW with its router / no-weight-decay parameter groups, gradient clipping,
+    warm-up scheduler, validation, checkpoint) drives the reference's DCASRModel whose encoder is the B200 drop-in: the loss
+    on three repeated batches goes down, every parameter moves, the checkpoint holds the reference's state_dict keys."""
+    r = subprocess.run([sys.executable, "-c", TRAIN_CODE % {"tests": REF_TESTS, "accum": accum}], capture_output=True, text=True,
+                       timeout=900, cwd=REF_TESTS)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")]
+    assert line, r.stdout[-3000:] + r.stderr[-5000:]
+    out = json.loads(line[0][6:])
+    print(out)
+    assert out["steps"] == 12 // accum
+    ls = out["losses"]
+    assert all(v == v and abs(v) < 1e6 for v in ls)
+    assert sum(ls[-3:]) < sum(ls[:3]), ls                       # same three batches at the start and at the end
+    assert out["moved"] == out["n_params"]                      # DDP contract: every parameter gets a gradient
+    assert out["launches"] > 100 and out["ckpt_has_encoder"]
