@@ -5,7 +5,9 @@
 After this, ``from mamba_ssm import Mamba2`` (reference src/dcasr/models/mamba_block.py:12) resolves to
 the B200 mixer, and ``dcasr.models.hnet_chunk`` / ``.mamba_block`` / ``.encoder`` expose the B200 classes,
 so ``dcasr.tasks.asr_task.build_model`` (reference :129-146), ``scripts/train.py`` and
-``scripts/decode.py`` construct and run the CUDA hot path with no source change.
+``scripts/decode.py`` construct and run the CUDA hot path with no source change.  ``Trainer._any_rank_oom`` (reference
+training/trainer.py:200-208) is rebound to a host-side collective (trainer_sync.py): same flag on every rank, no
+``.item()`` on the CUDA stream after every micro-batch.
 """
 from __future__ import annotations
 
@@ -13,7 +15,7 @@ import sys
 import types
 
 
-def install(patch_dcasr: bool = True) -> None:
+def install(patch_dcasr: bool = True, patch_trainer: bool = True) -> None:
     from . import encoder, hnet_chunk, mamba_block
 
     shim = types.ModuleType("mamba_ssm")
@@ -45,3 +47,10 @@ def install(patch_dcasr: bool = True) -> None:
         setattr(ref_enc, name, getattr(encoder, name))
     if "dcasr.tasks.asr_task" in sys.modules:
         sys.modules["dcasr.tasks.asr_task"].DCASREncoder = encoder.DCASREncoder
+    if patch_trainer:
+        try:                                                    # needs the trainer's own third-party imports (editdistance)
+            import dcasr.training.trainer as ref_trainer
+            from . import trainer_sync
+            trainer_sync.patch_trainer(ref_trainer.Trainer)     # per-micro-batch OOM flag: host-side collective, no .item()
+        except Exception:
+            pass

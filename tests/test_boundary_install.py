@@ -46,6 +46,8 @@ for arch, N, chunker in (("A", 2, "dynamic"), ("B", 4, "dynamic"), ("A", 2, "fix
         "no_decay": sorted(n for n, p in enc.named_parameters() if getattr(p, "_no_weight_decay", False)),
         "router": sorted(n for n, p in enc.named_parameters() if "router" in n.split(".") and n.split(".")[-2] in ("W_q", "W_k")),
     }
+from dcasr.training.trainer import Trainer
+out["trainer_sync"] = Trainer._any_rank_oom.__doc__ or ""
 out["rebinds"] = [ref_enc.DCASREncoder.__module__, ref_mb.MambaStack.__module__, ref_ch.DynamicChunker.__module__,
                   sys.modules["mamba_ssm"].Mamba2.__module__]
 try:
@@ -66,6 +68,7 @@ def test_reference_builders_construct_the_b200_classes():
     out = json.loads(line[0][6:])
     assert all(m.startswith("dcasr_b200") for m in out["rebinds"]), out["rebinds"]
     assert out["bad_arch"] == "ValueError"
+    assert "dcasr_b200.trainer_sync" in out["trainer_sync"]            # per-micro-batch OOM flag rebound to the host-side collective
     # the oracle mirrors the reference's module tree (tests/test_oracle_encoder.py pins it against the reference's own
     # encoder.py): identical key sets and shapes mean reference checkpoints load with strict=True
     from oracle.encoder_ref import EncoderRef

@@ -98,3 +98,31 @@ def test_shard_indices_cover_and_balance():
         assert len({len(p) for p in parts}) == 1
         flat = sorted(i for p in parts for i in p)
         assert flat == list(range(n - n % w))
+
+
+def _flag_worker(rank, world, port, out):
+    sys.path.insert(0, REPO); sys.path.insert(0, PKG_DIR)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dcasr_b200.trainer_sync import any_rank_flag, patch_trainer
+
+    class T:                                            # stands in for the reference Trainer (world_size attribute only)
+        world_size = world
+    patch_trainer(T)
+    tr = T()
+    res = [any_rank_flag(False, world), any_rank_flag(rank == 1, world), any_rank_flag(rank == 0, world), any_rank_flag(True, world),
+           tr._any_rank_oom(rank == 1), tr._any_rank_oom(False)]
+    torch.save(res, os.path.join(out, f"f{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_side_group_flag_matches_reference_semantics(tmp_path):
+    """Trainer._any_rank_oom (reference training/trainer.py:200-208): MAX over ranks, one matched collective per call --
+    here over a host-side group, so the CUDA stream is never read back."""
+    world, port = 2, 29547
+    mp.spawn(_flag_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert torch.load(tmp_path / f"f{r}.pt") == [False, True, True, True, True, False]
+    from dcasr_b200.trainer_sync import any_rank_flag
+    assert any_rank_flag(True, 1) is True and any_rank_flag(False, 1) is False      # one rank: identity, no process group
