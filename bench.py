@@ -320,6 +320,51 @@ def profile_step(step, pk):
 
 
 # ---------------------------------------------------------------------------------------------------
+def ctc_head_leg(dev, B=40, T=398, d=384, V=500, U=60, reps=10):
+    """The step after the path: CTC head fwd+bwd on the encoder's output shape, bf16 autocast -- the drop-in
+    (projection GEMM + hnb_ctc_lse / alpha_beta / grad / col_sum: no fp32 logits, no [B, L, V+1] fp32 log-probabilities) timed
+    beside the reference's own op sequence on the same GPU (nn.Linear -> .float() -> log_softmax -> F.ctc_loss, ctc.py:100-115)."""
+    import torch.nn.functional as F
+    import dcasr_b200 as dd
+    torch.manual_seed(3)
+    head = dd.CTCHead(d, V).to(dev)
+    x = torch.randn(B, T, d, device=dev)
+    fl = torch.full((B,), T, device=dev, dtype=torch.int64)
+    tl = torch.randint(U // 2, U + 1, (B,), device=dev)
+    tg = torch.randint(0, V, (B, U), device=dev)
+
+    def ours():
+        xx = x.requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = head.loss(xx, fl, tg, tl)
+        loss.backward()
+        return loss
+
+    def ref_ops():
+        xx = x.requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            lp = F.log_softmax(F.linear(xx, head.proj.weight, head.proj.bias).float(), dim=-1).transpose(0, 1)
+            loss = F.ctc_loss(lp, tg, fl, tl, blank=V, reduction="mean", zero_infinity=True)
+        loss.backward()
+        return loss
+
+    out = {}
+    for name, fn in (("ours_ms", ours), ("reference_ops_same_gpu_ms", ref_ops)):
+        for _ in range(3):
+            l = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            l = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = round(e0.elapsed_time(e1) / reps, 4)
+        out[name.replace("_ms", "_loss")] = round(float(l), 5)
+    out["shape"] = f"{B} x {T} frames, d {d}, {V} pieces + blank, targets <= {U}"
+    return out
+
+
 def parity_check(enc, kw, feats1, lens1, dev, mode):
     """After the timed region: utterance 0 of the bench batch through the CPU oracle (fp32) and through the product, once
     in fp32 (exact kernels; features at north_star's 1e-3, boundaries bit-exact) and once as timed (bf16 autocast; loss
@@ -617,6 +662,11 @@ def run_ours(args):
                 line["parity"] = parity_check(enc, kw, f0[:1, : int(l0[0])].contiguous(), l0[:1], dev, args.mode)
             except Exception as e:            # a parity failure must be visible in the line, never hide the measurement
                 line["parity"] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1 and train and not args.no_parity:
+            try:
+                line["ctc_head"] = ctc_head_leg(dev)
+            except Exception as e:
+                line["ctc_head"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
             secs = args.seconds or wl["seconds"] or 12.4

@@ -45,8 +45,16 @@ def install(patch_dcasr: bool = True, patch_trainer: bool = True) -> None:
     import dcasr.models.encoder as ref_enc
     for name in ("DCASREncoder", "EncoderOutput", "ConvSubsampling4", "build_chunker"):
         setattr(ref_enc, name, getattr(encoder, name))
+    try:                                                        # the step after the path: CTC head (projection + fused loss)
+        import dcasr.decoders.ctc as ref_ctc
+        from . import ctc
+        ref_ctc.CTCHead = ctc.CTCHead
+    except Exception:
+        ref_ctc = None
     if "dcasr.tasks.asr_task" in sys.modules:
         sys.modules["dcasr.tasks.asr_task"].DCASREncoder = encoder.DCASREncoder
+        if ref_ctc is not None:
+            sys.modules["dcasr.tasks.asr_task"].CTCHead = ref_ctc.CTCHead
     if patch_trainer:
         try:                                                    # needs the trainer's own third-party imports (editdistance)
             import dcasr.training.trainer as ref_trainer

@@ -288,6 +288,32 @@ int hnb_bias_relu_fwd(void* x, const float* bias, long long rows, int C, void* s
 /* its backward in one pass: dpre = dout * [out > 0] (bf16), db [C] ACCUMULATED (pre-zeroed fp32, 16-byte aligned) */
 int hnb_bias_relu_bwd(const void* dout, const void* out, void* dpre, float* db, long long rows, int C, void* stream);
 
+/* ---- CTC head (the step after the hot path) ------------------------------------ */
+
+/* Reference: CTCHead.log_probs / CTCHead.loss / CTCHead.frame_argmax, src/dcasr/decoders/ctc.py:100-120:
+ *   lp = log_softmax(Linear(features).float(), -1);  F.ctc_loss(lp^T, targets, feat_lengths, target_lengths, blank,
+ *   reduction, zero_infinity=True).  The kernels work on the LOGITS as the projection wrote them (fp32 or bf16,
+ *   [B, T, V1] with row stride ldl) and never materialise the fp32 log-probabilities.
+ * hnb_ctc_lse: lse[row] = logsumexp over the V1 classes (fp32); argmax (optional, int32): per-frame top class, ties to the
+ *   lowest id as torch.argmax (greedy decoding / frame_argmax). */
+int hnb_ctc_lse(const void* logits, int dtype, long long rows, int V1, long long ldl, float* lse, int* argmax, void* stream);
+/* alpha, beta [B, T, 2U+1] fp32 (log domain; both include the emission at t, PyTorch's convention) and nll [B] =
+ * -log p(targets_b | logits_b) (inf when no alignment exists).  targets [B, U] int64 (padding beyond tgt_lens ignored),
+ * feat_lens, tgt_lens [B] int64 (clamped to [0, T] and [0, U]).  U <= 511. */
+int hnb_ctc_alpha_beta(const void* logits, int dtype, const float* lse, const long long* targets, const long long* feat_lens,
+                       const long long* tgt_lens, int B, int T, int V1, long long ldl, int U, int blank, float* alpha,
+                       float* beta, float* nll, void* stream);
+/* dlogits [B, T, V1] (logits' dtype, row stride ldd) = gscale[b] * d nll[b] / d logits; zero beyond feat_lens[b] and for
+ * utterances with nll = inf (zero_infinity).  gscale carries the upstream gradient and the reduction's weights. */
+int hnb_ctc_grad(const void* logits, int dtype, const float* lse, const float* alpha, const float* beta,
+                 const long long* targets, const long long* feat_lens, const long long* tgt_lens, const float* nll,
+                 const float* gscale, int B, int T, int V1, long long ldl, int U, int blank, void* dlogits, long long ldd,
+                 void* stream);
+
+/* out[c] += sum over rows of x[r, c] (fp32, ACCUMULATED into a pre-zeroed buffer): the bias gradient of nn.Linear
+ * (CTCHead.proj, DCASREncoder.proj_in / proj_out: src/dcasr/models/encoder.py:104-111), x row-major with row stride ldx. */
+int hnb_col_sum(const void* x, int dtype, long long rows, int cols, long long ldx, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

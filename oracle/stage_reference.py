@@ -52,9 +52,10 @@ import pytest, torch
 
 @pytest.fixture(autouse=True)
 def _hnb_cuda_default_device(request):
-    """tests/test_fixed_pool.py of the reference creates its tensors on the default device (it is a CPU test of a pure-torch
-    module); the drop-in is CUDA-only, so that file runs with the GPU as default device -- the other files set it themselves."""
-    if request.module.__name__.split(".")[-1] == "test_fixed_pool" and torch.cuda.is_available():
+    """tests/test_fixed_pool.py and tests/test_ctc.py of the reference create their tensors on the default device (they are
+    CPU tests of pure-torch modules); the drop-in is CUDA-only, so those files run with the GPU as default device -- the
+    other files set it themselves."""
+    if request.module.__name__.split(".")[-1] in ("test_fixed_pool", "test_ctc") and torch.cuda.is_available():
         torch.set_default_device("cuda")
         yield
         torch.set_default_device("cpu")
