@@ -26,14 +26,22 @@ struct Dims {
 };
 
 // forward workspace (kept for the backward)
-enum { F_H2, F_MEAN, F_RSTDLN, F_WIN, F_WOUT, F_SMALL, F_ZX, F_XCONV, F_DT, F_Y, F_SSD, F_YN, F_RSTD, F_COUNT };
+enum { F_H2, F_MEAN, F_RSTDLN, F_WIN, F_WOUT, F_SMALL, F_ZX, F_XCONV, F_DT, F_Y, F_SSD, F_YN, F_RSTD, F_GEMM, F_COUNT };
+// fp32 activations: the large projections run as bf16-piece GEMMs on the tensor cores (hnb_gemm_f32_tc) and need scratch
+inline bool f32_tc(long long M, long long N, long long K) { return (double)M * (double)N * (double)K >= 67108864.0; }
+size_t f32_gemm_scratch(int act, long long M, long long N, long long K) {
+  return (act == HNB_F32 && f32_tc(M, N, K)) ? (size_t)hnb_gemm_f32_tc_ws_bytes((int)M, (int)N, (int)K) : 0;
+}
+inline size_t max2(size_t x, size_t y) { return x > y ? x : y; }
+
 size_t fwd_layout(const Dims& m, size_t* off) {
   const size_t a = esz(m.act), T = (size_t)m.T();
+  const size_t gs = max2(f32_gemm_scratch(m.act, m.T(), m.ldz(), m.d), f32_gemm_scratch(m.act, m.T(), m.d, m.ndir * m.di));
   const size_t sz[F_COUNT] = {
       T * m.d * a, T * 4, T * 4, (size_t)m.ldz() * m.d * a, (size_t)m.d * m.ndir * m.di * a,
       (size_t)m.ndir * (m.C() * 5 + 3 * m.H + m.di) * 4, T * m.ldz() * a, (size_t)m.ndir * T * m.C() * a,
       (size_t)m.ndir * T * m.H * 4, (size_t)m.ndir * T * m.di * a,
-      (size_t)hnb_ssd_ws_bytes(m.ndir, m.B, m.L, m.di, m.N, m.H), T * m.ndir * m.di * a, (size_t)m.ndir * T * 4};
+      (size_t)hnb_ssd_ws_bytes(m.ndir, m.B, m.L, m.di, m.N, m.H), T * m.ndir * m.di * a, (size_t)m.ndir * T * 4, gs};
   size_t o = 0;
   for (int i = 0; i < F_COUNT; ++i) { off[i] = o; o += up(sz[i]); }
   return o;
@@ -53,13 +61,16 @@ Small small_ptrs(const Dims& m, uint8_t* base) {
 }
 
 // backward scratch (dead when the call returns)
-enum { S_DA, S_DYN, S_DZX, S_DY, S_DXC, S_DBC, S_DDT, S_WS2, S_DH2, S_COUNT };
+enum { S_DA, S_DYN, S_DZX, S_DY, S_DXC, S_DBC, S_DDT, S_WS2, S_DH2, S_GEMM, S_COUNT };
 size_t bwd_layout(const Dims& m, int parts, size_t* off) {
   const size_t a = esz(m.act), T = (size_t)m.T();
+  const long long nd = (long long)m.ndir * m.di;
+  const size_t gs = max2(max2(f32_gemm_scratch(m.act, m.T(), nd, m.d), f32_gemm_scratch(m.act, m.d, nd, m.T())),
+                         max2(f32_gemm_scratch(m.act, m.T(), m.d, m.ldz()), f32_gemm_scratch(m.act, m.ldz(), m.d, m.T())));
   const size_t sz[S_COUNT] = {
       T * m.d * a, T * m.ndir * m.di * a, T * m.ldz() * a, (size_t)m.ndir * T * m.di * a, (size_t)m.ndir * T * m.di * a,
       (size_t)parts * m.ndir * T * 2 * m.N * a, (size_t)m.ndir * T * m.H * 4,
-      (size_t)hnb_ssd_ws_bytes(m.ndir, m.B, m.L, m.di, m.N, m.H), T * m.d * a};
+      (size_t)hnb_ssd_ws_bytes(m.ndir, m.B, m.L, m.di, m.N, m.H), T * m.d * a, gs};
   size_t o = 0;
   for (int i = 0; i < S_COUNT; ++i) { off[i] = o; o += up(sz[i]); }
   return o;
@@ -105,8 +116,11 @@ int check_dims(const char* who, const Dims& m, int x_dtype) {
 
 // C = op(A) op(B) in the activation dtype's GEMM (tensor cores for bf16, exact CUDA-core GEMM for fp32)
 int gemm(int act, const void* A, long long lda, int tA, const void* Bm, long long ldb, int tB, int M, int N, int K,
-         const void* R, long long ldr, void* Cm, long long ldc, int c_dtype, int splitk, void* st) {
+         const void* R, long long ldr, void* Cm, long long ldc, int c_dtype, int splitk, void* st, void* scratch = nullptr) {
   if (act == HNB_BF16) return hnb_gemm_bf16(A, lda, tA, Bm, ldb, tB, M, N, K, nullptr, R, ldr, Cm, ldc, c_dtype, splitk, st);
+  if (scratch && f32_tc(M, N, K))
+    return hnb_gemm_f32_tc((const float*)A, lda, tA, (const float*)Bm, ldb, tB, M, N, K, nullptr, (const float*)R, ldr,
+                           (float*)Cm, ldc, scratch, st);
   return hnb_gemm_f32((const float*)A, lda, tA, (const float*)Bm, ldb, tB, M, N, K, nullptr, (const float*)R, ldr,
                       (float*)Cm, ldc, 0, st);
 }
@@ -165,14 +179,15 @@ extern "C" int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths,
   else
     HNB_TRY(hnb_pack_mixer_params(P[0], P[7], P[1], P[2], P[3], P[4], P[5], P[6], 0, 1, d, di, N, H, dstride, Win, Wout,
                                   act_dtype, s.conv_w, s.conv_b, s.dt_bias, s.A_log, s.D, s.norm_w, stream));
-  HNB_TRY(gemm(act_dtype, h2, d, 0, Win, d, 0, (int)T, ldz, d, nullptr, 0, zx, ldz, act_dtype, 1, stream));
+  void* gsc = act_dtype == HNB_F32 ? w + off[F_GEMM] : nullptr;
+  HNB_TRY(gemm(act_dtype, h2, d, 0, Win, d, 0, (int)T, ldz, d, nullptr, 0, zx, ldz, act_dtype, 1, stream, gsc));
   HNB_TRY(hnb_conv_fwd(zx, act_dtype, ldz, dstride, lengths, s.conv_w, s.conv_b, s.dt_bias, ndir, B, L, di, N, H, xconv, dt,
                        stream));
   HNB_TRY(hnb_ssd_fwd(xconv, act_dtype, dt, s.A_log, s.D, ndir, B, L, di, N, H, y, ssd, ssd_impl, stream));
   HNB_TRY(hnb_gated_norm_fwd(y, zx, act_dtype, ldz, dstride, lengths, s.norm_w, ndir, B, L, di, 1e-5f, yn, rstd, stream));
   // out-projection of both directions (K = ndir*di) with the residual in its epilogue; the residual stream keeps its dtype
   HNB_TRY(gemm(act_dtype, yn, (long long)ndir * di, 0, Wout, (long long)ndir * di, 0, (int)T, d, ndir * di, x, d, out, d,
-               x_dtype, 1, stream));
+               x_dtype, 1, stream, gsc));
   return HNB_OK;
 }
 
@@ -219,8 +234,9 @@ extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const
     da = buf;
   }
   const int bf = act_dtype == HNB_BF16;
+  void* gsc = act_dtype == HNB_F32 ? sc + so[S_GEMM] : nullptr;
   HNB_TRY(gemm(act_dtype, da, d, 0, Wout, (long long)ndir * di, 1, (int)T, ndir * di, d, nullptr, 0, dyn, (long long)ndir * di,
-               act_dtype, 1, stream));                                                        // d ynorm
+               act_dtype, 1, stream, gsc));                                                   // d ynorm
   // dWout of both directions from ONE GEMM, each direction's [d, di] matrix contiguous (column-blocked C): the parameter's
   // .grad can then alias the arena instead of being a strided copy of it
   if (bf && (ndir == 1 || di % 32 == 0)) {
@@ -232,7 +248,7 @@ extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const
       const size_t a = esz(act_dtype);
       const void* yn_r = static_cast<const uint8_t*>(yn) + (size_t)r * di * a;
       HNB_TRY(gemm(act_dtype, da, d, 1, yn_r, (long long)ndir * di, 1, d, di, (int)T, nullptr, 0,
-                   grads + ao[A_WOUT] + (long long)r * d * di, di, HNB_F32, bf ? hnb_gemm_splitk_hint(d, di, (int)T) : 1, stream));
+                   grads + ao[A_WOUT] + (long long)r * d * di, di, HNB_F32, bf ? hnb_gemm_splitk_hint(d, di, (int)T) : 1, stream, gsc));
     }
   }
   if (dstride != dip) {                                       // pad columns of dzxbcdt feed the two GEMMs below
@@ -246,9 +262,9 @@ extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const
                       grads + ao[A_DA], grads + ao[A_DD], ws2, ssd_impl, stream));
   HNB_TRY(hnb_conv_bwd(zx, dxc, act_dtype, ldz, dstride, dBC, ddt, lengths, s.conv_w, s.conv_b, s.dt_bias, ndir, B, L, di, N,
                        H, dzx, grads + ao[A_CW], grads + ao[A_CB], grads + ao[A_DTB], parts, stream));
-  HNB_TRY(gemm(act_dtype, dzx, ldz, 0, Win, d, 1, (int)T, d, ldz, nullptr, 0, dh2, d, act_dtype, 1, stream));        // d LN output
+  HNB_TRY(gemm(act_dtype, dzx, ldz, 0, Win, d, 1, (int)T, d, ldz, nullptr, 0, dh2, d, act_dtype, 1, stream, gsc));   // d LN output
   HNB_TRY(gemm(act_dtype, dzx, ldz, 1, h2, d, 1, ldz, d, (int)T, nullptr, 0, grads + ao[A_WIN], d, HNB_F32,
-               bf ? hnb_gemm_splitk_hint(ldz, d, (int)T) : 1, stream));                                              // dWin
+               bf ? hnb_gemm_splitk_hint(ldz, d, (int)T) : 1, stream, gsc));                                         // dWin
   HNB_TRY(hnb_layernorm_bwd(dh2, act_dtype, x, x_dtype, ln_w, mean, rstd_ln, dout, T, d, dx, x_dtype, grads + ao[A_LN],
                             grads + ao[A_LN] + d, stream));
   return HNB_OK;

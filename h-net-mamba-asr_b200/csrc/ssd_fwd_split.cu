@@ -315,8 +315,6 @@ ssd_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int gp = g - 1, pb = gp & 1;
     umma::mbar_wait(bar_y + pb, (gp >> 1) & 1);
     umma::tc_fence_after();
-    if (loader) issue_h();                                 // stage of g - 1: X, S consumed by the MMAs that just retired, the
-                                                           // tables read by every thread before that head step's barrier
     if ((row >> 5) < ((qv_prev + 31) >> 5)) {
       umma::tmem_ld16(t_lane + TM_YD + 64u * pb + 16u * cg, yd);
       if (yo_prev) umma::tmem_ld16(t_lane + TM_YO + 64u * pb + 16u * cg, yo);
@@ -350,7 +348,10 @@ ssd_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (g > 0) {
       epi_issue();
       umma::tc_fence_before();
-      __syncthreads();                                     // (also: every thread has taken its x out of the stage refilled next)
+      __syncthreads();
+      // stage of head step g - 1: X, S consumed by its MMAs (epi_issue waited for them), its tables read before that step's
+      // barrier, and -- this barrier -- every thread has taken its x for the D x term out of it
+      if (loader) issue_h();
     }
     if (issuer) {
       umma::mbar_wait(bar_c + (k & 1), (k >> 1) & 1);
@@ -410,6 +411,7 @@ ssd_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (hh > 0) epi_issue();
       umma::tc_fence_before();
       __syncthreads();
+      if (loader && hh > 0) issue_h();                     // refill the stage of head step g - 1 (see the item prologue)
       if (issuer) {
         umma::tc_fence_after();
         const uint64_t dX0 = umma::make_smem_desc(umma::smem_u32(sX + st * HALF), 1024, 1024);
@@ -442,7 +444,7 @@ ssd_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       st = st == SC_STAGES - 1 ? 0 : st + 1;
     }
   }
-  if (g > 0) { epi_issue(); epi_finish(); }
+  if (g > 0) { epi_issue(); epi_finish(); }                // (nothing left to fetch)
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);

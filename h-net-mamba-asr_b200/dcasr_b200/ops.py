@@ -14,6 +14,8 @@ from ._lib import BF16, F32, HnbError, dtype_code, lib, stream
 SSD_IMPL = "auto"
 # dense projections: "tcgen05" (own kernel) for bf16; fp32 always uses the exact CUDA-core GEMM
 GEMM_BF16_IMPL = "tcgen05"
+# fp32 projections: "tc" = large ones as bf16-piece GEMMs on the tensor cores (fp32-class accuracy), "exact" = CUDA cores only
+GEMM_F32_IMPL = "tc"
 
 
 def _c(t: torch.Tensor) -> torch.Tensor:
@@ -48,6 +50,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
             raise HnbError("gemm: mixed operand dtypes")
         c = out if out is not None else _empty((M, N), torch.float32, a)
         r = residual
+        if GEMM_F32_IMPL == "tc" and float(M) * N * K >= 67108864.0:
+            # large fp32 projections (decode): bf16-piece GEMM on the tensor cores, fp32-class accuracy (csrc/gemm_f32.cu)
+            ws = torch.empty(int(L.raw("gemm_f32_tc_ws_bytes")(M, N, K)), dtype=torch.uint8, device=a.device)
+            L.call("gemm_f32_tc", ptr(a), a.stride(0), int(trans_a), ptr(b), b.stride(0), int(trans_b), M, N, K,
+                   bias, ptr(r), r.stride(0) if r is not None else 0, ptr(c), c.stride(0), ws, stream())
+            return c
         L.call("gemm_f32", ptr(a), a.stride(0), int(trans_a), ptr(b), b.stride(0), int(trans_b), M, N, K,
                bias, ptr(r), r.stride(0) if r is not None else 0, ptr(c), c.stride(0), 0, stream())
         return c

@@ -267,6 +267,13 @@ int hnb_gemm_bf16_path(int M, int N, int K, int splitk);
 int hnb_gemm_f32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
                  int M, int N, int K, const float* bias, const float* R, long long ldr,
                  float* C, long long ldc, int accumulate, void* stream);
+/* the same product on the tcgen05 tensor cores at fp32-class accuracy: each operand is split into three bf16 pieces and the
+ * six piece products that matter are accumulated in fp32 as one GEMM over K' = 6 K (csrc/gemm_f32.cu).  Used for the large
+ * projections of the fp32 (decode) path.  ws: hnb_gemm_f32_tc_ws_bytes(M, N, K) bytes of scratch, 256-byte aligned. */
+long long hnb_gemm_f32_tc_ws_bytes(int M, int N, int K);
+int hnb_gemm_f32_tc(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
+                    int M, int N, int K, const float* bias, const float* R, long long ldr,
+                    float* C, long long ldc, void* ws, void* stream);
 /* on-device self test of the tcgen05 descriptor variants; returns 0 and fills max_abs_err[4] (host) */
 int hnb_umma_selftest(float* max_abs_err_host, void* stream);
 

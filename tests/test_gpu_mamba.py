@@ -97,6 +97,34 @@ def test_gemm_f32_vs_torch():
         assert rel_err(ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb)), ref) < 1e-6
 
 
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(1999, 1804, 384), (777, 384, 1536), (384, 1000, 5003), (520, 131, 1001)])
+def test_gemm_f32_tensor_core_pieces_vs_exact(ta, tb, M, N, K):
+    """hnb_gemm_f32_tc (fp32 operands as three bf16 pieces, six piece products in one tcgen05 GEMM) against fp64 and against
+    the exact CUDA-core kernel: fp32-class accuracy, all four operand layouts, ragged M / N / K (K not a multiple of 8),
+    bias and residual in the epilogue, wide-dynamic-range operands."""
+    from dcasr_b200 import ops
+    torch.manual_seed(1)
+    a = torch.randn((K, M) if ta else (M, K), device=DEV) * torch.exp(torch.randn(1, device=DEV) * 3)
+    b = torch.randn((K, N) if tb else (N, K), device=DEV) * torch.exp2(torch.randint(-6, 7, (1,), device=DEV).float())
+    ref = (a.double().t() if ta else a.double()) @ (b.double() if tb else b.double().t())
+    assert float(M) * N * K >= 67108864.0                    # routed to the tensor-core path
+    c = ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb))
+    old = ops.GEMM_F32_IMPL
+    ops.GEMM_F32_IMPL = "exact"
+    try:
+        c0 = ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb))
+    finally:
+        ops.GEMM_F32_IMPL = old
+    e_tc, e_exact = rel_err(c, ref), rel_err(c0, ref)
+    print(f"fp32 GEMM {M}x{N}x{K} ta={ta} tb={tb}: tensor-core pieces {e_tc:.2e}, exact CUDA-core kernel {e_exact:.2e}")
+    assert e_tc < 2e-6 and e_tc < 2.5 * e_exact + 2e-7
+    if not ta and not tb:
+        bias, r = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+        c2 = ops.gemm(a, b, bias=bias, residual=r)
+        assert rel_err(c2, ref + bias + r) < 2e-6
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layernorm_fwd_bwd(dtype):
     from dcasr_b200 import ops
