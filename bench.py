@@ -418,8 +418,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")               # its banner goes to stdout: keep stdout to the one JSON line
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     wl = WORKLOADS[args.workload]
@@ -437,7 +437,8 @@ def run_ours(args):
             dist.broadcast(p.data, 0)
     params = [p for p in enc.parameters()]
     from dcasr_b200.distributed import GradAllReducer
-    reducer = GradAllReducer(params, bucket_mb=32.0, overlap=True) if (world > 1 and train) else None
+    reducer = (GradAllReducer(params, bucket_mb=float(os.environ.get("HNB_BUCKET_MB", "32")),
+                              overlap=os.environ.get("HNB_REDUCER_OVERLAP", "1") != "0") if (world > 1 and train) else None)
     # ---- the batches: one fixed-length batch (each rank its own shard of utterances), or a cycle of ragged batches
     if ragged:
         host_batches, ragged_stats = ragged_batches(rank)

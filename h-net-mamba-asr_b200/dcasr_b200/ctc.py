@@ -83,9 +83,7 @@ class _HeadProjFn(torch.autograd.Function):
         dw = ops.gemm(d2, xa, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)
         db = None
         if bdt is not None:
-            db = torch.zeros(V1, dtype=torch.float32, device=d2.device)
-            lib().call("col_sum", d2.data_ptr(), dtype_code(d2.dtype), d2.shape[0], V1, d2.stride(0), db, stream())
-            db = db.to(bdt)
+            db = ops.col_sum(d2).to(bdt)
         return dx.to(xdt).view(shp), dw.to(wdt), db
 
 

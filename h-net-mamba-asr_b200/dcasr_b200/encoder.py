@@ -158,7 +158,7 @@ class _LinearFn(torch.autograd.Function):
         dx = ops.gemm(da, wa, trans_b=True, out_dtype=xdt if xa.dtype == torch.bfloat16 else None)
         sk = ops.wgrad_splitk(xa.shape[0], wa.shape[0], wa.shape[1]) if xa.dtype == torch.bfloat16 else 1
         dw = ops.gemm(da, xa, trans_a=True, trans_b=True, splitk=sk, out_dtype=torch.float32)
-        db = d2.float().sum(0) if has_b else None
+        db = ops.col_sum(da) if has_b else None                     # bias gradient: one column-sum kernel over d y
         return dx.to(xdt).view(shp), dw.to(wdt), (db.to(wdt) if has_b else None)
 
 

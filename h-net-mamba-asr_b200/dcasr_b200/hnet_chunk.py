@@ -54,13 +54,31 @@ class ChunkOutput:
 # ------------------------------------------------------------------------------------------------
 # autograd functions
 # ------------------------------------------------------------------------------------------------
+_WQK_CACHE: dict = {}
+
+
+def _packed_router_weights(Wq, Wk, adt):
+    """W_q | W_k stacked and cast for the one router GEMM; rebuilt only when a parameter was written (its version counter
+    moves with every optimiser step) -- under no_grad / decode this is once per model, not once per call."""
+    key = (Wq.data_ptr(), Wk.data_ptr(), adt)
+    ver = (Wq._version, Wk._version)
+    hit = _WQK_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w = torch.cat([Wq.detach(), Wk.detach()], 0).to(adt)
+    if len(_WQK_CACHE) > 64:
+        _WQK_CACHE.clear()
+    _WQK_CACHE[key] = (ver, w)
+    return w
+
+
 def _router_core(x, Wq, Wk, mask_u8, N):
     B, L, D = x.shape
     adt = _autocast_dtype() or x.dtype
     x2 = x.reshape(B * L, D)
     xa = x2 if x2.dtype == adt else x2.to(adt)
     xa = xa if xa.is_contiguous() else xa.contiguous()
-    Wqk = torch.cat([Wq, Wk], 0).to(adt)
+    Wqk = _packed_router_weights(Wq, Wk, adt)
     qk = ops.gemm(xa, Wqk)                                              # [B*L, 2D]
     pb_dtype = torch.float32 if (adt != x.dtype or x.dtype == torch.float32) else x.dtype
     p, b, stats = ops.router_fwd(qk, mask_u8, B, L, D, pb_dtype, N)

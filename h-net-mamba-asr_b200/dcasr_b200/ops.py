@@ -75,6 +75,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, bias
     return c
 
 
+def col_sum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a 2-D activation (rows of stride x.stride(0)): the bias gradient of nn.Linear."""
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    lib().call("col_sum", x.data_ptr(), dtype_code(x.dtype), x.shape[0], x.shape[1], x.stride(0), out, stream())
+    return out
+
+
 def wgrad_splitk(k_tokens: int, m: int, n: int) -> int:
     """split-K factor for weight gradients (K = tokens), chosen by the library for the tile grid it will use."""
     return max(1, int(lib().raw("gemm_splitk_hint")(int(m), int(n), int(k_tokens))))
