@@ -18,7 +18,7 @@ cols = [("dur us", "gpu__time_duration.sum", 1), ("DRAM rd MB", "dram__bytes_rea
         ("st short_sb", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", 1)]
 units = rows[1]
 lines = [f"# ncu --set full summary: `{rep.split('/')[-1]}`", "",
-         "Command: `ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"ssd_|conv_|gemm_bf16|norm_|pack_mixer" python scratch/ncu_target.py`",
+         "Command: `ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:\"ssd_|conv_|gemm_bf16|norm_|pack_mixer\" python scratch/ncu_target.py`",
          "(one bidirectional MambaBlock forward+backward at the headline shape B = 40 x 398 frames, d = 384, bf16, plus one",
          "chunk/dechunk round trip).  Per-launch values; durations are cold-cache and serialised (ncu replays each kernel).",
          "`st *` = average warps stalled for that reason per issue-active cycle.", "",
