@@ -75,6 +75,17 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
                ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+// descriptor = (hi << 32) | lo with lo = start address (16-byte units, 14 bits) | LBO << 16 and a constant hi word (SBO 1024 B,
+// version 1, SWIZZLE_128B): the issuing thread only adds to the 32-bit low word (uniform datapath), see the MMA loops
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(0x40004040u));
+  return d;
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+
 struct GemmParams {
   int M, N, K;
   int tiles_m, tiles_n, splitk, kblocks_per_split, total_kb;
@@ -305,6 +316,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma::make_idesc_bf16(BM, BN, TA, TB);
+      const uint32_t dA_ring = desc_lo(umma::smem_u32(sA), TA == 0 ? 16 : 8192);
+      const uint32_t dB_ring = desc_lo(umma::smem_u32(sB), TB == 0 ? 16 : 8192);
       uint32_t it = 0, li = 0;
       for (int item = first_item; item < n_items; item += item_stride, ++li) {
         int m0, n0, kb0, nkb;
@@ -318,16 +331,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           umma::mbar_wait(&full[s], ph);
           umma::tc_fence_after();
-          const uint32_t a = umma::smem_u32(sA + s * A_STAGE);
-          const uint32_t b = umma::smem_u32(sB + s * B_STAGE);
+          // descriptors by 64-bit adds on the ring's base descriptors (the start-address field counts 16-byte units and
+          // never carries out of its 14 bits: shared memory ends below 256 KB).  The issuing thread is ONE thread: rebuilding
+          // both descriptors from addresses cost ~16 instructions per MMA and made the issue loop (~830 cycles per k-block,
+          // HNB_GEMM_DEBUG=1) slower than the 512 cycles the four MMAs take.
+          const uint32_t da0 = dA_ring + (uint32_t)s * (uint32_t)(A_STAGE >> 4);
+          const uint32_t db0 = dB_ring + (uint32_t)s * (uint32_t)(B_STAGE >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = (TA == 0) ? umma::make_smem_desc(a + k * 32, 16, 1024)
-                                          : umma::make_smem_desc(a + k * 2048, 8192, 1024);
-            const uint64_t db = (TB == 0) ? umma::make_smem_desc(b + k * 32, 16, 1024)
-                                          : umma::make_smem_desc(b + k * 2048, 8192, 1024);
-            umma::mma_bf16_ss(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma::mma_bf16_ss(tmem_d, desc_from_lo(da0 + (uint32_t)(TA == 0 ? k * 2 : k * 128)),
+                              desc_from_lo(db0 + (uint32_t)(TB == 0 ? k * 2 : k * 128)), idesc, (i > 0 || k > 0) ? 1u : 0u);
           if (CL == 1) umma::mma_commit(&empty[s]);                        // frees the smem slot when the MMAs retire
           else umma::mma_commit_mc(&empty[s], 0x3);                        // ... in both CTAs: either may refill it
         }
@@ -442,6 +455,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0 && crank == 0) {
       // ---------------- MMA issuer (leader only) ----------------
       constexpr uint32_t idesc = umma::make_idesc_bf16(2 * BM, PAIR_BN, TA, TB);
+      const uint32_t dA_ring = desc_lo(umma::smem_u32(sA), TA == 0 ? 16 : 8192);
+      const uint32_t dB_ring = desc_lo(umma::smem_u32(sB), TB == 0 ? 16 : 8192);
       uint32_t it = 0, li = 0;
       for (int item = first_item; item < n_items; item += item_stride, ++li) {
         int m0, n0, kb0, nkb;
@@ -455,16 +470,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t ph = (it / PAIR_STAGES) & 1;
           umma::mbar_wait(&full[s], ph);
           umma::tc_fence_after();
-          const uint32_t a = umma::smem_u32(sA + s * A_STAGE);
-          const uint32_t b = umma::smem_u32(sB + s * PAIR_B_STAGE);
+          const uint32_t da0 = dA_ring + (uint32_t)s * (uint32_t)(A_STAGE >> 4);
+          const uint32_t db0 = dB_ring + (uint32_t)s * (uint32_t)(PAIR_B_STAGE >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = (TA == 0) ? umma::make_smem_desc(a + k * 32, 16, 1024)
-                                          : umma::make_smem_desc(a + k * 2048, 8192, 1024);
-            const uint64_t db = (TB == 0) ? umma::make_smem_desc(b + k * 32, 16, 1024)
-                                          : umma::make_smem_desc(b + k * 2048, 8192, 1024);
-            umma::mma_bf16_ss_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma::mma_bf16_ss_pair(tmem_d, desc_from_lo(da0 + (uint32_t)(TA == 0 ? k * 2 : k * 128)),
+                                   desc_from_lo(db0 + (uint32_t)(TB == 0 ? k * 2 : k * 128)), idesc, (i > 0 || k > 0) ? 1u : 0u);
           umma::mma_commit_pair(&empty[s], 0x3);                           // frees the slot in both CTAs
         }
         umma::mma_commit_pair(&tmem_full[acc], 0x3);

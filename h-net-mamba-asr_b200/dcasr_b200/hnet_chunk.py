@@ -59,16 +59,19 @@ _WQK_CACHE: dict = {}
 
 def _packed_router_weights(Wq, Wk, adt):
     """W_q | W_k stacked and cast for the one router GEMM; rebuilt only when a parameter was written (its version counter
-    moves with every optimiser step) -- under no_grad / decode this is once per model, not once per call."""
+    moves with every optimiser step) -- under no_grad / decode this is once per model, not once per call.  An entry is
+    valid only for the very tensor objects it was built from (weak references): a freed parameter's address is reused by
+    the allocator, and a new tensor at the same address with the same version count must not hit."""
+    import weakref
     key = (Wq.data_ptr(), Wk.data_ptr(), adt)
     ver = (Wq._version, Wk._version)
     hit = _WQK_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[2]() is Wq and hit[3]() is Wk:
         return hit[1]
     w = torch.cat([Wq.detach(), Wk.detach()], 0).to(adt)
     if len(_WQK_CACHE) > 64:
         _WQK_CACHE.clear()
-    _WQK_CACHE[key] = (ver, w)
+    _WQK_CACHE[key] = (ver, w, weakref.ref(Wq), weakref.ref(Wk))
     return w
 
 
