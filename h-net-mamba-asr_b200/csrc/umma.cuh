@@ -34,14 +34,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// With a suspend-time hint the thread sleeps in hardware until the phase completes (or the hint elapses) instead of returning
+// after the short default interval: a warp that waits no longer takes issue slots from the warps of its scheduler that work
+// (ncu, fused SSD backward: 34 % of all executed instructions were this poll loop).
+#ifndef HNB_MBAR_SUSPEND_NS
+#define HNB_MBAR_SUSPEND_NS 20000u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(HNB_MBAR_SUSPEND_NS)
       : "memory");
   return ok != 0;
 }
@@ -53,7 +59,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 26)) {
+    if (++polls > (1u << 22)) {
       printf("hnet_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x);
       __trap();
