@@ -313,7 +313,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (umma::elect_one()) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma::make_idesc_bf16(BM, BN, TA, TB);
       const uint32_t dA_ring = desc_lo(umma::smem_u32(sA), TA == 0 ? 16 : 8192);
@@ -452,7 +452,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+    if (crank == 0 && umma::elect_one()) {
       // ---------------- MMA issuer (leader only) ----------------
       constexpr uint32_t idesc = umma::make_idesc_bf16(2 * BM, PAIR_BN, TA, TB);
       const uint32_t dA_ring = desc_lo(umma::smem_u32(sA), TA == 0 ? 16 : 8192);
