@@ -61,3 +61,26 @@ def test_install_shim_provides_mamba_ssm():
             sys.modules["mamba_ssm"] = saved
         else:
             sys.modules.pop("mamba_ssm", None)
+
+
+def test_ctc_host_helpers():
+    """Host-side pieces of the CTC head that need no GPU: the greedy collapse rule (reference decoders/ctc.py:70-83), the
+    unpacking of 1-D concatenated targets, the padded row stride of the logits buffer, and the CPU refusal."""
+    import pytest
+    import torch
+    import dcasr_b200 as dd
+    from dcasr_b200.ctc import _ld, _pad_targets
+    assert dd.ctc_greedy_collapse([5, 5, 9, 9, 5, 9, 3, 3, 9], 9) == [5, 5, 3]          # a blank separates equal labels
+    assert dd.ctc_greedy_collapse([], 9) == [] and dd.ctc_greedy_collapse([9, 9], 9) == []
+    flat = torch.tensor([1, 2, 3, 7, 8])
+    pad = _pad_targets(flat, torch.tensor([3, 0, 2]), 3)
+    assert pad.shape == (3, 3) and pad.dtype == torch.int64
+    assert pad[0].tolist() == [1, 2, 3] and pad[2, :2].tolist() == [7, 8]
+    two_d = torch.tensor([[1, 2], [3, 4]], dtype=torch.int32)
+    assert _pad_targets(two_d, torch.tensor([2, 1]), 2).dtype == torch.int64
+    assert _ld(501) == 512 and _ld(512) == 512 and _ld(6) == 16                       # 32-byte aligned bf16 rows
+    head = dd.CTCHead(8, 5)
+    assert head.blank_id == 5 and head.num_classes == 6 and sorted(head.state_dict()) == ["proj.bias", "proj.weight"]
+    assert dd.CTCHead(8, 5, blank_id=0).blank_id == 0
+    with pytest.raises(dd.HnbError):
+        head.loss(torch.randn(1, 3, 8), torch.tensor([3]), torch.tensor([[1]]), torch.tensor([1]))
