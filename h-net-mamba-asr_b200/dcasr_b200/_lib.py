@@ -54,7 +54,7 @@ def _ctype(ty: str):
     ty = ty.replace("const ", "").strip()
     if ty.endswith("*"):
         return ctypes.c_char_p if ty == "char*" else ctypes.c_void_p
-    return {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float,
+    return {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double,
             "void": None}[ty]
 
 

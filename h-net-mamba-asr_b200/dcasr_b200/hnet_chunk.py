@@ -185,7 +185,8 @@ class _EmaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, p, p_clamp):
         xc = x.contiguous()
-        Pf = p.to(torch.float32).contiguous()
+        # weights in >= fp32 (hnet_chunk.py:242); float64 inputs (the reference's gradcheck tests) keep float64 throughout
+        Pf = p.to(torch.float64 if xc.dtype == torch.float64 else torch.float32).contiguous()
         out = ops.ema_fwd(xc, Pf, p_clamp)
         ctx.save_for_backward(xc, out, Pf)
         ctx.meta = (p_clamp, p.dtype)

@@ -145,6 +145,9 @@ def compact_rows_bwd(dz, b, memb, L, dx=None):
 def ema_fwd(x, P, p_clamp=1e-4):
     B, M, D = x.shape
     out = torch.empty_like(x)
+    if x.dtype == torch.float64:                    # the reference's double-precision gradchecks (csrc/f64_kernels.cu)
+        lib().call("ema_fwd_f64", x, P, B, M, D, float(p_clamp), out, stream())
+        return out
     lib().call("ema_fwd", x, dtype_code(x.dtype), P, B, M, D, float(p_clamp), out, stream())
     return out
 
@@ -153,6 +156,9 @@ def ema_bwd(dout, x, out, P, p_clamp=1e-4):
     B, M, D = x.shape
     dx = torch.empty_like(x)
     dP = torch.zeros_like(P)
+    if x.dtype == torch.float64:
+        lib().call("ema_bwd_f64", dout, x, out, P, B, M, D, float(p_clamp), dx, dP, stream())
+        return dx, dP
     lib().call("ema_bwd", dout, x, out, dtype_code(x.dtype), P, B, M, D, float(p_clamp), dx, dP, stream())
     return dx, dP
 
@@ -359,6 +365,9 @@ def window_reduce(x, mask_u8, M, stride, normalize, z_dtype, want_cnt=True):
     B, L, D = x.shape
     z = _empty((B, M, D), z_dtype, x)
     cnt = _empty((B, M), torch.float32, x) if want_cnt else None
+    if x.dtype == torch.float64 and z_dtype == torch.float64:
+        lib().call("window_reduce_f64", x, mask_u8, B, L, D, M, int(stride), int(bool(normalize)), z, cnt, stream())
+        return z, cnt
     lib().call("window_reduce", x, dtype_code(x.dtype), mask_u8, B, L, D, M, int(stride), int(bool(normalize)), z,
                dtype_code(z_dtype), cnt, stream())
     return z, cnt
@@ -368,6 +377,9 @@ def window_broadcast(z, mask_u8, cnt, resid, L, stride, out_dtype):
     """z [B,M,D] -> out [B,L,D]: out[b,t] = m[b,t] / max(cnt[b,w],1) * z[b,w(t)] (+ resid), w(t) = min(t//stride, M-1)."""
     B, M, D = z.shape
     out = _empty((B, L, D), out_dtype, z)
+    if z.dtype == torch.float64 and out_dtype == torch.float64:
+        lib().call("window_broadcast_f64", z, mask_u8, cnt, resid, B, L, D, M, int(stride), out, stream())
+        return out
     lib().call("window_broadcast", z, dtype_code(z.dtype), mask_u8, cnt, resid, B, L, D, M, int(stride), out,
                dtype_code(out_dtype), stream())
     return out

@@ -317,6 +317,17 @@ int hnb_ctc_grad(const void* logits, int dtype, const float* lse, const float* a
                  const float* gscale, int B, int T, int V1, long long ldl, int U, int blank, void* dlogits, long long ldd,
                  void* stream);
 
+/* float64 twins of hnb_ema_fwd / _bwd (P float64 too) and hnb_window_reduce / _broadcast, for the reference's own
+ * double-precision gradcheck tests of DynamicChunker._ema (tests/test_hnet_chunk.py:242-263) and of the fixed-stride pool
+ * (tests/test_fixed_pool.py:197-207); one thread per (row, channel), test-sized tensors.  dP pre-zeroed. */
+int hnb_ema_fwd_f64(const double* x, const double* P, int B, int M, int D, double p_clamp, double* out, void* stream);
+int hnb_ema_bwd_f64(const double* dout, const double* x, const double* out, const double* P, int B, int M, int D,
+                    double p_clamp, double* dx, double* dP, void* stream);
+int hnb_window_reduce_f64(const double* x, const uint8_t* mask, int B, int L, int D, int M, int stride, int normalize,
+                          double* z, float* cnt, void* stream);
+int hnb_window_broadcast_f64(const double* z, const uint8_t* mask, const float* cnt, const double* resid, int B, int L,
+                             int D, int M, int stride, double* out, void* stream);
+
 /* out[c] += sum over rows of x[r, c] (fp32, ACCUMULATED into a pre-zeroed buffer): the bias gradient of nn.Linear
  * (CTCHead.proj, DCASREncoder.proj_in / proj_out: src/dcasr/models/encoder.py:104-111), x row-major with row stride ldx. */
 int hnb_col_sum(const void* x, int dtype, long long rows, int cols, long long ldx, float* out, void* stream);
