@@ -60,6 +60,16 @@ Small small_ptrs(const Dims& m, uint8_t* base) {
   return s;
 }
 
+// weights of one block as hnb_pack_mixer_stack leaves them: Win | Wout | small vectors
+size_t packed_layout(const Dims& m, size_t* off3) {
+  const size_t a = esz(m.act);
+  const size_t sz[3] = {(size_t)m.ldz() * m.d * a, (size_t)m.d * m.ndir * m.di * a,
+                        (size_t)m.ndir * (m.C() * 5 + 3 * m.H + m.di) * 4};
+  size_t o = 0;
+  for (int i = 0; i < 3; ++i) { off3[i] = o; o += up(sz[i]); }
+  return o;
+}
+
 // backward scratch (dead when the call returns)
 enum { S_DA, S_DYN, S_DZX, S_DY, S_DXC, S_DBC, S_DDT, S_WS2, S_DH2, S_GEMM, S_COUNT };
 size_t bwd_layout(const Dims& m, int parts, size_t* off) {
@@ -130,6 +140,17 @@ int gemm(int act, const void* A, long long lda, int tA, const void* Bm, long lon
 
 using namespace hnb;
 
+extern "C" long long hnb_block_packed_layout(int d, int ndir, int di, int N, int H, int act_dtype, long long* off3) {
+  const Dims m{1, 1, d, ndir, di, N, H, act_dtype};
+  size_t o[3];
+  const size_t n = packed_layout(m, o);
+  if (off3) for (int i = 0; i < 3; ++i) off3[i] = (long long)o[i];
+  return (long long)n;
+}
+extern "C" long long hnb_block_packed_bytes(int d, int ndir, int di, int N, int H, int act_dtype) {
+  return hnb_block_packed_layout(d, ndir, di, N, H, act_dtype, nullptr);
+}
+
 extern "C" long long hnb_block_fwd_ws_bytes(int B, int L, int d, int ndir, int di, int N, int H, int act_dtype) {
   const Dims m{B, L, d, ndir, di, N, H, act_dtype};
   size_t off[F_COUNT];
@@ -150,11 +171,12 @@ extern "C" long long hnb_block_grad_floats(int B, int L, int d, int ndir, int di
 
 extern "C" int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths, const float* ln_w, const float* ln_b,
                              const void* const* params, int B, int L, int d, int ndir, int di, int N, int H,
-                             int act_dtype, int ssd_impl, void* out, void* ws, void* stream) {
+                             int act_dtype, int ssd_impl, const void* packed, void* out, void* ws, void* stream) {
   const Dims m{B, L, d, ndir, di, N, H, act_dtype};
   HNB_TRY(check_dims("block_fwd", m, x_dtype));
-  HNB_CHECK_ARG(x && ln_w && ln_b && params && out && ws, "block_fwd: null pointer");
-  for (int i = 0; i < 8 * ndir; ++i) HNB_CHECK_ARG(params[i] != nullptr, "block_fwd: null parameter pointer");
+  HNB_CHECK_ARG(x && ln_w && ln_b && (params || packed) && out && ws, "block_fwd: null pointer");
+  if (!packed)
+    for (int i = 0; i < 8 * ndir; ++i) HNB_CHECK_ARG(params[i] != nullptr, "block_fwd: null parameter pointer");
   size_t off[F_COUNT];
   fwd_layout(m, off);
   uint8_t* w = static_cast<uint8_t*>(ws);
@@ -163,8 +185,11 @@ extern "C" int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths,
   void* h2 = w + off[F_H2];
   float* mean = reinterpret_cast<float*>(w + off[F_MEAN]);
   float* rstd_ln = reinterpret_cast<float*>(w + off[F_RSTDLN]);
-  void* Win = w + off[F_WIN]; void* Wout = w + off[F_WOUT];
-  const Small s = small_ptrs(m, w + off[F_SMALL]);
+  size_t po[3];
+  packed_layout(m, po);
+  uint8_t* pk = const_cast<uint8_t*>(static_cast<const uint8_t*>(packed));     // weights packed once per stack, or here
+  void* Win = packed ? pk + po[0] : w + off[F_WIN]; void* Wout = packed ? pk + po[1] : w + off[F_WOUT];
+  const Small s = small_ptrs(m, packed ? pk + po[2] : w + off[F_SMALL]);
   void* zx = w + off[F_ZX]; void* xconv = w + off[F_XCONV];
   float* dt = reinterpret_cast<float*>(w + off[F_DT]);
   void* y = w + off[F_Y]; void* ssd = w + off[F_SSD]; void* yn = w + off[F_YN];
@@ -172,7 +197,9 @@ extern "C" int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths,
   const float* const* P = reinterpret_cast<const float* const*>(params);   // per direction: in_w, conv_w, conv_b, dt_bias, A_log, D, norm_w, out_w
 
   HNB_TRY(hnb_layernorm_fwd(x, x_dtype, ln_w, ln_b, T, d, 1e-5f, h2, act_dtype, mean, rstd_ln, stream));
-  if (ndir == 2)
+  if (packed) {
+    // nothing to pack
+  } else if (ndir == 2)
     HNB_TRY(hnb_pack_mixer_params2(P[0], P[7], P[1], P[2], P[3], P[4], P[5], P[6], P[8], P[15], P[9], P[10], P[11], P[12],
                                    P[13], P[14], d, di, N, H, dstride, Win, Wout, act_dtype, s.conv_w, s.conv_b, s.dt_bias,
                                    s.A_log, s.D, s.norm_w, stream));
@@ -193,7 +220,8 @@ extern "C" int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths,
 
 extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const int32_t* lengths, const float* ln_w,
                              const void* ws, int B, int L, int d, int ndir, int di, int N, int H, int act_dtype,
-                             int ssd_impl, void* dx, float* grads, int zero_grads, void* scratch, void* stream) {
+                             int ssd_impl, const void* packed, void* dx, float* grads, int zero_grads, void* scratch,
+                             void* stream) {
   const Dims m{B, L, d, ndir, di, N, H, act_dtype};
   HNB_TRY(check_dims("block_bwd", m, x_dtype));
   HNB_CHECK_ARG(dout && x && ln_w && ws && dx && grads && scratch, "block_bwd: null pointer");
@@ -209,8 +237,11 @@ extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const
   const void* h2 = w + off[F_H2];
   const float* mean = reinterpret_cast<const float*>(w + off[F_MEAN]);
   const float* rstd_ln = reinterpret_cast<const float*>(w + off[F_RSTDLN]);
-  const void* Win = w + off[F_WIN]; const void* Wout = w + off[F_WOUT];
-  const Small s = small_ptrs(m, const_cast<uint8_t*>(w) + off[F_SMALL]);
+  size_t po[3];
+  packed_layout(m, po);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  const void* Win = packed ? pk + po[0] : w + off[F_WIN]; const void* Wout = packed ? pk + po[1] : w + off[F_WOUT];
+  const Small s = small_ptrs(m, const_cast<uint8_t*>(packed ? pk + po[2] : w + off[F_SMALL]));
   const void* zx = w + off[F_ZX]; const void* xconv = w + off[F_XCONV];
   const float* dt = reinterpret_cast<const float*>(w + off[F_DT]);
   const void* y = w + off[F_Y]; const void* ssd = w + off[F_SSD]; const void* yn = w + off[F_YN];

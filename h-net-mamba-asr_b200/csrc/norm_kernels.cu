@@ -370,19 +370,33 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
 // in_proj.weight -> rows [dir*dstride, +dip) of Win (pad rows zeroed), out_proj.weight -> columns [dir*di, +di) of
 // Wout, both cast to the activation dtype; the small fp32 vectors are copied into their [ndir, ...] stacks.
 // ---------------------------------------------------------------------------------------------
-struct PackSrc { const float* p[2][8]; };          // per direction: in_w, out_w, conv_w, conv_b, dt_bias, A_log, D, norm_w
+constexpr int PACK_MAX_LAYERS = 24;
+// per layer and direction: in_w, out_w, conv_w, conv_b, dt_bias, A_log, D, norm_w  (3 KB: passed by value as a kernel argument)
+struct PackSrc { const float* p[PACK_MAX_LAYERS][2][8]; };
 
 template <typename TW>
 __global__ void __launch_bounds__(256)
 pack_mixer_kernel(const PackSrc src, int dir0, int ndir, int d, int di, const FastDiv dd4, const FastDiv ddi4,
                   int N, int H, int dstride, TW* __restrict__ Win, TW* __restrict__ Wout, float* __restrict__ conv_w_o,
                   float* __restrict__ conv_b_o, float* __restrict__ dt_bias_o, float* __restrict__ A_log_o,
-                  float* __restrict__ D_o, float* __restrict__ norm_w_o) {
-  const int dir = dir0 + blockIdx.y;                                // one launch packs gridDim.y directions
-  const float* __restrict__ in_w = src.p[blockIdx.y][0]; const float* __restrict__ out_w = src.p[blockIdx.y][1];
-  const float* __restrict__ conv_w = src.p[blockIdx.y][2]; const float* __restrict__ conv_b = src.p[blockIdx.y][3];
-  const float* __restrict__ dt_bias = src.p[blockIdx.y][4]; const float* __restrict__ A_log = src.p[blockIdx.y][5];
-  const float* __restrict__ Dk = src.p[blockIdx.y][6]; const float* __restrict__ norm_w = src.p[blockIdx.y][7];
+                  float* __restrict__ D_o, float* __restrict__ norm_w_o, long long layer_stride_bytes) {
+  const int dir = dir0 + blockIdx.y;                                // one launch packs gridDim.y directions of gridDim.z layers
+  const int ly = blockIdx.z;
+  {
+    const long long off = (long long)ly * layer_stride_bytes;       // every output of layer ly sits `off` bytes after layer 0's
+    Win = reinterpret_cast<TW*>(reinterpret_cast<uint8_t*>(Win) + off);
+    Wout = reinterpret_cast<TW*>(reinterpret_cast<uint8_t*>(Wout) + off);
+    conv_w_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(conv_w_o) + off);
+    conv_b_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(conv_b_o) + off);
+    dt_bias_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dt_bias_o) + off);
+    A_log_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(A_log_o) + off);
+    D_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(D_o) + off);
+    norm_w_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(norm_w_o) + off);
+  }
+  const float* __restrict__ in_w = src.p[ly][blockIdx.y][0]; const float* __restrict__ out_w = src.p[ly][blockIdx.y][1];
+  const float* __restrict__ conv_w = src.p[ly][blockIdx.y][2]; const float* __restrict__ conv_b = src.p[ly][blockIdx.y][3];
+  const float* __restrict__ dt_bias = src.p[ly][blockIdx.y][4]; const float* __restrict__ A_log = src.p[ly][blockIdx.y][5];
+  const float* __restrict__ Dk = src.p[ly][blockIdx.y][6]; const float* __restrict__ norm_w = src.p[ly][blockIdx.y][7];
   const int dip = 2 * di + 2 * N + H, C = di + 2 * N;
   // The two weight matrices are 99.9 % of the bytes: 32-bit index arithmetic (multiply-high division) and four
   // independent 16-byte loads in flight per thread -- the first version spent its time in 64-bit divisions
@@ -587,20 +601,24 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
 
 static int pack_launch(const PackSrc& src, int ndirs, int dir0, int ndir, int d, int di, int N, int H, int dstride,
                        void* Win, void* Wout, int w_dtype, float* conv_w_o, float* conv_b_o, float* dt_bias_o,
-                       float* A_log_o, float* D_o, float* norm_w_o, void* stream) {
+                       float* A_log_o, float* D_o, float* norm_w_o, void* stream, int nlayers = 1,
+                       long long layer_stride_bytes = 0) {
   HNB_CHECK_ARG(Win && Wout && conv_w_o && conv_b_o && dt_bias_o && A_log_o && D_o && norm_w_o, "pack_mixer_params: null pointer");
-  for (int r = 0; r < ndirs; ++r)
-    for (int k = 0; k < 8; ++k) HNB_CHECK_ARG(src.p[r][k] != nullptr, "pack_mixer_params: null pointer");
+  HNB_CHECK_ARG(nlayers >= 1 && nlayers <= PACK_MAX_LAYERS, "pack_mixer_params: at most %d layers per call", PACK_MAX_LAYERS);
+  for (int l = 0; l < nlayers; ++l)
+    for (int r = 0; r < ndirs; ++r)
+      for (int k = 0; k < 8; ++k) HNB_CHECK_ARG(src.p[l][r][k] != nullptr, "pack_mixer_params: null pointer");
   HNB_CHECK_ARG(d % 4 == 0 && di % 4 == 0 && dir0 >= 0 && dir0 + ndirs <= ndir && dstride >= 2 * di + 2 * N + H,
                 "pack_mixer_params: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = ((long long)dstride * d + (long long)d * di) / 4 + (long long)(di + 2 * N) * 5 + 3 * H + di;
   HNB_CHECK_ARG((long long)dstride * d < (1LL << 31) && (long long)d * di < (1LL << 31), "pack_mixer_params: weights too large");
   int gx = cdiv(total, 256 * 4);
-  if (gx > 148 * 8 / ndirs) gx = 148 * 8 / ndirs;
-  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<dim3(gx, ndirs), 256, 0, st>>>(src, dir0, ndir, d, di,
+  const int cap = 148 * 8 / (ndirs * (nlayers < 4 ? nlayers : 4));
+  if (gx > cap) gx = cap > 0 ? cap : 1;
+  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<dim3(gx, ndirs, nlayers), 256, 0, st>>>(src, dir0, ndir, d, di,
       FastDiv(d / 4), FastDiv(di / 4), N, H,
-      dstride, (TW*)Win, (TW*)Wout, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o, norm_w_o)));
+      dstride, (TW*)Win, (TW*)Wout, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o, norm_w_o, layer_stride_bytes)));
   HNB_LAUNCH_CHECK("pack_mixer_params");
   return HNB_OK;
 }
@@ -612,7 +630,7 @@ extern "C" int hnb_pack_mixer_params(const float* in_w, const float* out_w, cons
                                      float* D_o, float* norm_w_o, void* stream) {
   PackSrc src = {};
   const float* one[8] = {in_w, out_w, conv_w, conv_b, dt_bias, A_log, Dk, norm_w};
-  for (int k = 0; k < 8; ++k) src.p[0][k] = one[k];
+  for (int k = 0; k < 8; ++k) src.p[0][0][k] = one[k];
   return pack_launch(src, 1, dir, ndir, d, di, N, H, dstride, Win, Wout, w_dtype, conv_w_o, conv_b_o, dt_bias_o, A_log_o,
                      D_o, norm_w_o, stream);
 }
@@ -627,7 +645,46 @@ extern "C" int hnb_pack_mixer_params2(const float* in_w0, const float* out_w0, c
   PackSrc src = {};
   const float* a[8] = {in_w0, out_w0, conv_w0, conv_b0, dt_bias0, A_log0, Dk0, norm_w0};
   const float* b[8] = {in_w1, out_w1, conv_w1, conv_b1, dt_bias1, A_log1, Dk1, norm_w1};
-  for (int k = 0; k < 8; ++k) { src.p[0][k] = a[k]; src.p[1][k] = b[k]; }
+  for (int k = 0; k < 8; ++k) { src.p[0][0][k] = a[k]; src.p[0][1][k] = b[k]; }
   return pack_launch(src, 2, 0, 2, d, di, N, H, dstride, Win, Wout, w_dtype, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o,
                      norm_w_o, stream);
+}
+
+// Every block of a stack in ONE launch (grid z = layer): 20 launches of ~18 us per encoder step were latency, not traffic
+// (a step casts 248 MB of fp32 masters, ~60 us of HBM time).  params: HOST array [nlayers][ndir][8] of device pointers in the
+// order of hnb_block_fwd's `params` (in_proj.w, conv1d.w, conv1d.b, dt_bias, A_log, D, norm.w, out_proj.w); packed: nlayers
+// blocks of hnb_block_packed_bytes() bytes, laid out as hnb_block_fwd / hnb_block_bwd expect their `packed` argument.
+extern "C" long long hnb_block_packed_layout(int d, int ndir, int di, int N, int H, int act_dtype, long long* off3);
+extern "C" int hnb_pack_mixer_stack(const void* const* params, int nlayers, int ndir, int d, int di, int N, int H, int act_dtype,
+                                    void* packed, void* stream) {
+  HNB_CHECK_ARG(params && packed && nlayers >= 1 && (ndir == 1 || ndir == 2), "pack_mixer_stack: bad arguments");
+  const int dip = 2 * di + 2 * N + H, dstride = (dip + 7) / 8 * 8, C = di + 2 * N;
+  long long off[3];
+  const long long per = hnb_block_packed_layout(d, ndir, di, N, H, act_dtype, off);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  float* sm = reinterpret_cast<float*>(base + off[2]);
+  float* conv_w = sm; float* conv_b = conv_w + (size_t)ndir * C * 4; float* dt_bias = conv_b + (size_t)ndir * C;
+  float* A_log = dt_bias + (size_t)ndir * H; float* Dk = A_log + (size_t)ndir * H; float* norm_w = Dk + (size_t)ndir * H;
+  const float* const* P = reinterpret_cast<const float* const*>(params);
+  for (int l0 = 0; l0 < nlayers; l0 += PACK_MAX_LAYERS) {
+    const int nl = nlayers - l0 < PACK_MAX_LAYERS ? nlayers - l0 : PACK_MAX_LAYERS;
+    PackSrc src = {};
+    for (int l = 0; l < nl; ++l)
+      for (int r = 0; r < ndir; ++r) {
+        const float* const* q = P + ((size_t)(l0 + l) * ndir + r) * 8;
+        // block order: in_w, conv_w, conv_b, dt_bias, A_log, D, norm_w, out_w  ->  kernel order: in_w, out_w, conv_w, ...
+        const float* k8[8] = {q[0], q[7], q[1], q[2], q[3], q[4], q[5], q[6]};
+        for (int k = 0; k < 8; ++k) src.p[l][r][k] = k8[k];
+      }
+    const long long shift = (long long)l0 * per;
+    int rc = pack_launch(src, ndir, 0, ndir, d, di, N, H, dstride, base + shift + off[0], base + shift + off[1], act_dtype,
+                         reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(conv_w) + shift),
+                         reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(conv_b) + shift),
+                         reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dt_bias) + shift),
+                         reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(A_log) + shift),
+                         reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(Dk) + shift),
+                         reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(norm_w) + shift), stream, nl, per);
+    if (rc != HNB_OK) return rc;
+  }
+  return HNB_OK;
 }

@@ -25,6 +25,8 @@ from .hnet_chunk import _autocast_dtype
 # MambaBlock through the library's one-call-per-block composites (hnb_block_fwd / hnb_block_bwd).  "0" keeps the
 # per-kernel Python orchestration (_MixerFn), which is also what a profiled step uses: bench.py times every entry point.
 BLOCK_COMPOSITE = os.environ.get("HNB_BLOCK_COMPOSITE", "1") != "0"
+# MambaStack packs the weights of all its blocks in one launch ("0": every block packs its own inside hnb_block_fwd)
+STACK_PACK = os.environ.get("HNB_STACK_PACK", "1") != "0"
 
 
 def _round_up(v: int, m: int) -> int:
@@ -216,7 +218,7 @@ class _BlockFn(torch.autograd.Function):
     which is what keeps eight ranks sharing one host from becoming launch-bound."""
 
     @staticmethod
-    def forward(ctx, x, lengths, ln_w, ln_b, ndir, di, N, H, *params):
+    def forward(ctx, x, lengths, ln_w, ln_b, ndir, di, N, H, packed, *params):
         B, L, d = x.shape
         adt = _autocast_dtype() or x.dtype
         x2 = x.reshape(B * L, d)
@@ -236,14 +238,14 @@ class _BlockFn(torch.autograd.Function):
         out2 = torch.empty_like(x2)
         ln_w32, ln_b32 = ln_w.detach().float().contiguous(), ln_b.detach().float().contiguous()
         L_.call("block_fwd", x2, xdt, lengths, ln_w32, ln_b32, ctypes.addressof(ptrs), B, L, d, ndir, di, N, H, act, impl,
-                out2, ws, stream())
-        ctx.save_for_backward(x2, lengths, ln_w32, ws)
+                packed, out2, ws, stream())
+        ctx.save_for_backward(x2, lengths, ln_w32, ws, packed)
         ctx.meta = (B, L, d, ndir, di, N, H, act, xdt, impl, x.dtype, [p_.dtype for p_ in params], ln_w.dtype)
         return out2.view(B, L, d)
 
     @staticmethod
     def backward(ctx, dout):
-        x2, lengths, ln_w32, ws = ctx.saved_tensors
+        x2, lengths, ln_w32, ws, packed = ctx.saved_tensors
         B, L, d, ndir, di, N, H, act, xdt, impl, x_dtype, pdts, ln_dtype = ctx.meta
         dout2 = dout.reshape(B * L, d)
         dout2 = dout2 if dout2.is_contiguous() else dout2.contiguous()
@@ -257,8 +259,8 @@ class _BlockFn(torch.autograd.Function):
         scratch = torch.empty(L_.raw("block_bwd_ws_bytes")(B, L, d, ndir, di, N, H, act, impl), dtype=torch.uint8,
                               device=x2.device)
         dx2 = torch.empty_like(x2)
-        L_.call("block_bwd", dout2, x2, xdt, lengths, ln_w32, ws, B, L, d, ndir, di, N, H, act, impl, dx2, arena, 1, scratch,
-                stream())
+        L_.call("block_bwd", dout2, x2, xdt, lengths, ln_w32, ws, B, L, d, ndir, di, N, H, act, impl, packed, dx2, arena, 1,
+                scratch, stream())
         C, dip = di + 2 * N, 2 * di + 2 * N + H
         dstride = _round_up(dip, 8)
         o = list(offs)
@@ -279,7 +281,7 @@ class _BlockFn(torch.autograd.Function):
         dg, db = ln[0], ln[1]
         if ln_dtype != torch.float32:
             dg, db = dg.to(ln_dtype), db.to(ln_dtype)
-        return (dx2.view(B, L, d), None, dg, db, None, None, None, None, *pg)
+        return (dx2.view(B, L, d), None, dg, db, None, None, None, None, None, *pg)
 
 
 class MambaBlock(nn.Module):
@@ -296,13 +298,15 @@ class MambaBlock(nn.Module):
         self.fwd = Mamba2(**kw)
         self.bwd = Mamba2(**kw) if bidirectional else None
 
-    def forward(self, x: torch.Tensor, lengths: torch.Tensor | None = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, lengths: torch.Tensor | None = None, packed: torch.Tensor | None = None) -> torch.Tensor:
+        """``packed`` (not in the reference signature): this block's slice of the weights MambaStack packed for all its
+        blocks in one launch; without it the block packs its own."""
         m = self.fwd
         params = m._params() + (self.bwd._params() if self.bwd is not None else ())
         ndir = 2 if self.bwd is not None else 1
         if BLOCK_COMPOSITE and _lib._PROFILE is None:
             return _BlockFn.apply(x, lengths if ndir == 2 else None, self.norm.weight, self.norm.bias, ndir,
-                                  m.d_inner, m.d_state, m.nheads, *params)
+                                  m.d_inner, m.d_state, m.nheads, packed, *params)
         return _MixerFn.apply(x, lengths if ndir == 2 else None, self.norm.weight, self.norm.bias, ndir,
                               m.d_inner, m.d_state, m.nheads, True, *params)
 
@@ -342,6 +346,34 @@ class MambaStack(nn.Module):
     def forward(self, x: torch.Tensor, lengths: torch.Tensor | None = None) -> torch.Tensor:
         if lengths is not None and lengths.dtype != torch.int32:
             lengths = lengths.to(torch.int32)
-        for layer in self.layers:
-            x = layer(x, lengths)
+        packed = self._pack_all(x) if (STACK_PACK and BLOCK_COMPOSITE and _lib._PROFILE is None and x.is_cuda) else None
+        for i, layer in enumerate(self.layers):
+            x = layer(x, lengths) if packed is None else layer(x, lengths, packed=packed[i])
         return _FinalNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps)
+
+    def _pack_all(self, x: torch.Tensor):
+        """The weights of EVERY block of the stack cast to the activation dtype and stacked per direction in ONE launch
+        (hnb_pack_mixer_stack): 20 per-block launches of ~18 us per encoder step were launch latency, not traffic."""
+        blocks = list(self.layers)
+        if not blocks:
+            return None
+        m0 = blocks[0].fwd
+        ndir = 2 if blocks[0].bwd is not None else 1
+        ps = []
+        for blk in blocks:
+            for mix in ((blk.fwd, blk.bwd) if ndir == 2 else (blk.fwd,)):
+                for t in mix._params():
+                    t = t.detach()
+                    if t.dtype != torch.float32 or t.device != x.device:
+                        return None                      # (unusual parameter dtypes: let each block validate and pack)
+                    ps.append(t if t.is_contiguous() else t.contiguous())
+        adt = _autocast_dtype() or x.dtype
+        L_ = lib()
+        act = dtype_code(adt)
+        per = int(L_.raw("block_packed_bytes")(m0.d_model, ndir, m0.d_inner, m0.d_state, m0.nheads, act))
+        buf = torch.empty((len(blocks), per), dtype=torch.uint8, device=x.device)
+        ptrs = (ctypes.c_void_p * len(ps))(*[t.data_ptr() for t in ps])
+        L_.call("pack_mixer_stack", ctypes.addressof(ptrs), len(blocks), ndir, m0.d_model, m0.d_inner, m0.d_state, m0.nheads, act,
+                buf, stream())
+        self._pack_keepalive = ps                        # contiguous copies (if any) must outlive the launch
+        return buf

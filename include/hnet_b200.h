@@ -219,11 +219,20 @@ int hnb_pack_mixer_params2(const float* in_w0, const float* out_w0, const float*
  *   params: HOST array of 8*ndir device pointers (fp32 masters), per direction in mamba_ssm order
  *           in_proj.w, conv1d.w, conv1d.b, dt_bias, A_log, D, norm.w, out_proj.w
  *   act_dtype: dtype of the activations / GEMM operands (bf16 under autocast); ssd_impl as in hnb_ssd_fwd
+ *   packed: NULL (the call casts / stacks the block's weights itself into ws), or this block's slice of the buffer
+ *           hnb_pack_mixer_stack filled for the whole stack in one launch (then `params` may be NULL); the backward
+ *           gets the same pointer.
  *   out [B*L, d] (x_dtype) = x + mixers(LayerNorm(x));  ws: hnb_block_fwd_ws_bytes() bytes, kept for the backward. */
 long long hnb_block_fwd_ws_bytes(int B, int L, int d, int ndir, int di, int N, int H, int act_dtype);
+long long hnb_block_packed_bytes(int d, int ndir, int di, int N, int H, int act_dtype);
+long long hnb_block_packed_layout(int d, int ndir, int di, int N, int H, int act_dtype, long long* off3);
+/* params: HOST array [nlayers][ndir][8] of device pointers (order as for hnb_block_fwd); packed: nlayers *
+ * hnb_block_packed_bytes() bytes.  One launch for the whole MambaStack (src/dcasr/models/mamba_block.py:59-73). */
+int hnb_pack_mixer_stack(const void* const* params, int nlayers, int ndir, int d, int di, int N, int H, int act_dtype,
+                         void* packed, void* stream);
 int hnb_block_fwd(const void* x, int x_dtype, const int32_t* lengths, const float* ln_w, const float* ln_b,
                   const void* const* params, int B, int L, int d, int ndir, int di, int N, int H,
-                  int act_dtype, int ssd_impl, void* out, void* ws, void* stream);
+                  int act_dtype, int ssd_impl, const void* packed, void* out, void* ws, void* stream);
 /* backward: dout [B*L, d] (x_dtype) -> dx [B*L, d] (x_dtype) and the parameter gradients, written into the fp32 arena
  * `grads` of hnb_block_grad_floats() floats (zero_grads != 0: the call clears the arena first on `stream`; 0: it
  * ACCUMULATES into what the caller left there).  offsets[9] (in floats) of that arena:
@@ -234,7 +243,7 @@ long long hnb_block_bwd_ws_bytes(int B, int L, int d, int ndir, int di, int N, i
 long long hnb_block_grad_floats(int B, int L, int d, int ndir, int di, int N, int H, long long* offsets);
 int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const int32_t* lengths, const float* ln_w,
                   const void* ws, int B, int L, int d, int ndir, int di, int N, int H, int act_dtype,
-                  int ssd_impl, void* dx, float* grads, int zero_grads, void* scratch, void* stream);
+                  int ssd_impl, const void* packed, void* dx, float* grads, int zero_grads, void* scratch, void* stream);
 
 /* ---- dense projections (in_proj / out_proj / router W_q,W_k / proj_in,out) ---------------- */
 /* C[M,N] = op(A) op(B) (+ bias[N]) (+ R[M,N]) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
