@@ -99,6 +99,7 @@ size_t arena_layout(const Dims& m, size_t* off) {      // in floats
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     uint2 o;
@@ -108,6 +109,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
   }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __bfloat162float(x[i]);
 }
@@ -259,8 +261,8 @@ extern "C" int hnb_block_bwd(const void* dout, const void* x, int x_dtype, const
     const long long n = T * d;
     const long long want = (n / 4 + 255) / 256;
     const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
-    if (x_dtype == HNB_F32) cast_f32_bf16_kernel<<<grid, 256, 0, st>>>((const float*)dout, (__nv_bfloat16*)buf, n / 4);
-    else cast_bf16_f32_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, (float*)buf, n);
+    if (x_dtype == HNB_F32) hnb::launch_pdl(cast_f32_bf16_kernel, dim3(grid), dim3(256), 0, st, (const float*)dout, (__nv_bfloat16*)buf, n / 4);
+    else hnb::launch_pdl(cast_bf16_f32_kernel, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dout, (float*)buf, n);
     HNB_LAUNCH_CHECK("block_bwd cast");
     da = buf;
   }

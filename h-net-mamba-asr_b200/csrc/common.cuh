@@ -203,6 +203,32 @@ __device__ __forceinline__ int scan_to_nat(int dir, int s, int len) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  An encoder step is ~375 launches of 5-50 us kernels on one stream: the launch
+// latency and the drain / ramp between two of them are a measurable share of the step.  Kernels launched through
+// launch_pdl() may become resident while their predecessor's last CTAs are still running; everything they do before
+// pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch, shared-memory fills) overlaps that tail.
+// RULE: a kernel launched through launch_pdl() executes pdl_wait() in EVERY thread before its first global-memory
+// access (read or write: the predecessor may still be reading what this kernel overwrites).  pdl_trigger() only allows
+// the successor to be scheduled early; the successor's own pdl_wait() still waits for this grid to complete and flush.
+// Without the launch attribute both instructions are no-ops.  HNB_PDL=0 switches the attribute off.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: per-launch driver queries cached (the host needs ~13 ms to enqueue one encoder step of ~650 launches, so a
 // few microseconds per launch in cudaFuncSetAttribute / occupancy queries are a measurable share of it)
 // ---------------------------------------------------------------------------------------------

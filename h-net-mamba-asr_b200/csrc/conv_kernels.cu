@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(CONV_CT * CONV_SEG)
 conv_fwd_kernel(const T* __restrict__ zx, long long ldz, long long dstride, const int* __restrict__ lengths,
                 const float* __restrict__ conv_w, const float* __restrict__ conv_b, const float* __restrict__ dt_bias,
                 int ndir, int B, int L, int di, int N, int H, T* __restrict__ xconv, float* __restrict__ dt_out) {
+  pdl_enter();
   constexpr int VN = V16<T>::N;
   constexpr int RUN = TS * NTILE;
   const int ct = threadIdx.x % CONV_CT, sg = threadIdx.x / CONV_CT;
@@ -207,6 +208,7 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
                 int ndir, int B, int L, int di, int N, int H, T* __restrict__ dzx, float* __restrict__ dconv_w,
                 float* __restrict__ dconv_b, float* __restrict__ ddt_bias, int vec_red, int dbc_parts,
                 long long dbc_part_stride) {
+  pdl_enter();
   constexpr int VN = VIO::N;
   constexpr int RUN = TS * NTILE - 3;
   static_assert(TS > 3, "layout");
@@ -395,11 +397,11 @@ extern "C" int hnb_conv_fwd(const void* zxbcdt, int dtype, long long ldz, long l
   dim3 grid(cdiv(C / 4, CONV_CT), cdiv(L, CONV_SEG * CONV_F_TS * CONV_F_NT), ndir * B);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == HNB_BF16)
-    conv_fwd_kernel<__nv_bfloat16, CONV_F_TS, CONV_F_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+    hnb::launch_pdl(conv_fwd_kernel<__nv_bfloat16, CONV_F_TS, CONV_F_NT>, dim3(grid), dim3(CONV_CT * CONV_SEG), 0, st, 
         (const __nv_bfloat16*)zxbcdt, ldz, dstride, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H,
         (__nv_bfloat16*)xconv, dt);
   else if (dtype == HNB_F32)
-    conv_fwd_kernel<float, CONV_F_TS, CONV_F_NT><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt, ldz, dstride,
+    hnb::launch_pdl(conv_fwd_kernel<float, CONV_F_TS, CONV_F_NT>, dim3(grid), dim3(CONV_CT * CONV_SEG), 0, st, (const float*)zxbcdt, ldz, dstride,
         lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (float*)xconv, dt);
   else { set_error("conv_fwd: unsupported dtype"); return HNB_ERR_INVALID_ARG; }
   HNB_LAUNCH_CHECK("conv_fwd");
@@ -424,22 +426,22 @@ extern "C" int hnb_conv_bwd(const void* zxbcdt, const void* dxc, int dtype, long
   if (dtype == HNB_BF16 && variant == 2 && dbc_parts == 1) {
     // 2 channels per thread (64 registers, 4 resident blocks): measured SLOWER (130 vs 89 us), 4-byte accesses cost more than occupancy gains
     dim3 grid(cdiv(C / 2, CONV_CT), ysegs, ndir * B);
-    conv_bwd_kernel<__nv_bfloat16, V8<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 4, false><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+    hnb::launch_pdl(conv_bwd_kernel<__nv_bfloat16, V8<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 4, false>, dim3(grid), dim3(CONV_CT * CONV_SEG), 0, st, 
         (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
         conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
   } else if (dtype == HNB_BF16 && dbc_parts == 2) {
     dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
-    conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2, true><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+    hnb::launch_pdl(conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2, true>, dim3(grid), dim3(CONV_CT * CONV_SEG), 0, st, 
         (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
         conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
   } else if (dtype == HNB_BF16) {
     dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
-    conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2, false><<<grid, CONV_CT * CONV_SEG, 0, st>>>(
+    hnb::launch_pdl(conv_bwd_kernel<__nv_bfloat16, V16<__nv_bfloat16>, CONV_B_TS, CONV_B_NT, 2, false>, dim3(grid), dim3(CONV_CT * CONV_SEG), 0, st, 
         (const __nv_bfloat16*)zxbcdt, (const __nv_bfloat16*)dxc, ldz, dstride, (const __nv_bfloat16*)dBC, ddt, lengths,
         conv_w, conv_b, dt_bias, ndir, B, L, di, N, H, (__nv_bfloat16*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
   } else if (dtype == HNB_F32) {
     dim3 grid(cdiv(C / 4, CONV_CT), ysegs, ndir * B);
-    conv_bwd_kernel<float, V16<float>, CONV_B_TS, CONV_B_NT, 2, false><<<grid, CONV_CT * CONV_SEG, 0, st>>>((const float*)zxbcdt,
+    hnb::launch_pdl(conv_bwd_kernel<float, V16<float>, CONV_B_TS, CONV_B_NT, 2, false>, dim3(grid), dim3(CONV_CT * CONV_SEG), 0, st, (const float*)zxbcdt,
         (const float*)dxc, ldz, dstride, (const float*)dBC, ddt, lengths, conv_w, conv_b, dt_bias, ndir, B, L, di, N, H,
         (float*)dzxbcdt, dconv_w, dconv_b, ddt_bias, vec, dbc_parts, pstride);
   } else { set_error("conv_bwd: unsupported dtype"); return HNB_ERR_INVALID_ARG; }

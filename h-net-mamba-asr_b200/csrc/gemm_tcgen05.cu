@@ -228,6 +228,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ad
 template <int TA, int TB, int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  pdl_trigger();
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES, B_STAGE = Cfg::B_STAGE;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -256,6 +257,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (CL > 1) umma::cluster_sync_all();        // the peer's barriers are initialised before anything is multicast into them
   umma::tc_fence_after();
+  pdl_wait();                                             // everything above overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
@@ -383,6 +385,7 @@ constexpr int PAIR_SMEM = PAIR_RING + 256 + 1024;
 template <int TA, int TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + PAIR_STAGES * A_STAGE;
@@ -409,6 +412,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   umma::cluster_sync_all();
   umma::tc_fence_after();
+  pdl_wait();                                             // everything above overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
@@ -655,11 +659,13 @@ extern "C" int hnb_gemm_bf16_ex(const void* A, long long lda, int transA, const 
   const int grid = CL * (n_items < sms / CL ? n_items : sms / CL);
   cudaStream_t st = (cudaStream_t)stream;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // common.cuh: the prologue overlaps the previous kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = hnb::pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 2;
 #define LAUNCH(TA, TB, BN_, CL_)                                                                                     \
   do {                                                                                                               \
     HNB_CUDA_CALL(hnb_set_max_smem((const void*)gemm_bf16_kernel<TA, TB, BN_, CL_>, \

@@ -28,6 +28,7 @@ template <typename TQ, typename TP, int VN>
 __global__ void __launch_bounds__(ROUTER_WARPS * 32)
 router_fwd_kernel(const TQ* __restrict__ qk, long long ld, const uint8_t* __restrict__ mask, int B, int L,
                   int D, float eps, TP* __restrict__ p_out, TP* __restrict__ b_out, float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float sred[ROUTER_WARPS][3];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long n = (long long)B * L;
@@ -73,6 +74,7 @@ template <typename TP>
 __global__ void __launch_bounds__(ROUTER_WARPS * 32)
 masked_sums_kernel(const TP* __restrict__ p, const TP* __restrict__ b, const uint8_t* __restrict__ mask, long long n,
                    float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float red[32];
   const long long i = (long long)blockIdx.x * (ROUTER_WARPS * 32) + threadIdx.x;
   float sb = 0.f, sp = 0.f, sm = 0.f;
@@ -89,6 +91,7 @@ masked_sums_kernel(const TP* __restrict__ p, const TP* __restrict__ b, const uin
 
 // deterministic fixed-order reduction of the per-block partials + the scalar ratio loss
 __global__ void ratio_finalize_kernel(const float* __restrict__ partial, int nblk, float N, float* __restrict__ stats) {
+  pdl_enter();
   __shared__ double s[3][256];
   double a0 = 0, a1 = 0, a2 = 0;
   for (int i = threadIdx.x; i < nblk; i += 256) {
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(ROUTER_WARPS * 32)
 router_bwd_kernel(const TQ* __restrict__ qk, long long ld, const uint8_t* __restrict__ mask, int B, int L, int D,
                   float eps, const float* __restrict__ dp_ext, const float* __restrict__ dratio,
                   const float* __restrict__ stats, float N, TQ* __restrict__ dqk) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long n = (long long)B * L;
   const long long tok = (long long)blockIdx.x * ROUTER_WARPS + w;
@@ -186,6 +190,7 @@ template <typename TP>
 __global__ void __launch_bounds__(SCAN_THREADS)
 boundary_scan_kernel(const TP* __restrict__ bflag, long long n, int L, long long* __restrict__ memb,
                      int* __restrict__ counts, unsigned long long* tile_state, unsigned int* tile_counter) {
+  pdl_enter();
   __shared__ unsigned int s_tile;
   __shared__ SegPair s_warp[SCAN_THREADS / 32];
   __shared__ int s_prefix;
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 compact_rows_kernel(const TX* __restrict__ x, const TP* __restrict__ p, const TP* __restrict__ bflag,
                     const long long* __restrict__ memb, const int* __restrict__ counts, int B, int L, int D, int M,
                     TX* __restrict__ z, uint8_t* __restrict__ zmask, float* __restrict__ P, int* __restrict__ starts) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (tok >= (long long)B * L) return;
@@ -303,6 +309,7 @@ template <typename TX, typename TP, int VN>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 compact_rows_bwd_kernel(const TX* __restrict__ dz, const TP* __restrict__ bflag, const long long* __restrict__ memb,
                         int B, int L, int D, int M, TX* __restrict__ dx, int accumulate) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (tok >= (long long)B * L) return;
@@ -344,6 +351,7 @@ ema_kernel(const T* __restrict__ xin,      // fwd: x        bwd: dout
            const float* __restrict__ P, int M, int D, float pcl,
            T* __restrict__ yout,           // fwd: out      bwd: dx
            float* __restrict__ dP) {
+  pdl_enter();
   __shared__ float sA[EMA_SEGS][32];
   __shared__ float sS[EMA_SEGS][32][VN];
   const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
@@ -461,6 +469,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 upsample_fwd_kernel(const TZ* __restrict__ zbar, const long long* __restrict__ memb, const TP* __restrict__ p,
                     const TP* __restrict__ bflag, const TY* __restrict__ resid, int B, int L, int D, int M,
                     TY* __restrict__ y) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (tok >= (long long)B * L) return;
@@ -485,6 +494,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 upsample_bwd_kernel(const TY* __restrict__ dy, const TZ* __restrict__ zbar, const int* __restrict__ starts,
                     const int* __restrict__ counts, const TP* __restrict__ p, const TP* __restrict__ bflag,
                     int B, int L, int D, int M, TZ* __restrict__ dzbar, float* __restrict__ dp) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long slot = (long long)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (slot >= (long long)B * M) return;
@@ -551,7 +561,7 @@ extern "C" int hnb_router_fwd(const void* qk, int qk_dtype, long long ldqk, cons
   const int grid = cdiv(n, ROUTER_WARPS);
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = vec_ok(qk, ldqk, D, esize(qk_dtype), 4);
-#define RUN(TQ, TP, VN) router_fwd_kernel<TQ, TP, VN><<<grid, ROUTER_WARPS * 32, 0, st>>>( \
+#define RUN(TQ, TP, VN) hnb::launch_pdl(router_fwd_kernel<TQ, TP, VN>, dim3(grid), dim3(ROUTER_WARPS * 32), 0, st,  \
       (const TQ*)qk, ldqk, mask, B, L, D, eps, (TP*)p, (TP*)b, partial)
   HNB_DISPATCH_DTYPE(qk_dtype, TQ, HNB_DISPATCH_DTYPE(pb_dtype, TP, { if (v4) RUN(TQ, TP, 4); else RUN(TQ, TP, 1); }));
 #undef RUN
@@ -563,7 +573,7 @@ extern "C" int hnb_masked_sums(const void* p, const void* b, int pb_dtype, const
                                float* partial, void* stream) {
   HNB_CHECK_ARG(p && b && partial && n > 0, "masked_sums: bad arguments");
   const int grid = cdiv(n, ROUTER_WARPS * 32);
-  HNB_DISPATCH_DTYPE(pb_dtype, TP, (masked_sums_kernel<TP><<<grid, ROUTER_WARPS * 32, 0, (cudaStream_t)stream>>>(
+  HNB_DISPATCH_DTYPE(pb_dtype, TP, (hnb::launch_pdl(masked_sums_kernel<TP>, dim3(grid), dim3(ROUTER_WARPS * 32), 0, (cudaStream_t)stream, 
       (const TP*)p, (const TP*)b, mask, n, partial)));
   HNB_LAUNCH_CHECK("masked_sums");
   return HNB_OK;
@@ -571,7 +581,7 @@ extern "C" int hnb_masked_sums(const void* p, const void* b, int pb_dtype, const
 
 extern "C" int hnb_ratio_finalize(const float* partial, int nblk, float N, float* stats, void* stream) {
   HNB_CHECK_ARG(partial && stats && nblk > 0, "ratio_finalize: bad arguments");
-  ratio_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partial, nblk, N, stats);
+  hnb::launch_pdl(ratio_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, partial, nblk, N, stats);
   HNB_LAUNCH_CHECK("ratio_finalize");
   return HNB_OK;
 }
@@ -585,7 +595,7 @@ extern "C" int hnb_router_bwd(const void* qk, int qk_dtype, long long ldqk, cons
   const int grid = cdiv(n, ROUTER_WARPS);
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = vec_ok(qk, ldqk, D, esize(qk_dtype), 4) && vec_ok(dqk, ldqk, D, esize(qk_dtype), 4);
-#define RUN(TQ, VN) router_bwd_kernel<TQ, VN><<<grid, ROUTER_WARPS * 32, 0, st>>>( \
+#define RUN(TQ, VN) hnb::launch_pdl(router_bwd_kernel<TQ, VN>, dim3(grid), dim3(ROUTER_WARPS * 32), 0, st,  \
       (const TQ*)qk, ldqk, mask, B, L, D, eps, dp_ext, dratio, stats, N, (TQ*)dqk)
   HNB_DISPATCH_DTYPE(qk_dtype, TQ, { if (v4) RUN(TQ, 4); else RUN(TQ, 1); });
 #undef RUN
@@ -606,7 +616,7 @@ extern "C" int hnb_boundary_scan(const void* b, int pb_dtype, int B, int L, int6
   HNB_CUDA_CALL(cudaMemsetAsync(ws, 0, (size_t)hnb_boundary_scan_ws_bytes(n), st));
   unsigned long long* state = (unsigned long long*)ws + 1;
   unsigned int* counter = (unsigned int*)ws;
-  HNB_DISPATCH_DTYPE(pb_dtype, TP, (boundary_scan_kernel<TP><<<tiles, SCAN_THREADS, 0, st>>>(
+  HNB_DISPATCH_DTYPE(pb_dtype, TP, (hnb::launch_pdl(boundary_scan_kernel<TP>, dim3(tiles), dim3(SCAN_THREADS), 0, st, 
       (const TP*)b, n, L, (long long*)membership, counts, state, counter)));
   HNB_LAUNCH_CHECK("boundary_scan");
   return HNB_OK;
@@ -620,7 +630,7 @@ extern "C" int hnb_compact_rows(const void* x, int x_dtype, const void* p, const
   const int grid = cdiv((long long)B * L, ROW_WARPS);
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = vec_ok(x, D, D, esize(x_dtype), 4) && vec_ok(z, D, D, esize(x_dtype), 4);
-#define RUN(TX, TP, VN) compact_rows_kernel<TX, TP, VN><<<grid, ROW_WARPS * 32, 0, st>>>( \
+#define RUN(TX, TP, VN) hnb::launch_pdl(compact_rows_kernel<TX, TP, VN>, dim3(grid), dim3(ROW_WARPS * 32), 0, st,  \
       (const TX*)x, (const TP*)p, (const TP*)b, (const long long*)membership, counts, B, L, D, M, (TX*)z, z_mask, P, starts)
   HNB_DISPATCH_DTYPE(x_dtype, TX, HNB_DISPATCH_DTYPE(pb_dtype, TP, { if (v4) RUN(TX, TP, 4); else RUN(TX, TP, 1); }));
 #undef RUN
@@ -634,7 +644,7 @@ extern "C" int hnb_compact_rows_bwd(const void* dz, int dtype, const void* b, in
   const int grid = cdiv((long long)B * L, ROW_WARPS);
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = vec_ok(dz, D, D, esize(dtype), 4) && vec_ok(dx, D, D, esize(dtype), 4);
-#define RUN(TX, TP, VN) compact_rows_bwd_kernel<TX, TP, VN><<<grid, ROW_WARPS * 32, 0, st>>>( \
+#define RUN(TX, TP, VN) hnb::launch_pdl(compact_rows_bwd_kernel<TX, TP, VN>, dim3(grid), dim3(ROW_WARPS * 32), 0, st,  \
       (const TX*)dz, (const TP*)b, (const long long*)membership, B, L, D, M, (TX*)dx, accumulate)
   HNB_DISPATCH_DTYPE(dtype, TX, HNB_DISPATCH_DTYPE(pb_dtype, TP, { if (v4) RUN(TX, TP, 4); else RUN(TX, TP, 1); }));
 #undef RUN
@@ -648,7 +658,7 @@ extern "C" int hnb_ema_fwd(const void* x, int dtype, const float* P, int B, int 
   const int vn = vec_ok(x, D, D, esize(dtype), 2) && vec_ok(out, D, D, esize(dtype), 2) ? 2 : 1;
   dim3 grid(cdiv(D, 32 * vn), B);
   cudaStream_t st = (cudaStream_t)stream;
-#define RUN(T, VN) ema_kernel<T, false, VN><<<grid, EMA_SEGS * 32, 0, st>>>( \
+#define RUN(T, VN) hnb::launch_pdl(ema_kernel<T, false, VN>, dim3(grid), dim3(EMA_SEGS * 32), 0, st,  \
       (const T*)x, nullptr, nullptr, P, M, D, p_clamp, (T*)out, nullptr)
   HNB_DISPATCH_DTYPE(dtype, T, { if (vn == 2) RUN(T, 2); else RUN(T, 1); });
 #undef RUN
@@ -663,7 +673,7 @@ extern "C" int hnb_ema_bwd(const void* dout, const void* x, const void* out, int
                  vec_ok(dout, D, D, esize(dtype), 2) && vec_ok(dx, D, D, esize(dtype), 2) ? 2 : 1;
   dim3 grid(cdiv(D, 32 * vn), B);
   cudaStream_t st = (cudaStream_t)stream;
-#define RUN(T, VN) ema_kernel<T, true, VN><<<grid, EMA_SEGS * 32, 0, st>>>( \
+#define RUN(T, VN) hnb::launch_pdl(ema_kernel<T, true, VN>, dim3(grid), dim3(EMA_SEGS * 32), 0, st,  \
       (const T*)dout, (const T*)x, (const T*)out, P, M, D, p_clamp, (T*)dx, dP)
   HNB_DISPATCH_DTYPE(dtype, T, { if (vn == 2) RUN(T, 2); else RUN(T, 1); });
 #undef RUN
@@ -679,7 +689,7 @@ extern "C" int hnb_upsample_fwd(const void* zbar, int z_dtype, const int64_t* me
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = vec_ok(zbar, D, D, esize(z_dtype), 4) && vec_ok(y, D, D, esize(y_dtype), 4) &&
                   (!resid || vec_ok(resid, D, D, esize(y_dtype), 4));
-#define RUN(TZ, TY, TP, VN) upsample_fwd_kernel<TZ, TY, TP, VN><<<grid, ROW_WARPS * 32, 0, st>>>( \
+#define RUN(TZ, TY, TP, VN) hnb::launch_pdl(upsample_fwd_kernel<TZ, TY, TP, VN>, dim3(grid), dim3(ROW_WARPS * 32), 0, st,  \
       (const TZ*)zbar, (const long long*)membership, (const TP*)p, (const TP*)b, (const TY*)resid, B, L, D, M, (TY*)y)
   HNB_DISPATCH_DTYPE(z_dtype, TZ, HNB_DISPATCH_DTYPE(y_dtype, TY, HNB_DISPATCH_DTYPE(pb_dtype, TP, {
     if (v4) RUN(TZ, TY, TP, 4); else RUN(TZ, TY, TP, 1); })));
@@ -701,7 +711,7 @@ extern "C" int hnb_upsample_bwd(const void* dy, int y_dtype, const void* zbar, i
   const int vn = v4 ? 4 : 1;
   const int nv = cdiv(D, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "upsample_bwd: D=%d too large for the register tile", D);
-#define RUN2(TZ, TY, TP, VN, NV) upsample_bwd_kernel<TZ, TY, TP, VN, NV><<<grid, ROW_WARPS * 32, 0, st>>>( \
+#define RUN2(TZ, TY, TP, VN, NV) hnb::launch_pdl(upsample_bwd_kernel<TZ, TY, TP, VN, NV>, dim3(grid), dim3(ROW_WARPS * 32), 0, st,  \
       (const TY*)dy, (const TZ*)zbar, starts, counts, (const TP*)p, (const TP*)b, B, L, D, M, (TZ*)dzbar, dp)
 #define RUN(TZ, TY, TP, VN)                                                 \
   do {                                                                      \

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -16,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = !(getenv("HNB_PDL") && getenv("HNB_PDL")[0] == '0');
+  return on;
+}
 }  // namespace hnb
 
 extern "C" int hnb_version(void) { return 100; }

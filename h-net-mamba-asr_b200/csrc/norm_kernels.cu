@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(NORM_WARPS * 32)
 layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      long long rows, int d, float eps, TY* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(NORM_WARPS * 32)
 layernorm_fwd_reg_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                          long long rows, int d, float eps, TY* __restrict__ y, float* __restrict__ mean_out,
                          float* __restrict__ rstd_out) {
+  pdl_enter();
   constexpr int VN = 4, R = 2;
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5)) * R;
@@ -122,6 +124,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
                      const float* __restrict__ mean, const float* __restrict__ rstd, const TDX* __restrict__ dres,
                      long long rows, int d, TDX* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta) {
+  pdl_enter();
   extern __shared__ float sm[];                                     // [2][d]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float ag[NV][VN], ab[NV][VN], gm[NV][VN];
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(NORM_WARPS * 32)
 gated_norm_fwd_kernel(const T* __restrict__ y, const T* __restrict__ zx, long long ldz, long long dstride, const int* __restrict__ lengths,
                       const float* __restrict__ w, int ndir, int B, int L, int di, float eps, T* __restrict__ out,
                       float* __restrict__ rstd_out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long T_ = (long long)B * L;
   const long long idx = (long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
@@ -287,6 +291,7 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
                       long long dstride, const int* __restrict__ lengths, const float* __restrict__ w,
                       const float* __restrict__ rstd, int ndir, int B, int L, int di, T* __restrict__ dy,
                       T* __restrict__ dzx, float* __restrict__ dw) {
+  pdl_enter();
   extern __shared__ float sm[];                                     // [di]
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const long long T_ = (long long)B * L;
@@ -380,6 +385,7 @@ pack_mixer_kernel(const PackSrc src, int dir0, int ndir, int d, int di, const Fa
                   int N, int H, int dstride, TW* __restrict__ Win, TW* __restrict__ Wout, float* __restrict__ conv_w_o,
                   float* __restrict__ conv_b_o, float* __restrict__ dt_bias_o, float* __restrict__ A_log_o,
                   float* __restrict__ D_o, float* __restrict__ norm_w_o, long long layer_stride_bytes) {
+  pdl_enter();
   const int dir = dir0 + blockIdx.y;                                // one launch packs gridDim.y directions of gridDim.z layers
   const int ly = blockIdx.z;
   {
@@ -465,12 +471,12 @@ extern "C" int hnb_layernorm_fwd(const void* x, int x_dtype, const float* gamma,
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = cdiv(rows, NORM_WARPS);
   const bool v4 = d % 4 == 0 && al(x, 4 * esz(x_dtype)) && al(y, 4 * esz(y_dtype)) && al(gamma, 16) && al(beta, 16);
-#define RUN(TX, TY, VN) layernorm_fwd_kernel<TX, TY, VN><<<grid, NORM_WARPS * 32, 0, st>>>( \
+#define RUN(TX, TY, VN) hnb::launch_pdl(layernorm_fwd_kernel<TX, TY, VN>, dim3(grid), dim3(NORM_WARPS * 32), 0, st,  \
       (const TX*)x, gamma, beta, rows, d, eps, (TY*)y, mean, rstd)
   const int nv = cdiv(d, 128);
   if (v4 && nv <= 6) {
     const int grid2 = cdiv(rows, NORM_WARPS * 2);
-#define RUNR(TX, TY, NV) layernorm_fwd_reg_kernel<TX, TY, NV><<<grid2, NORM_WARPS * 32, 0, st>>>( \
+#define RUNR(TX, TY, NV) hnb::launch_pdl(layernorm_fwd_reg_kernel<TX, TY, NV>, dim3(grid2), dim3(NORM_WARPS * 32), 0, st,  \
       (const TX*)x, gamma, beta, rows, d, eps, (TY*)y, mean, rstd)
     HNB_DISPATCH_DTYPE(x_dtype, TX, HNB_DISPATCH_DTYPE(y_dtype, TY, {
       if (nv <= 1) RUNR(TX, TY, 1); else if (nv <= 2) RUNR(TX, TY, 2); else if (nv <= 3) RUNR(TX, TY, 3);
@@ -518,8 +524,8 @@ extern "C" int hnb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, in
   const int nv = cdiv(d, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "layernorm_bwd: d=%d too large", d);
   const size_t smem = 2 * (size_t)d * sizeof(float);
-#define RUN2(A, Bx, C, VN, NV) layernorm_bwd_kernel<A, Bx, C, VN, NV><<<norm_grid(layernorm_bwd_kernel<A, Bx, C, VN, NV>, rows, smem), \
-      NORM_WARPS * 32, smem, st>>>((const A*)dy, (const Bx*)x, gamma, mean, rstd, (const C*)dres, rows, d, (C*)dx, dgamma, dbeta)
+#define RUN2(A, Bx, C, VN, NV) hnb::launch_pdl(layernorm_bwd_kernel<A, Bx, C, VN, NV>, dim3(norm_grid(layernorm_bwd_kernel<A, Bx, C, VN, NV>, rows, smem)), dim3(\
+      NORM_WARPS * 32), smem, st, (const A*)dy, (const Bx*)x, gamma, mean, rstd, (const C*)dres, rows, d, (C*)dx, dgamma, dbeta)
 #define RUN(A, Bx, C, VN)                                                                  \
   do {                                                                                     \
     if (nv <= 2) RUN2(A, Bx, C, VN, 2); else if (nv <= 3) RUN2(A, Bx, C, VN, 3);           \
@@ -550,7 +556,7 @@ extern "C" int hnb_gated_norm_fwd(const void* y, const void* zxbcdt, int dtype, 
   const int vn = v8 ? 8 : (v4 ? 4 : 1);
   const int nv = cdiv(di, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "gated_norm_fwd: d_inner=%d too large", di);
-#define RUN2(T, VN, NV) gated_norm_fwd_kernel<T, VN, NV><<<grid, NORM_WARPS * 32, 0, st>>>( \
+#define RUN2(T, VN, NV) hnb::launch_pdl(gated_norm_fwd_kernel<T, VN, NV>, dim3(grid), dim3(NORM_WARPS * 32), 0, st,  \
       (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, ndir, B, L, di, eps, (T*)out, rstd)
 #define RUN(T, VN)                                                             \
   do {                                                                         \
@@ -582,8 +588,8 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
   const int nv = cdiv(di, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "gated_norm_bwd: d_inner=%d too large", di);
   const size_t smem = (size_t)di * sizeof(float);
-#define RUN2(T, VN, NV) gated_norm_bwd_kernel<T, VN, NV><<<dim3(std::max(1, norm_grid(gated_norm_bwd_kernel<T, VN, NV>, rows * ndir, smem) / ndir), ndir), \
-      NORM_WARPS * 32, smem, st>>>((const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w)
+#define RUN2(T, VN, NV) hnb::launch_pdl(gated_norm_bwd_kernel<T, VN, NV>, dim3(dim3(std::max(1, norm_grid(gated_norm_bwd_kernel<T, VN, NV>, rows * ndir, smem) / ndir), ndir)), dim3(\
+      NORM_WARPS * 32), smem, st, (const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w)
 #define RUN(T, VN)                                                             \
   do {                                                                         \
     if (nv <= 1) RUN2(T, VN, 1); else if (nv <= 2) RUN2(T, VN, 2);             \
@@ -616,7 +622,7 @@ static int pack_launch(const PackSrc& src, int ndirs, int dir0, int ndir, int d,
   int gx = cdiv(total, 256 * 4);
   const int cap = 148 * 8 / (ndirs * (nlayers < 4 ? nlayers : 4));
   if (gx > cap) gx = cap > 0 ? cap : 1;
-  HNB_DISPATCH_DTYPE(w_dtype, TW, (pack_mixer_kernel<TW><<<dim3(gx, ndirs, nlayers), 256, 0, st>>>(src, dir0, ndir, d, di,
+  HNB_DISPATCH_DTYPE(w_dtype, TW, (hnb::launch_pdl(pack_mixer_kernel<TW>, dim3(dim3(gx, ndirs, nlayers)), dim3(256), 0, st, src, dir0, ndir, d, di,
       FastDiv(d / 4), FastDiv(di / 4), N, H,
       dstride, (TW*)Win, (TW*)Wout, conv_w_o, conv_b_o, dt_bias_o, A_log_o, D_o, norm_w_o, layer_stride_bytes)));
   HNB_LAUNCH_CHECK("pack_mixer_params");

@@ -75,6 +75,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int NH>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 ssd_states_tc_kernel(const __grid_constant__ CUtensorMap tmX, const SplitParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   uint8_t* sB = base + ST_OFF_B; uint8_t* sX = base + ST_OFF_X;
@@ -97,6 +98,7 @@ ssd_states_tc_kernel(const __grid_constant__ CUtensorMap tmX, const SplitParams 
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  pdl_wait();                                             // everything above overlaps the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
   const int H = p.H, di = p.di, nc = p.nc, ns = nc - 1;
@@ -227,6 +229,7 @@ static_assert(TAB_BYTES % 16 == 0 && SC_OFF_BAR % 8 == 0, "SSD scan kernel: alig
 
 __global__ void __launch_bounds__(SC_THREADS, 1)
 ssd_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmS, const SplitParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   uint8_t* sC = base + SC_OFF_C; uint8_t* sB = base + SC_OFF_B; uint8_t* sX = base + SC_OFF_X; uint8_t* sS = base + SC_OFF_S;
@@ -252,6 +255,7 @@ ssd_scan_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  pdl_wait();                                             // everything above overlaps the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
   constexpr uint32_t TM_G = 0, TM_M = 128, TM_YD = 256, TM_YO = 384;          // M, Yd, Yo: two buffers of 64 columns
@@ -517,7 +521,7 @@ int hnb_ssd_fwd_split_tc(const CUtensorMap* tmX, const void* xconv, const float*
 #define HNB_ST_LAUNCH(NH_)                                                                               \
     do {                                                                                                 \
       HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_states_tc_kernel<NH_>, st_smem(NH_)));            \
-      ssd_states_tc_kernel<NH_><<<grid, ST_THREADS, st_smem(NH_), st>>>(*tmX, p);                         \
+      hnb::launch_pdl(ssd_states_tc_kernel<NH_>, dim3(grid), dim3(ST_THREADS), st_smem(NH_), st, *tmX, p);                         \
     } while (0)
     if (nh == 4) HNB_ST_LAUNCH(4); else if (nh == 3) HNB_ST_LAUNCH(3); else if (nh == 2) HNB_ST_LAUNCH(2); else HNB_ST_LAUNCH(1);
 #undef HNB_ST_LAUNCH
@@ -529,7 +533,7 @@ int hnb_ssd_fwd_split_tc(const CUtensorMap* tmX, const void* xconv, const float*
     p.nh = nh; p.n_items = p.ndirB * nc * (H / nh);
     p.dHG = FastDiv(H / nh); p.dnh = FastDiv(nh); p.dper = FastDiv(1);
     HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_scan_tc_kernel, SC_SMEM));
-    ssd_scan_tc_kernel<<<p.n_items < sms ? p.n_items : sms, SC_THREADS, SC_SMEM, st>>>(*tmX, tmS, p);
+    hnb::launch_pdl(ssd_scan_tc_kernel, dim3(p.n_items < sms ? p.n_items : sms), dim3(SC_THREADS), SC_SMEM, st, *tmX, tmS, p);
     HNB_LAUNCH_CHECK("ssd_scan_tc");
   }
   return HNB_OK;

@@ -43,6 +43,7 @@ namespace {
 __global__ void __launch_bounds__(TQ)
 ssd_tables_kernel(const float* __restrict__ dt, const float* __restrict__ A_log, float* __restrict__ tables, int B, int L,
                   int H, int nc, int* __restrict__ work_counter) {
+  pdl_enter();
   __shared__ float tab[TAB_FLOATS];
   if (blockIdx.x == 0 && threadIdx.x == 0) *work_counter = 0;          // the forward kernel's dynamic work queue
   const int item = blockIdx.x;                                        // ((db * H) + h) * nc + c
@@ -321,6 +322,7 @@ static_assert(2 * (F2_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
 
 __global__ void __launch_bounds__(F2_THREADS, 2)
 ssd_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   uint8_t* sC = base + F2_OFF_C; uint8_t* sB = base + F2_OFF_B; uint8_t* sX = base + F2_OFF_X; uint8_t* sS = base + F2_OFF_S;
@@ -346,6 +348,7 @@ ssd_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  pdl_wait();                                             // everything above overlaps the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
   constexpr uint32_t TM_G = 0, TM_YO = 0, TM_DS = 64, TM_M = 128, TM_YD = 192;
@@ -586,8 +589,20 @@ struct BwdParams {
   __device__ __forceinline__ void chunk_of(int base, int& db, int& c) const {
     if (base < n_full) dnfc.divmod(base, db, c); else { db = base - n_full; c = nc - 1; }
   }
+  // Fused kernel, span schedule: the head-steps of all items, in the order above, form ONE sequence g = base * H + h; CTA k
+  // works the contiguous piece [cuts.g[k], cuts.g[k + 1]) of it.  The host places the cuts at equal cost and moves a cut
+  // to the item's end where an item would be cut twice, so every item is cut at most once.  dB | dC of a cut item (a sum
+  // over its heads) is finished by the CTA holding the item's FIRST heads: the CTA holding the last heads meets the item
+  // as its first piece, leaves its fp32 partial sum in fix[k] and raises fix_flags[k]; its left neighbour reaches the
+  // item as its LAST piece, long after, and adds the partial sum before it rounds and stores (stream-K style fix-up; all
+  // CTAs are resident: one per SM).  fix_flags are cleared by the state-gradient kernel that runs in front.
+  float* fix;                    // [G][2][8][4][128] float4
+  int* fix_flags;                // [SPAN_MAX_CTAS + 1]
   long long* dbg;                // optional [8] phase-cycle accumulators of CTA 0 (HNB_SSD_DEBUG=1)
 };
+
+constexpr int SPAN_MAX_CTAS = 160;
+struct SpanCuts { int g[SPAN_MAX_CTAS + 1]; };
 
 // ---- 1. dstate (256 threads, 2 CTAs per SM) -----------------------------------------------------------
 constexpr int D1_THREADS = 256;
@@ -598,6 +613,7 @@ constexpr int D1_SMEM = D1_OFF_BAR + 64 + 1024;
 __global__ void __launch_bounds__(D1_THREADS, 2)
 ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                          const BwdParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   uint8_t* sC = base + D1_OFF_C; uint8_t* sdY = base + D1_OFF_DY; uint8_t* sdYs = base + D1_OFF_DYS;
@@ -614,9 +630,11 @@ ssd_bwd_dstate_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   }
   if (warp == 0) umma::tmem_alloc(tmem_slot, 64);
   umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
+  pdl_wait();                                             // everything above overlaps the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
   const int H = p.H, L = p.L, di = p.di, nc = p.nc, n_items = p.ndirB * H;
+  if (blockIdx.x == 0 && tid <= SPAN_MAX_CTAS && p.fix_flags) p.fix_flags[tid] = 0;   // the fused kernel's fix-up counters
   constexpr uint32_t idesc = umma::make_idesc_bf16(128, 64, 1, 1);
   auto issue_load = [&](int item, int c, int buf) {
     int db, h; p.dH.divmod(item, db, h);
@@ -1257,7 +1275,8 @@ template <bool DBG>
 __global__ void __launch_bounds__(DF_THREADS, 1)
 ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                         const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG,
-                        const BwdParams p) {
+                        const BwdParams p, const SpanCuts cuts) {
+  pdl_trigger();
   constexpr int NT = BWD_THREADS, NCG = NT / 128;
   static_assert(NCG == 4, "the balanced score-tile split assumes 16 compute warps");
   constexpr uint32_t TM_DC = 0, TM_DB = 128, TM_G = 256, TM_R = 384, TM_DU1 = 256, TM_DU2 = 320, TM_YO = 384,
@@ -1296,9 +1315,21 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   for (int i = tid; i < 4 * HALF / 16; i += DF_THREADS) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);   // sK | sW: finite padding rows
   umma::fence_async_smem();
   umma::tc_fence_before(); __syncthreads(); umma::tc_fence_after();
+  pdl_wait();                                             // everything above overlaps the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(lq * 32) << 16);
-  const int H = p.H, L = p.L, di = p.di, nc = p.nc, HG = p.HG, Hh = H / HG, n_items = p.ndirB * nc * HG;
+  const int H = p.H, L = p.L, di = p.di, nc = p.nc;
+  // this CTA's work: piece j = heads [hb, he) of item `bs`
+  const long long t_enter = HNB_CLK();
+  const int g0 = cuts.g[blockIdx.x], g1 = cuts.g[blockIdx.x + 1];
+  const int b0 = p.dH.div(g0);
+  auto seg_at = [&](int j, int& bs, int& hb, int& he) -> bool {
+    const int g = j == 0 ? g0 : (b0 + j) * H;
+    if (g >= g1) return false;
+    bs = b0 + j; hb = g - bs * H;
+    he = min(g1 - bs * H, H);
+    return true;
+  };
 
   const bool isA = tid == 8 * 32;                                      // TMA, G | R, du1 | du2 | Yo
   const bool isB = tid == 4 * 32;                                      // dC | dB accumulation
@@ -1307,48 +1338,51 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   constexpr uint32_t i_mm128 = umma::make_idesc_bf16(128, 128, 1, 1);
   constexpr uint32_t i_km64 = umma::make_idesc_bf16(128, 64, 0, 1);
   constexpr uint32_t i_mm64 = umma::make_idesc_bf16(128, 64, 1, 1);
-  auto load_cb = [&](int item) {
-    int db, c; p.chunk_of(p.dHG.div(item), db, c);
+  auto load_cb = [&](int bs) {
+    int db, c; p.chunk_of(bs, db, c);
     umma::mbar_expect_tx(bar_cb, 4 * HALF);
     umma::tma_load_3d(sC, &tmX, bar_cb, di + TN, c * TQ, db);
     umma::tma_load_3d(sC + HALF, &tmX, bar_cb, di + TN + 64, c * TQ, db);
     umma::tma_load_3d(sB, &tmX, bar_cb, di, c * TQ, db);
     umma::tma_load_3d(sB + HALF, &tmX, bar_cb, di + 64, c * TQ, db);
   };
-  auto load_x = [&](int item, int hh) {
-    int bs, hg, db, c; p.dHG.divmod(item, bs, hg); p.chunk_of(bs, db, c);
+  auto load_x = [&](int bs, int h) {
+    int db, c; p.chunk_of(bs, db, c);
     umma::mbar_expect_tx(bar_x, HALF);
-    umma::tma_load_3d(sX, &tmX, bar_x, (hg * Hh + hh) * TP, c * TQ, db);
+    umma::tma_load_3d(sX, &tmX, bar_x, h * TP, c * TQ, db);
   };
-  auto load_dy = [&](int item, int hh, int buf) {
-    int bs, hg, db, c; p.dHG.divmod(item, bs, hg); p.chunk_of(bs, db, c);
-    const int h = hg * Hh + hh;
+  auto load_dy = [&](int bs, int h, int buf) {
+    int db, c; p.chunk_of(bs, db, c);
     const int srow = ((db * H + h) * nc) + c;
     umma::mbar_expect_tx(bar_dy, HALF + TAB_BYTES);
     umma::bulk_load(tabs + buf * TAB_FLOATS, p.tables + (long long)srow * TAB_FLOATS, TAB_BYTES, bar_dy);
     umma::tma_load_3d(sdY, &tmDY, bar_dy, h * TP, c * TQ, db);
   };
-  auto load_sg = [&](int item, int hh) {
-    int bs, hg, db, c; p.dHG.divmod(item, bs, hg); p.chunk_of(bs, db, c);
-    const int srow = (((db * H + hg * Hh + hh) * nc) + c) * TN;
+  auto load_sg = [&](int bs, int h) {
+    int db, c; p.chunk_of(bs, db, c);
+    const int srow = (((db * H + h) * nc) + c) * TN;
     umma::mbar_expect_tx(bar_sg, 2 * HALF);
     umma::tma_load_2d(sS, &tmS, bar_sg, 0, srow);
     umma::tma_load_2d(sG, &tmG, bar_sg, 0, srow);
   };
-  if (isA && blockIdx.x < n_items) { load_cb(blockIdx.x); load_x(blockIdx.x, 0); load_dy(blockIdx.x, 0, 0); load_sg(blockIdx.x, 0); }
   {
-    uint32_t iseq = 0, seq = 0;                                        // item / head-step sequence numbers of this CTA
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iseq) {
-      int bs, hg, db, c; p.dHG.divmod(it, bs, hg); p.chunk_of(bs, db, c);
+    int bs, hb, he;
+    if (isA && seg_at(0, bs, hb, he)) { load_cb(bs); load_x(bs, hb); load_dy(bs, hb, 0); load_sg(bs, hb); }
+  }
+  {
+    uint32_t iseq = 0, seq = 0;                                        // segment / head-step sequence numbers of this CTA
+    int bs, hb, he;
+    for (int sj = 0; seg_at(sj, bs, hb, he); ++sj, ++iseq) {
+      int db, c; p.chunk_of(bs, db, c);
       const int dir = p.dB.div(db);
       const int q0 = c * TQ, qv = min(TQ, L - q0);
       const int nblk = (qv + 31) >> 5, nkb = (qv + 15) >> 4;           // row blocks / k-steps that hold valid frames
       const long long row0 = (long long)db * L + q0;
-      for (int hh = 0; hh < Hh; ++hh, ++seq) {
-        const int h = hg * Hh + hh;
+      for (int h = hb; h < he; ++h, ++seq) {
         const uint32_t par = seq & 1;
-        int nit = it, nh = hh + 1;                                     // the head-step after this one
-        if (nh == Hh) { nit = it + gridDim.x; nh = 0; }
+        int nbs = bs, nh = h + 1;                                      // the head-step after this one
+        bool has_next = true;
+        if (nh == he) { int e2; has_next = seg_at(sj + 1, nbs, nh, e2); }
         const float* tab = tabs + (seq & 1) * TAB_FLOATS;
         const float* s_dt = tab + TQ; const float* s_w = tab + 2 * TQ; const float* s_ecs = tab + 3 * TQ;
         const float* s_eq = tab + 4 * TQ;
@@ -1364,10 +1398,10 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         long long* dbg = p.dbg + (tid == 0 ? 0 : 16);
         const long long tk0 = HNB_CLK();
         if (isA) {
-          if (hh == 0) {
+          if (h == hb) {
             if (seq > 0) {                                             // C, B, S, Gst are free once the last accumulation retired
               umma::mbar_wait(bar_acc, par ^ 1);
-              load_cb(it); load_sg(it, 0);
+              load_cb(bs); load_sg(bs, hb);
             }
             umma::mbar_wait(bar_cb, iseq & 1);
           }
@@ -1387,9 +1421,9 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             umma::mma_bf16_ss(tmem + TM_R, umma::make_smem_desc(umma::smem_u32(sdY) + kb * 32, 16, 1024),
                               umma::make_smem_desc(umma::smem_u32(sX) + kb * 32, 16, 1024), i_kk128, kb > 0);
           umma::mma_commit(bar_gr);
-          if (hh > 0) {                                                // same item: S, Gst of this head once the last accumulation retired
+          if (h > hb) {                                                // same item: S, Gst of this head once the last accumulation retired
             umma::mbar_wait(bar_acc, par ^ 1);
-            load_sg(it, hh);
+            load_sg(bs, h);
           }
         }
         umma::mbar_wait(bar_x, par); umma::mbar_wait(bar_dy, par);     // X, dY and the tables are visible to this thread
@@ -1535,20 +1569,20 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         umma::tc_fence_before();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(bar_ldb);                     // the accumulation (and the next G, R) may go on the pipe
-        if (isA && nit < n_items) {                                    // X, dY tiles are free: du1 retired, every thread holds its rows
+        if (isA && has_next) {                                         // X, dY tiles are free: du1 retired, every thread holds its rows
           umma::mbar_wait(bar_ldb, par);
-          load_x(nit, nh); load_dy(nit, nh, (seq & 1) ^ 1);
+          load_x(nbs, nh); load_dy(nbs, nh, (seq & 1) ^ 1);
         }
         if (isB) {                                                     // ---- MMA group 2b: accumulate dC, dB over the item's heads
           umma::mbar_wait(bar_ldb, par);
-          if (hh == 0 && iseq > 0) umma::mbar_wait(bar_out, (iseq - 1) & 1);   // the last item's dB | dC have left TMEM
+          if (h == hb && iseq > 0) umma::mbar_wait(bar_out, (iseq - 1) & 1);   // the last item's dB | dC have left TMEM
           umma::tc_fence_after();
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb) {                             // dC += W B        (k = time q: valid frames only)
             const uint32_t o = (kb >> 2) * HALF + (kb & 3) * 32;
             if (kb < nkb)
               umma::mma_bf16_ss(tmem + TM_DC, umma::make_smem_desc(umma::smem_u32(sW) + o, 16, 1024),
-                                umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024), i_km128, (hh > 0 || kb > 0));
+                                umma::make_smem_desc(umma::smem_u32(sB) + kb * 2048, HALF, 1024), i_km128, (h > hb || kb > 0));
           }
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb)                               // dC += (e^{cs} dY) S_in^T
@@ -1558,7 +1592,7 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           for (int kb = 0; kb < 8; ++kb)                               // dB += W^T C      (k = time t: valid frames only)
             if (kb < nkb)
               umma::mma_bf16_ss(tmem + TM_DB, umma::make_smem_desc(umma::smem_u32(sW) + kb * 2048, HALF, 1024),
-                                umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024), i_mm128, (hh > 0 || kb > 0));
+                                umma::make_smem_desc(umma::smem_u32(sC) + kb * 2048, HALF, 1024), i_mm128, (h > hb || kb > 0));
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb)                               // dB += (w X) Gst^T
             umma::mma_bf16_ts(tmem + TM_DB, tmem + TM_XW + 8 * kb,
@@ -1604,6 +1638,7 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           const long long tk7 = HNB_CLK();
           dbg[0] += tk1 - tk0; dbg[1] += tk2 - tk1; dbg[2] += tk3 - tk2; dbg[3] += tk4 - tk3; dbg[4] += tk5 - tk4;
           dbg[5] += tk6 - tk5; dbg[6] += tk7 - tk6; dbg[9] += 1;
+          if (h == hb) { dbg[10] += tk7 - tk0; dbg[11] += 1; }         // first head-step of a piece
         }
         // ---- reverse inclusive cumsum of d cs over the chunk -> ddt, dA_log: ONE warp (lane l owns frames 4l..4l+3);
         //      every other warp goes on to the next head-step
@@ -1650,25 +1685,62 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (lane == 0) { atomicAdd(p.dA_log + dir * H + h, accA * A); atomicAdd(p.dD + dir * H + h, dd); }
         }
       }
-      // ---- write dB | dC of this item (bf16, like the rest of the activation gradients)
+      // ---- dB | dC of this piece: the item's last heads (hb > 0) go to the fix-up buffer, its first heads (or all of them)
+      //      are rounded and stored (bf16, like the rest of the activation gradients) after the neighbour's part was added
+      const long long te0 = HNB_CLK();
       umma::mbar_wait(bar_acc, (seq - 1) & 1);
       umma::tc_fence_after();
+      const long long te1 = HNB_CLK();
       {
         const int t = row;
+        const bool to_fix = hb > 0, from_fix = he < H;
+        // fix[k]: [dB | dC][8 float4 of a thread's 32 columns][column group][row] -- a warp's access is 512 contiguous bytes
+        float4* fx = reinterpret_cast<float4*>(p.fix + (size_t)(blockIdx.x + (from_fix ? 1 : 0)) * (2 * NCG * TQ * 32)) + cg * TQ + t;
+        if (from_fix) {                                                 // (raised ~a whole piece ago: this does not spin in practice)
+          const int* fl = p.fix_flags + blockIdx.x + 1;
+          int got;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(fl) : "memory");
+            if (got < NT / 32) __nanosleep(256);
+          } while (got < NT / 32);
+        }
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {                          // 0: dB, 1: dC
+        for (int bc = 0; bc < 2; ++bc) {                                // 0: dB, 1: dC
           float v[32];
-          umma::tmem_ld32(t_lane + (part == 0 ? TM_DB : TM_DC) + 32u * cg, v);
+          umma::tmem_ld32(t_lane + (bc == 0 ? TM_DB : TM_DC) + 32u * cg, v);
           umma::tmem_ld_wait();
-          if (t < qv) {                                                 // 64 contiguous bytes per thread: two full 32-byte sectors
-            __nv_bfloat16* og = p.dBC + hg * p.dbc_part_stride + (row0 + t) * (2 * TN) + part * TN + 32 * cg;
+          if (DBG && p.dbg && blockIdx.x == 0 && tid == 0 && iseq < 7) p.dbg[400 + 4 * iseq + bc] = HNB_CLK() - te1;
+          float4* f4 = fx + bc * (8 * NCG * TQ);
+          if (to_fix) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint4 lo = pack8(v + 16 * k), hi = pack8(v + 16 * k + 8);
-              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(og + 16 * k), "r"(lo.x), "r"(lo.y),
-                           "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+            for (int k = 0; k < 8; ++k) __stcg(f4 + k * (NCG * TQ), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+          } else {
+            if (from_fix) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 a = __ldcg(f4 + k * (NCG * TQ));
+                v[4 * k] += a.x; v[4 * k + 1] += a.y; v[4 * k + 2] += a.z; v[4 * k + 3] += a.w;
+              }
+            }
+            if (t < qv) {                                               // 64 contiguous bytes per thread: two full 32-byte sectors
+              __nv_bfloat16* og = p.dBC + (row0 + t) * (2 * TN) + bc * TN + 32 * cg;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const uint4 lo = pack8(v + 16 * k), hi = pack8(v + 16 * k + 8);
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(og + 16 * k), "r"(lo.x), "r"(lo.y),
+                             "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+              }
             }
           }
+        }
+        if (to_fix) {                                                   // every warp's share is visible before its count
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(p.fix_flags + blockIdx.x, 1);
+        }
+        if (DBG && p.dbg && blockIdx.x == 0 && tid == 0) {
+          p.dbg[12] += te1 - te0; p.dbg[13] += HNB_CLK() - te1; p.dbg[14] += 1;
+          if (iseq < 7) { p.dbg[400 + 4 * iseq + 2] = HNB_CLK() - te1; p.dbg[400 + 4 * iseq + 3] = (to_fix ? 1 : 0) + (from_fix ? 2 : 0) + 4; }
         }
       }
       umma::tc_fence_before();
@@ -1677,6 +1749,9 @@ ssd_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
   }
   umma::tc_fence_before(); __syncthreads();
+  if (DBG && p.dbg && tid == 0) {                                      // per-CTA: cycles from entry to here, head-steps done
+    p.dbg[32 + 2 * blockIdx.x] = HNB_CLK() - t_enter; p.dbg[33 + 2 * blockIdx.x] = g1 - g0;
+  }
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
@@ -1701,8 +1776,12 @@ static size_t tc_tables_offset(int ndir, int B, int L, int H) {
   const size_t st = (size_t)ndir * B * H * cdiv(L, TQ) * TN * TP * sizeof(__nv_bfloat16);
   return (st + 127) / 128 * 128;
 }
+// the backward's second workspace holds the state gradients where the forward's holds the states, and behind them the
+// fix-up buffer of the fused kernel's span schedule instead of the tables
+constexpr size_t FIX_BYTES = (size_t)SPAN_MAX_CTAS * 2 * 4 * TQ * 32 * sizeof(float) + (SPAN_MAX_CTAS + 1 + 31) / 32 * 32 * sizeof(int);
 long long hnb_ssd_tc_ws_bytes(int ndir, int B, int L, int H) {
-  return (long long)(tc_tables_offset(ndir, B, L, H) + (size_t)ndir * B * H * cdiv(L, TQ) * TAB_BYTES + 128);
+  const size_t tabs = (size_t)ndir * B * H * cdiv(L, TQ) * TAB_BYTES + 128;
+  return (long long)(tc_tables_offset(ndir, B, L, H) + (tabs > FIX_BYTES ? tabs : FIX_BYTES));
 }
 
 int hnb_ssd_fwd_split_tc(const CUtensorMap* tmX, const void* xconv, const float* Dskip, const float* tables, int ndir, int B,
@@ -1728,7 +1807,7 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
   p.tables = tables;
   const int items = ndir * B * H;
   int* counter = reinterpret_cast<int*>(tables + (size_t)items * p.nc * TAB_FLOATS);   // the workspace's spare 128 bytes
-  ssd_tables_kernel<<<items * p.nc, TQ, 0, (cudaStream_t)stream>>>(dt, A_log, tables, B, L, H, p.nc, counter);
+  hnb::launch_pdl(ssd_tables_kernel, dim3(items * p.nc), dim3(TQ), 0, (cudaStream_t)stream, dt, A_log, tables, B, L, H, p.nc, counter);
   static const bool dynamic = getenv("HNB_SSD_FWD_DYNAMIC") && atoi(getenv("HNB_SSD_FWD_DYNAMIC")) != 0;
   p.counter = dynamic ? counter : nullptr;
   HNB_LAUNCH_CHECK("ssd_tables");
@@ -1745,7 +1824,7 @@ int hnb_ssd_fwd_tc(const void* xconv, const float* dt, const float* A_log, const
     static const int per_sm = getenv("HNB_SSD_FWD2_PER_SM") ? atoi(getenv("HNB_SSD_FWD2_PER_SM")) : 2;   // diagnosis
     const int grid2 = items < per_sm * sm_count() ? items : per_sm * sm_count();
     HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_fwd2_tc_kernel, F2_SMEM));
-    ssd_fwd2_tc_kernel<<<grid2, F2_THREADS, F2_SMEM, (cudaStream_t)stream>>>(tm, p);
+    hnb::launch_pdl(ssd_fwd2_tc_kernel, dim3(grid2), dim3(F2_THREADS), F2_SMEM, (cudaStream_t)stream, tm, p);
     HNB_LAUNCH_CHECK("ssd_fwd2_tc");
     return HNB_OK;
   }
@@ -1778,8 +1857,61 @@ static bool ssd_bwd_legacy_env() {
   static const bool legacy = getenv("HNB_SSD_BWD") && atoi(getenv("HNB_SSD_BWD")) == 3;   // 3 = round-1 three-kernel backward
   return legacy;
 }
+// Span schedule of the fused backward (BwdParams::span_mode): cost of a head-step in 1/64 of a full-chunk head-step, the
+// per-item overhead (C | B load, dB | dC store: ~0.6 head-steps) spread over the item's heads.  Applicable when every CTA's
+// piece is longer than an item (H head-steps), so that no item is cut twice.
+static bool span_enabled() {
+  static const bool off = getenv("HNB_SSD_SPAN") && atoi(getenv("HNB_SSD_SPAN")) == 0;
+  return !off;
+}
+static int span_ctas() {
+  static const int force = getenv("HNB_SSD_SPAN_CTAS") ? atoi(getenv("HNB_SSD_SPAN_CTAS")) : 0;   // diagnosis: fewer SMs
+  const int n = sm_count() < SPAN_MAX_CTAS ? sm_count() : SPAN_MAX_CTAS;
+  return force > 0 && force < n ? force : n;
+}
+// Cut positions (head-step indices) of the G pieces: equal cost.  A head-step is a chain of hand-offs whose latencies
+// hardly shrink with the frame count, so a head-step of the partly filled last chunk weighs w = w0 + (1 - w0) rem / 128 of a
+// full one with w0 close to 1 (measured: with w0 = 0.45 the CTAs holding the 14-frame chunks of the 398-frame rows ran
+// 43 head-steps against 23 elsewhere and the kernel took 279 us instead of 223).  HNB_SSD_SPAN=0: cuts at item borders only.
+static void span_cuts(int ndirB, int L, int H, int G, SpanCuts* out) {
+  static const double w0 = getenv("HNB_SSD_SPAN_W0") ? atof(getenv("HNB_SSD_SPAN_W0")) : 0.9;
+  const int nc = cdiv(L, TQ), rem = L - (nc - 1) * TQ;
+  const long long nfull = (long long)ndirB * (rem == TQ ? nc : nc - 1), npart = (long long)ndirB * nc - nfull;
+  const double w = w0 + (1.0 - w0) * rem / TQ;
+  const double cfull = (double)nfull * H, total = cfull + (double)npart * H * w;
+  const long long steps = (nfull + npart) * H;
+  if (!span_enabled()) {                                               // whole items, contiguous runs of equal length
+    const long long n = nfull + npart;
+    for (int k = 0; k <= SPAN_MAX_CTAS; ++k) out->g[k] = (int)((k >= G ? n : n * k / G) * H);
+    return;
+  }
+  out->g[0] = 0;
+  double done = 0.0;                                                   // cost in front of the previous cut
+  for (int k = 1; k < G; ++k) {
+    const double x = done + (total - done) / (G - k + 1);               // what is left, shared by the CTAs that are left
+    long long c = x < cfull ? (long long)(x + 0.5) : (long long)(cfull + (x - cfull) / w + 0.5);
+    const long long prev = out->g[k - 1];
+    if (c < prev) c = prev;
+    if (c > steps) c = steps;
+    if (prev % H != 0 && c % H != 0 && prev / H == c / H) c = (c / H + 1) * H;   // never two cuts inside one item
+    out->g[k] = (int)c;
+    done = c < (long long)cfull ? (double)c : cfull + ((double)c - cfull) * w;
+  }
+  for (int k = G; k <= SPAN_MAX_CTAS; ++k) out->g[k] = (int)steps;
+}
+
+// host-only query (tests): the G + 1 cut positions of the span schedule for a problem, G pieces
+extern "C" int hnb_ssd_span_cuts(int ndirB, int L, int H, int G, int* out) {
+  HNB_CHECK_ARG(out && ndirB > 0 && L > 0 && H > 0 && G >= 1 && G <= SPAN_MAX_CTAS, "ssd_span_cuts: bad arguments");
+  SpanCuts c;
+  span_cuts(ndirB, L, H, G, &c);
+  for (int k = 0; k <= G; ++k) out[k] = c.g[k];
+  return HNB_OK;
+}
+
 int hnb_ssd_dbc_parts_tc(int ndir, int B, int L, int H, int variant) {
   if (ssd_bwd_legacy_env()) variant = 1;
+  if (variant == 0) return 1;                          // fused kernel: cut items are summed inside the kernel (fix-up buffer)
   const int sms = sm_count(), nc = cdiv(L, TQ), rem = L - (nc - 1) * TQ;
   const int nfull = ndir * B * (rem == TQ ? nc : nc - 1), npart = ndir * B * nc - nfull;
   int best = 1;
@@ -1856,8 +1988,13 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   HNB_CHECK_ARG((long long)ndir * B * H * nc * (H > B ? H : B) < (1LL << 31), "ssd_bwd(tcgen05): problem too large");
   p.tables = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(states) + tc_tables_offset(ndir, B, L, H));
   p.dbg = nullptr;
+  HNB_CHECK_ARG(variant != 0 || dbc_parts == 1, "ssd_bwd(tcgen05): the fused backward writes one dBC part");
+  p.fix = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws2) + tc_tables_offset(ndir, B, L, H));
+  p.fix_flags = reinterpret_cast<int*>(p.fix + (size_t)SPAN_MAX_CTAS * 2 * 4 * TQ * 32);
+  SpanCuts cuts = {};
+  if (variant == 0) span_cuts(p.ndirB, L, H, span_ctas(), &cuts);
   const bool debug = getenv("HNB_SSD_DEBUG") != nullptr;
-  if (debug) { cudaMalloc(&p.dbg, 256); cudaMemsetAsync(p.dbg, 0, 256, st); }
+  if (debug) { cudaMalloc(&p.dbg, 4096); cudaMemsetAsync(p.dbg, 0, 4096, st); }
   const int sms = sm_count();
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dstate_tc_kernel, D1_SMEM));
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dx_tc_kernel<BWD_THREADS, false>, D2_SMEM));
@@ -1865,20 +2002,33 @@ int hnb_ssd_bwd_tc(const void* dy, const void* xconv, const void* y, const float
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dx_tc_kernel<BWD_THREADS, true>, D2_SMEM));
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_dbc_tc_kernel<BWD_THREADS, true>, D3_SMEM));
   int items = ndir * B * H;
-  ssd_bwd_dstate_tc_kernel<<<items < 2 * sms ? items : 2 * sms, D1_THREADS, D1_SMEM, st>>>(tmX, tmDY, p);
+  hnb::launch_pdl(ssd_bwd_dstate_tc_kernel, dim3(items < 2 * sms ? items : 2 * sms), dim3(D1_THREADS), D1_SMEM, st, tmX, tmDY, p);
   HNB_LAUNCH_CHECK("ssd_bwd_dstate_tc");
   if (variant == 0) {                                   // dx / ddt / dA / dD and dB / dC in one pass
     HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_fused_tc_kernel<false>, DF_SMEM));
     HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_fused_tc_kernel<true>, DF_SMEM));
-    items = ndir * B * nc * dbc_parts;
-    if (debug) ssd_bwd_fused_tc_kernel<true><<<items < sms ? items : sms, DF_THREADS, DF_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
-    else ssd_bwd_fused_tc_kernel<false><<<items < sms ? items : sms, DF_THREADS, DF_SMEM, st>>>(tmX, tmDY, tmS, tmG, p);
+    items = span_ctas();                                 // one resident CTA per SM: the fix-up wait relies on it
+    if (debug) hnb::launch_pdl(ssd_bwd_fused_tc_kernel<true>, dim3(items), dim3(DF_THREADS), DF_SMEM, st, tmX, tmDY, tmS, tmG, p, cuts);
+    else hnb::launch_pdl(ssd_bwd_fused_tc_kernel<false>, dim3(items), dim3(DF_THREADS), DF_SMEM, st, tmX, tmDY, tmS, tmG, p, cuts);
     HNB_LAUNCH_CHECK("ssd_bwd_fused_tc");
     if (debug) {
-      long long h[32];
+      long long h[512];
       cudaStreamSynchronize(st);
-      cudaMemcpy(h, p.dbg, 256, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h, p.dbg, 4096, cudaMemcpyDeviceToHost);
       cudaFree(p.dbg);
+      {
+        long long mn = 1LL << 60, mx = 0; int imx = 0;
+        for (int k = 0; k < items; ++k) { const long long c = h[32 + 2 * k]; if (c < mn) mn = c; if (c > mx) { mx = c; imx = k; } }
+        fprintf(stderr, "[ssd_bwd_fused CTA0 pieces] first head-step of a piece %.0f cycles (%lld) | piece end: wait for the accumulation %.0f, dB|dC out %.0f (%lld)\n",
+                h[11] ? (double)h[10] / h[11] : 0.0, h[11], h[14] ? (double)h[12] / h[14] : 0.0, h[14] ? (double)h[13] / h[14] : 0.0, h[14]);
+        for (int i = 0; i < 7; ++i)
+          if (h[400 + 4 * i + 3])
+            fprintf(stderr, "[ssd_bwd_fused CTA0 piece %d] dB in registers after %lld cycles, dC after %lld, all stored after %lld (to_fix %lld from_fix %lld)\n",
+                    i, h[400 + 4 * i], h[401 + 4 * i], h[402 + 4 * i], h[403 + 4 * i] & 1, (h[403 + 4 * i] >> 1) & 1);
+        fprintf(stderr, "[ssd_bwd_fused per-CTA cycles] min %lld max %lld (CTA %d, %lld steps) | CTA0 %lld (%lld steps) CTA%d %lld (%lld steps) CTA%d %lld (%lld steps)\n",
+                mn, mx, imx, h[33 + 2 * imx], h[32], h[33], items / 2, h[32 + 2 * (items / 2)], h[33 + 2 * (items / 2)], items - 1,
+                h[32 + 2 * (items - 1)], h[33 + 2 * (items - 1)]);
+      }
       for (int w = 0; w < 2; ++w) {
         const long long* d = h + 16 * w;
         const double n = d[9] > 0 ? (double)d[9] : 1.0;

@@ -19,6 +19,7 @@ template <int CPT>
 __global__ void __launch_bounds__(256)
 sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B, int T,
                      int F, int C, int T1, int F1, __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   extern __shared__ float s_in[];                       // [3][F]
   const int CG = C / CPT;                               // threads per pixel
   const int cgp = threadIdx.x % CG, pl = threadIdx.x / CG, PX = blockDim.x / CG;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256, 3)
 sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ a1, const __nv_bfloat16* __restrict__ dout,
                      int B, int T, int F, int C, int T1, int F1, int rows_per_block, float* __restrict__ dw,
                      float* __restrict__ db) {
+  pdl_enter();
   static_assert(CPT == 4, "vector reductions below assume channel quads");
   extern __shared__ float s_in[];                       // [3][F], then reused for the block reduction
   const int CG = C / CPT;
@@ -154,6 +156,7 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
 // broadcast add, a clamp, a threshold_backward and a 116 M-element bf16 column reduction: four passes each way).
 __global__ void __launch_bounds__(256)
 bias_relu_fwd_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ bias, long long rows, int C) {
+  pdl_enter();
   const int CG = C / 8, cgp = threadIdx.x % CG, rl = threadIdx.x / CG, RL = blockDim.x / CG;
   float b[8];
   ldv<float, 8>(bias + cgp * 8, b);
@@ -170,6 +173,7 @@ bias_relu_fwd_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ bi
 __global__ void __launch_bounds__(256)
 bias_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      __nv_bfloat16* __restrict__ dpre, float* __restrict__ db, long long rows, int C) {
+  pdl_enter();
   extern __shared__ float s_red[];                      // [RL-1][CG][8]
   const int CG = C / 8, cgp = threadIdx.x % CG, rl = threadIdx.x / CG, RL = blockDim.x / CG;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -218,7 +222,7 @@ extern "C" int hnb_subsample_conv1_fwd(const float* feats, const float* w, const
   const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
   const long long rows = (long long)B * T1;
   const int CG = C / 8, PX = 256 / CG > 0 ? 256 / CG : 1;
-  sub_conv1_fwd_kernel<8><<<cdiv(rows, SUB_RB), CG * PX, 3 * F * sizeof(float), (cudaStream_t)stream>>>(
+  hnb::launch_pdl(sub_conv1_fwd_kernel<8>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream, 
       feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
   HNB_LAUNCH_CHECK("subsample_conv1_fwd");
   return HNB_OK;
@@ -246,7 +250,7 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const
   const size_t red = (size_t)(PX > 1 ? PX - 1 : 0) * CG * 40 * sizeof(float);
   if (red > smem) smem = red;
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4>, (int)smem));
-  sub_conv1_bwd_kernel<4><<<blocks, CG * PX, smem, (cudaStream_t)stream>>>(feats, (const __nv_bfloat16*)a1,
+  hnb::launch_pdl(sub_conv1_bwd_kernel<4>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
       (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
   HNB_LAUNCH_CHECK("subsample_conv1_bwd");
   return HNB_OK;
@@ -270,7 +274,7 @@ extern "C" int hnb_bias_relu_fwd(void* x, const float* bias, long long rows, int
                 "bias_relu_fwd: null or misaligned pointer");
   int threads, blocks, rc = bias_relu_geometry("bias_relu_fwd", rows, C, &threads, &blocks);
   if (rc) return rc;
-  bias_relu_fwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, bias, rows, C);
+  hnb::launch_pdl(bias_relu_fwd_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (__nv_bfloat16*)x, bias, rows, C);
   HNB_LAUNCH_CHECK("bias_relu_fwd");
   return HNB_OK;
 }
@@ -281,7 +285,7 @@ extern "C" int hnb_bias_relu_bwd(const void* dout, const void* out, void* dpre, 
   if (rc) return rc;
   const int CG = C / 8, RL = threads / CG;
   const size_t smem = (size_t)(RL > 1 ? RL - 1 : 0) * CG * 8 * sizeof(float);
-  bias_relu_bwd_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)out,
+  hnb::launch_pdl(bias_relu_bwd_kernel, dim3(blocks), dim3(threads), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out,
                                                                        (__nv_bfloat16*)dpre, db, rows, C);
   HNB_LAUNCH_CHECK("bias_relu_bwd");
   return HNB_OK;

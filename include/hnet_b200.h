@@ -175,6 +175,9 @@ int hnb_ssd_fwd(const void* xconv, int dtype, const float* dt, const float* A_lo
  * work items fill whole waves of SMs; each group writes its own partial sum and hnb_conv_bwd adds the parts up.
  * ws2: second workspace of hnb_ssd_ws_bytes() bytes. */
 int hnb_ssd_dbc_parts(int ndir, int B, int L, int H, int impl);
+/* host-only (tests): out[0..G] = the cut positions of that schedule for G SMs, as indices into the sequence of
+ * (row-chunk item, head) steps (items: every full chunk first, then the partly filled last chunks) */
+int hnb_ssd_span_cuts(int ndirB, int L, int H, int G, int* out);
 int hnb_ssd_bwd(const void* dy, const void* xconv, const void* y, int dtype, const float* dt,
                 const float* A_log, const float* Dskip, const void* states,
                 int ndir, int B, int L, int di, int N, int H,

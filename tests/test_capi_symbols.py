@@ -79,10 +79,11 @@ def test_host_side_cost_models_are_sane():
     L_ = lib()
     parts = L_.raw("ssd_dbc_parts")
     for (ndir, B, L, H) in ((2, 40, 398, 12), (2, 40, 196, 16), (2, 2, 1498, 24), (1, 1, 7, 3), (2, 3, 150, 5)):
-        p1 = parts(ndir, B, L, H, 1)
-        assert p1 in (1, 2) and H % p1 == 0, (ndir, B, L, H, p1)
+        p1, p3 = parts(ndir, B, L, H, 1), parts(ndir, B, L, H, 3)
+        assert p1 == 1, (ndir, B, L, H, p1)          # fused backward: cut items are summed inside the kernel (fix-up buffer)
+        assert p3 in (1, 2) and H % p3 == 0, (ndir, B, L, H, p3)
         assert parts(ndir, B, L, H, 0) == 1
-    assert parts(2, 40, 196, 16, 1) == 2            # the main stack at the headline batch: 160 items are 1.1 waves of 148 SMs
+    assert parts(2, 40, 196, 16, 3) == 2            # three-kernel backward, main stack at the headline batch: 160 items are 1.1 waves of 148 SMs
     hint = L_.raw("gemm_splitk_hint")
     for (M, N, K) in ((3616, 384, 15920), (384, 1536, 15920), (4640, 512, 7840), (128, 128, 64), (8, 8, 8)):
         sk = hint(M, N, K)
@@ -90,3 +91,33 @@ def test_host_side_cost_models_are_sane():
     assert hint(3616, 384, 15920) > 1               # weight gradients (K = tokens) are split
     ws = L_.raw("ssd_ws_bytes")
     assert 0 < ws(2, 4, 398, 768, 128, 12) < ws(2, 8, 398, 768, 128, 12) < ws(2, 8, 1498, 768, 128, 12)
+
+
+def test_ssd_span_schedule_cuts():
+    """The fused SSD backward cuts the sequence of all (row-chunk, head) steps into one piece per SM.  Host arithmetic only:
+    the cuts are monotone, cover every step exactly once, never fall twice inside one item (so dB | dC has at most two
+    partial sums per row-chunk), and the pieces carry equal cost within one head-step plus the snapping slack."""
+    import ctypes
+    from dcasr_b200._lib import lib
+    f = lib().raw("ssd_span_cuts")
+    for (ndirB, L, H, G) in ((80, 398, 12, 148), (80, 196, 16, 148), (20, 1498, 16, 148), (20, 640, 24, 148), (6, 398, 12, 148),
+                             (1, 7, 3, 148), (4, 150, 5, 132), (80, 256, 12, 148), (3, 129, 4, 16)):
+        out = (ctypes.c_int * (G + 1))()
+        assert f(ndirB, L, H, G, out) == 0
+        c = list(out)
+        nc = (L + 127) // 128
+        steps = ndirB * nc * H
+        assert c[0] == 0 and c[-1] == steps and all(a <= b for a, b in zip(c, c[1:])), (ndirB, L, H, c[:8])
+        inner = {}
+        for v in c[1:-1]:
+            if v % H and v < steps:
+                inner[v // H] = inner.get(v // H, set()) | {v}
+        assert all(len(v) == 1 for v in inner.values()), (ndirB, L, H)
+        if steps >= 8 * G:                           # big problems: the pieces are balanced
+            rem = L - (nc - 1) * 128
+            nfull = ndirB * (nc if rem == 128 else nc - 1) * H
+            w = 0.9 + 0.1 * rem / 128
+            cost = lambda a, b: max(0, min(b, nfull) - a) + w * max(0, b - max(a, nfull))
+            costs = [cost(a, b) for a, b in zip(c, c[1:])]
+            ideal = sum(costs) / G
+            assert max(costs) <= ideal + (1.5 if ideal >= H else H / 2 + 1.5), (ndirB, L, H, ideal, max(costs))
