@@ -138,6 +138,47 @@ conv_fwd_kernel(const T* __restrict__ zx, long long ldz, long long dstride, cons
       bias[i] = __ldg(conv_b + (long long)dir * C + c + i);
     }
     const T* src = rowbase + xoff + c;
+    // Fast path (block-uniform; every segment of a fixed-length batch takes it): the segment and its halo lie inside the row
+    // and on one side of `len`, so the natural index moves by a constant +-1 per scan position -- running pointers, no
+    // per-position index arithmetic or bounds predicates (the kernel is issue-bound: ~40 % of its instructions were those).
+    const int blk_lo = blockIdx.y * CONV_SEG * RUN - 3, blk_hi = (blockIdx.y + 1) * CONV_SEG * RUN;    // [lo, hi): the block's positions and halo
+    const bool fast = blk_hi <= L && (dir == 0 || blk_hi <= len || (blk_lo >= len && blk_lo >= 0));
+    if (fast) {
+      const long long dstep = (dir == 1 && sb < len) ? -ldz : ldz;
+      const T* pl = src + (long long)scan_to_nat(dir, sb, len) * ldz;
+      typename V16<T>::raw_t h[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) h[k] = sb > 0 ? V16<T>::ldg(pl - (3 - k) * dstep) : V16<T>::zero();   // (sb = 0: warp-uniform)
+      typename V16<T>::raw_t nxt[TS];
+#pragma unroll
+      for (int k = 0; k < TS; ++k) { nxt[k] = V16<T>::ldg(pl); pl += dstep; }
+      float win[3][VN];
+      V16<T>::unpack(h[0], win[0]); V16<T>::unpack(h[1], win[1]); V16<T>::unpack(h[2], win[2]);
+      T* po = xconv + (sbase + sb) * C + c;
+#pragma unroll
+      for (int tile = 0; tile < NTILE; ++tile) {
+        typename V16<T>::raw_t raw[TS];
+#pragma unroll
+        for (int k = 0; k < TS; ++k) raw[k] = nxt[k];
+        if (tile + 1 < NTILE) {
+#pragma unroll
+          for (int k = 0; k < TS; ++k) { nxt[k] = V16<T>::ldg(pl); pl += dstep; }
+        }
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+          float cur[VN], o[VN];
+          V16<T>::unpack(raw[k], cur);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) {
+            const float pre = bias[i] + w[i][0] * win[0][i] + w[i][1] * win[1][i] + w[i][2] * win[2][i] + w[i][3] * cur[i];
+            o[i] = pre * sigmoid_t<T>(pre);
+            win[0][i] = win[1][i]; win[1][i] = win[2][i]; win[2][i] = cur[i];
+          }
+          V16<T>::st(po, V16<T>::pack(o));
+          po += C;
+        }
+      }
+    } else {
     typename V16<T>::raw_t h[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -178,6 +219,7 @@ conv_fwd_kernel(const T* __restrict__ zx, long long ldz, long long dstride, cons
         if (s0 + k < L) V16<T>::st(xconv + (sbase + s0 + k) * C + c, V16<T>::pack(o));
       }
     }
+  }
   }
   if (blockIdx.x == 0) {                                  // dt = softplus(raw + bias): H values per row, one column block does it
     const int s_lo = blockIdx.y * CONV_SEG * RUN, s_hi = min(s_lo + CONV_SEG * RUN, L);
@@ -250,6 +292,78 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
     // issued; `two` is uniform over the block (a block's 256 channels lie on one side of the x | BC border).
     const bool two = PARTS2 && !is_x;                                // (the one-part instantiation carries no gn2)
     const T* gsrc2 = gsrc + dbc_part_stride;
+    // Fast path (block-uniform; see the forward): every position this block touches lies inside the row and on one side of
+    // `len` -- running pointers instead of per-position index arithmetic and bounds predicates.
+    const int blk_lo = blockIdx.y * CONV_SEG * RUN - 3, blk_hi = (blockIdx.y * CONV_SEG + CONV_SEG - 1) * RUN + TS * NTILE;
+    const bool fast = blk_hi <= L && (dir == 0 || blk_hi <= len || (blk_lo >= len && blk_lo >= 0));
+    if (fast) {
+      const long long dstep = (dir == 1 && sb < len) ? -ldz : ldz;
+      const T* px = src + (long long)scan_to_nat(dir, sb, len) * ldz;
+      T* pd = dst + (long long)scan_to_nat(dir, sb, len) * ldz;           // (the first store, three positions on, goes to position sb)
+      const T* pg = gsrc + (long long)sb * gld;
+      typename VIO::raw_t h[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) h[k] = sb > 0 ? VIO::ldg(px - (3 - k) * dstep) : VIO::zero();   // (sb = 0: warp-uniform)
+      float win[3][VN], dp[3][VN];
+      VIO::unpack(h[0], win[0]); VIO::unpack(h[1], win[1]); VIO::unpack(h[2], win[2]);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { dp[0][i] = 0.f; dp[1][i] = 0.f; dp[2][i] = 0.f; }
+      typename VIO::raw_t xn[TS], gn[TS], gn2[PARTS2 ? TS : 1];
+#pragma unroll
+      for (int k = 0; k < TS; ++k) {
+        xn[k] = VIO::ldg(px); px += dstep;
+        gn[k] = VIO::ldg(pg);
+        if (PARTS2) gn2[k] = two ? VIO::ldg(pg + dbc_part_stride) : VIO::zero();
+        pg += gld;
+      }
+#pragma unroll 2
+      for (int tile = 0; tile < NTILE; ++tile) {
+        const bool first = tile == 0, last = tile == NTILE - 1;
+        typename VIO::raw_t xr[TS], gr[TS];
+#pragma unroll
+        for (int k = 0; k < TS; ++k) { xr[k] = xn[k]; gr[k] = (PARTS2 && two) ? VIO::add(gn[k], gn2[PARTS2 ? k : 0]) : gn[k]; }
+        if (!last) {
+#pragma unroll
+          for (int k = 0; k < TS; ++k) {
+            xn[k] = VIO::ldg(px); px += dstep;
+            gn[k] = VIO::ldg(pg);
+            if (PARTS2 && two) gn2[k] = VIO::ldg(pg + dbc_part_stride);
+            pg += gld;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+          float cur[VN], g[VN], dcur[VN];
+          VIO::unpack(xr[k], cur);
+          VIO::unpack(gr[k], g);
+          const bool own = !(k >= TS - 3 && last);                        // halo positions belong to the next segment
+#pragma unroll
+          for (int i = 0; i < VN; ++i) {
+            const float pre = bias[i] + w[i][0] * win[0][i] + w[i][1] * win[1][i] + w[i][2] * win[2][i] + w[i][3] * cur[i];
+            const float sgm = sigmoid_t<T>(pre);
+            dcur[i] = g[i] * sgm * (1.f + pre * (1.f - sgm));
+            if (own) {
+              gw[i][0] += dcur[i] * win[0][i]; gw[i][1] += dcur[i] * win[1][i];
+              gw[i][2] += dcur[i] * win[2][i]; gw[i][3] += dcur[i] * cur[i];
+              gb[i] += dcur[i];
+            }
+          }
+          if (!(k < 3 && first)) {                                        // d input at position s - 3 is complete
+            float o[VN];
+#pragma unroll
+            for (int i = 0; i < VN; ++i)
+              o[i] = w[i][3] * dp[0][i] + w[i][2] * dp[1][i] + w[i][1] * dp[2][i] + w[i][0] * dcur[i];
+            VIO::st(pd, VIO::pack(o));
+            pd += dstep;
+          }
+#pragma unroll
+          for (int i = 0; i < VN; ++i) {
+            win[0][i] = win[1][i]; win[1][i] = win[2][i]; win[2][i] = cur[i];
+            dp[0][i] = dp[1][i]; dp[1][i] = dp[2][i]; dp[2][i] = dcur[i];
+          }
+        }
+      }
+    } else {
     typename VIO::raw_t h[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -319,6 +433,7 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
         }
       }
     }
+  }
   }
   // parameter gradients: segments 1..3 -> shared memory -> segment 0 adds and issues 5 vector reductions per thread
   if (sg > 0) {
