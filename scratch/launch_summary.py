@@ -4,8 +4,10 @@ src = sys.argv[1]
 rows = [r for r in csv.reader(open(src)) if len(r) > 5]
 hdr = next(r for r in rows if "Kernel Name" in r); i0 = rows.index(hdr)
 kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+mn = hdr.index("Metric Name")
 agg = collections.OrderedDict(); tot = 0.0; n = 0
 for r in rows[i0 + 1:]:
+    if not r[mn].startswith("gpu__time_duration"): continue     # (the CSV may carry DRAM byte counters too)
     v = float(r[mv].replace(",", ""))
     v = v / 1000 if r[mu] in ("ns", "nsecond") else (v * 1000 if r[mu] in ("ms", "msecond") else v)
     name = r[kn].replace("void ", "")
