@@ -9,6 +9,8 @@
 // Every small matmul is written as an outer-product loop over the contraction index k with the
 // lane-varying operand stored [k][lanes] in shared memory (conflict-free) and the other operand
 // broadcast.  Per-chunk states are stored [N][P] (p contiguous) so that no state tile is ever transposed.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hnb {
@@ -47,16 +49,17 @@ __device__ __forceinline__ void chunk_cumsum(const float* __restrict__ dtp, long
 // grid (nchunks, ndir*B), loop over heads.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE>
-__global__ void __launch_bounds__(ST, 2)
+__global__ void __launch_bounds__(ST, 4)                        // 64 registers, 48.5 KB: four CTAs per SM
 ssd_chunk_state_kernel(const T* __restrict__ U, long long ldu, const T* __restrict__ xconv, int C, int di,
                        const float* __restrict__ dt, const float* __restrict__ A_log, int ndir, int B, int L, int H,
-                       int nc, float* __restrict__ states, float* __restrict__ decay) {
+                       int nc, int hpg, float* __restrict__ states, float* __restrict__ decay) {
   extern __shared__ float smem[];
   float* Vs = smem;                       // [SQ][SN]
   float* Us = Vs + SQ * SN;               // [SQ][SP] (pre-scaled by w_q)
   float* s_dt = Us + SQ * SP;             // [SQ]
   float* s_cs = s_dt + SQ;                // [SQ]
-  const int c = blockIdx.x, db = blockIdx.y, dir = db / B;
+  const int c = blockIdx.z, db = blockIdx.y, dir = db / B;      // grid (head groups, ndir*B, chunks): the short last chunks run last
+  const int h_lo = blockIdx.x * hpg, h_hi = min(H, h_lo + hpg);
   const int tid = threadIdx.x;
   const int q0 = c * SQ, qv = min(SQ, L - q0);
   const long long row0 = (long long)db * L + q0;
@@ -73,7 +76,7 @@ ssd_chunk_state_kernel(const T* __restrict__ U, long long ldu, const T* __restri
   const int tp = tid & 15, tn = tid >> 4;
   const float4* Va = reinterpret_cast<const float4*>(Vs) + 2 * tn;
   const float4* Ub = reinterpret_cast<const float4*>(Us) + tp;
-  for (int h = 0; h < H; ++h) {
+  for (int h = h_lo; h < h_hi; ++h) {
     const float A = -__expf(A_log[dir * H + h]);
     __syncthreads();
     chunk_cumsum(dt + row0 * H + h, H, qv, A, s_dt, s_cs);
@@ -172,7 +175,8 @@ template <typename T>
 __global__ void __launch_bounds__(ST, 2)
 ssd_chunk_scan_kernel(const T* __restrict__ xconv, int C, int di, const float* __restrict__ dt,
                       const float* __restrict__ A_log, const float* __restrict__ Dskip,
-                      const float* __restrict__ states, int ndir, int B, int L, int H, int nc, T* __restrict__ y) {
+                      const float* __restrict__ states, int ndir, int B, int L, int H, int nc, int hpg,
+                      T* __restrict__ y) {
   extern __shared__ float smem[];
   float* Ct = smem;                        // [SN][SQ]   C transposed
   float* Bt = Ct + SN * SQ;                // [SN][PADQ] B transposed (dead after G)
@@ -181,7 +185,8 @@ ssd_chunk_scan_kernel(const T* __restrict__ xconv, int C, int di, const float* _
   float* Ss = Xs + SQ * SP;                // [SN][SP]
   float* s_dt = smem + SCAN_SMEM_FLOATS - 2 * SQ;
   float* s_cs = s_dt + SQ;
-  const int c = blockIdx.x, db = blockIdx.y, dir = db / B;
+  const int c = blockIdx.z, db = blockIdx.y, dir = db / B;      // grid (head groups, ndir*B, chunks): the short last chunks run last
+  const int h_lo = blockIdx.x * hpg, h_hi = min(H, h_lo + hpg);
   const int tid = threadIdx.x;
   const int q0 = c * SQ, qv = min(SQ, L - q0);
   const long long row0 = (long long)db * L + q0;
@@ -219,7 +224,7 @@ ssd_chunk_scan_kernel(const T* __restrict__ xconv, int C, int di, const float* _
   const float4* Xb = reinterpret_cast<const float4*>(Xs) + tj;
   const float4* Sb = reinterpret_cast<const float4*>(Ss) + tj;
   const int s_end = min(qv, 4 * ti + 4);             // M[t][s] = 0 for s > t
-  for (int h = 0; h < H; ++h) {
+  for (int h = h_lo; h < h_hi; ++h) {
     const float A = -__expf(A_log[dir * H + h]);
     const float Dh = Dskip[dir * H + h];
     __syncthreads();                                 // B^T (first head) / the previous head's tiles are no longer read
@@ -620,6 +625,18 @@ extern "C" int hnb_ssd_dbc_parts(int ndir, int B, int L, int H, int impl) {
   return (impl == 1 || impl == 3 || impl == 4 || impl == 5) ? hnb_ssd_dbc_parts_tc(ndir, B, L, H, impl == 3 ? 1 : 0) : 1;
 }
 
+// chunk_state has no per-group recomputation (only the 32 KB B tile is staged again): small groups fill the SMs
+static int ssd_heads_per_group_state(int H) {
+  static const int env = [] { const char* e = getenv("HNB_SSD_EXACT_HPG_STATE"); return e ? atoi(e) : 0; }();
+  const int want = env > 0 ? env : 4;
+  return want < H ? want : H;
+}
+
+static int ssd_heads_per_group(int H) {
+  static const int env = [] { const char* e = getenv("HNB_SSD_EXACT_HPG"); return e ? atoi(e) : 0; }();
+  return env > 0 && env < H ? env : H;      // measured (40 rows, B200): 16 / 4 / 1 heads per group = 555 / 581 / 724 us (main stack), 748 / 731 / 972 (outer)
+}
+
 template <typename T>
 static int ssd_fwd_impl(const T* xconv, const float* dt, const float* A_log, const float* Dskip, int ndir, int B,
                         int L, int di, int H, T* y, float* ws, cudaStream_t st) {
@@ -630,13 +647,18 @@ static int ssd_fwd_impl(const T* xconv, const float* dt, const float* A_log, con
   const size_t sm3 = SCAN_SMEM_FLOATS * sizeof(float);
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_chunk_state_kernel<T, 0>, (int)sm1));
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_chunk_scan_kernel<T>, (int)sm3));
-  dim3 grid(nc, ndir * B);
-  ssd_chunk_state_kernel<T, 0><<<grid, ST, sm1, st>>>(xconv, C, xconv, C, di, dt, A_log, ndir, B, L, H, nc, states, decay);
+  // Grid (head groups, rows, chunks): chunks slowest, so the short last chunk of every row runs in the tail of the launch
+  // (627 -> 555 us on the main stack by itself).  Splitting the heads of a (row, chunk) into groups (HNB_SSD_EXACT_HPG) makes
+  // the grid several waves deep but re-stages B | C and recomputes G = C B^T per group: no gain measured, one group by default.
+  const int hpg = ssd_heads_per_group(H);
+  const int hpg_s = ssd_heads_per_group_state(H);
+  dim3 grid(cdiv(H, hpg), ndir * B, nc);
+  ssd_chunk_state_kernel<T, 0><<<dim3(cdiv(H, hpg_s), ndir * B, nc), ST, sm1, st>>>(xconv, C, xconv, C, di, dt, A_log, ndir, B, L, H, nc, hpg_s, states, decay);
   HNB_LAUNCH_CHECK("ssd_chunk_state");
   const long long total4 = (long long)ndir * B * H * (SN * SP / 4);
   ssd_state_pass_kernel<false><<<cdiv(total4, 256), 256, 0, st>>>(states, decay, H, nc, total4);
   HNB_LAUNCH_CHECK("ssd_state_pass");
-  ssd_chunk_scan_kernel<T><<<grid, ST, sm3, st>>>(xconv, C, di, dt, A_log, Dskip, states, ndir, B, L, H, nc, y);
+  ssd_chunk_scan_kernel<T><<<grid, ST, sm3, st>>>(xconv, C, di, dt, A_log, Dskip, states, ndir, B, L, H, nc, hpg, y);
   HNB_LAUNCH_CHECK("ssd_chunk_scan");
   return HNB_OK;
 }
@@ -676,7 +698,8 @@ static int ssd_bwd_impl(const T* dy, const T* xconv, const T* y, const float* dt
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_chunk_state_kernel<T, 1>, (int)sm1));
   HNB_CUDA_CALL(hnb_set_max_smem((const void*)ssd_bwd_chunk_kernel<T>, (int)smb));
   dim3 grid(nc, ndir * B);
-  ssd_chunk_state_kernel<T, 1><<<grid, ST, sm1, st>>>(dy, di, xconv, C, di, dt, A_log, ndir, B, L, H, nc, gstates, nullptr);
+  const int hpg = ssd_heads_per_group_state(H);
+  ssd_chunk_state_kernel<T, 1><<<dim3(cdiv(H, hpg), ndir * B, nc), ST, sm1, st>>>(dy, di, xconv, C, di, dt, A_log, ndir, B, L, H, nc, hpg, gstates, nullptr);
   HNB_LAUNCH_CHECK("ssd_bwd_dstate");
   const long long total4 = (long long)ndir * B * H * (SN * SP / 4);
   ssd_state_pass_kernel<true><<<cdiv(total4, 256), 256, 0, st>>>(gstates, decay, H, nc, total4);
