@@ -9,6 +9,8 @@
 // of PX pixel lanes and keeps its 9*CPT taps in registers; the three input rows a (b, t) row needs are staged in shared
 // memory.  NHWC stores/loads are 16 bytes (forward, 8 channels) / 8 bytes (backward, 4 channels) per thread, contiguous
 // across the threads of a pixel.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hnb {
@@ -57,8 +59,8 @@ sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
 // backward: dA1 and the saved output A1 (both NHWC, bf16) -> dW1 [C, 9], db1 [C] (fp32, accumulated).  The ReLU mask
 // is A1 > 0, as in the reference's threshold_backward; the input needs no gradient.  A block reduces its rows in
 // registers, then across its pixel lanes through shared memory, then issues 10 vector reductions per channel quad.
-template <int CPT>
-__global__ void __launch_bounds__(256, 3)
+template <int CPT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ a1, const __nv_bfloat16* __restrict__ dout,
                      int B, int T, int F, int C, int T1, int F1, int rows_per_block, float* __restrict__ dw,
                      float* __restrict__ db) {
@@ -76,27 +78,40 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
     gb[i] = 0.f;
   }
   const long long rows = (long long)B * T1;
-  const long long r_end = min(rows, (long long)(blockIdx.x + 1) * rows_per_block);
-  for (long long r = (long long)blockIdx.x * rows_per_block; r < r_end; ++r) {
+  const long long r_beg = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = min(rows, r_beg + rows_per_block);
+  // Four pixel vectors of each tensor per thread and step, and the NEXT step's eight loads are issued before the current
+  // step's arithmetic (also across the row boundary): without that every step was one exposed DRAM round trip
+  // (ncu: long-scoreboard stalls 4.4 per issue, 3.1 TB/s).
+  const int NG = (F1 + 4 * PX - 1) / (4 * PX);
+  uint2 gn[4], an[4];
+  auto issue = [&](long long r, int g) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int f = pl + (4 * g + u) * PX;
+      if (f < F1) {
+        gn[u] = __ldg(reinterpret_cast<const uint2*>(dout + ((r * F1 + f) * C + c0)));
+        an[u] = __ldg(reinterpret_cast<const uint2*>(a1 + ((r * F1 + f) * C + c0)));
+      }
+    }
+  };
+  if (r_beg < r_end) issue(r_beg, 0);
+  for (long long r = r_beg; r < r_end; ++r) {
     const int b = (int)(r / T1), t = (int)(r % T1);
     __syncthreads();
     for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) s_in[i] = x[((long long)b * T + 2 * t + i / F) * F + i % F];
     __syncthreads();
-    for (int f0 = pl; f0 < F1; f0 += 4 * PX) {          // four pixel vectors of each tensor in flight per thread
+    for (int g = 0; g < NG; ++g) {
       uint2 gr[4], ar[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int f = f0 + u * PX;
-        if (f < F1) {
-          gr[u] = __ldg(reinterpret_cast<const uint2*>(dout + ((r * F1 + f) * C + c0)));
-          ar[u] = __ldg(reinterpret_cast<const uint2*>(a1 + ((r * F1 + f) * C + c0)));
-        }
-      }
+      for (int u = 0; u < 4; ++u) { gr[u] = gn[u]; ar[u] = an[u]; }
+      if (g + 1 < NG) issue(r, g + 1);
+      else if (r + 1 < r_end) issue(r + 1, 0);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int f = f0 + u * PX;
+        const int f = pl + (4 * g + u) * PX;
         if (f >= F1) break;
-        float xin[9], g[CPT], a[CPT];
+        float xin[9], gq[CPT], a[CPT];
 #pragma unroll
         for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
         {
@@ -104,12 +119,12 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
           const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ar[u]);
           const float2 g0 = __bfloat1622float2(gh[0]), g1 = __bfloat1622float2(gh[1]);
           const float2 a0 = __bfloat1622float2(ah[0]), a1v = __bfloat1622float2(ah[1]);
-          g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
+          gq[0] = g0.x; gq[1] = g0.y; gq[2] = g1.x; gq[3] = g1.y;
           a[0] = a0.x; a[1] = a0.y; a[2] = a1v.x; a[3] = a1v.y;
         }
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-          const float gi = a[i] > 0.f ? g[i] : 0.f;
+          const float gi = a[i] > 0.f ? gq[i] : 0.f;
           gb[i] += gi;
 #pragma unroll
           for (int k = 0; k < 9; ++k) gw[i][k] = fmaf(gi, xin[k], gw[i][k]);
@@ -221,9 +236,16 @@ extern "C" int hnb_subsample_conv1_fwd(const float* feats, const float* w, const
   if (rc) return rc;
   const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
   const long long rows = (long long)B * T1;
-  const int CG = C / 8, PX = 256 / CG > 0 ? 256 / CG : 1;
-  hnb::launch_pdl(sub_conv1_fwd_kernel<8>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream, 
-      feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
+  static const int cpt = [] { const char* e = getenv("HNB_SUB_FWD_CPT"); return e && atoi(e) == 8 ? 8 : 4; }();
+  if (cpt == 4) {                                        // half the taps per thread, 64 registers, five resident blocks: 401 -> 334 us (HNB_SUB_FWD_CPT=8: the former kernel)
+    const int CG = C / 4, PX = 256 / CG > 0 ? 256 / CG : 1;
+    hnb::launch_pdl(sub_conv1_fwd_kernel<4>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
+        feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
+  } else {
+    const int CG = C / 8, PX = 256 / CG > 0 ? 256 / CG : 1;
+    hnb::launch_pdl(sub_conv1_fwd_kernel<8>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
+        feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
+  }
   HNB_LAUNCH_CHECK("subsample_conv1_fwd");
   return HNB_OK;
 }
@@ -241,17 +263,30 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
-  const int CG = C / 4, PX = 256 / CG > 0 ? 256 / CG : 1;
-  int blocks = sms * 6;                                  // two waves of three resident blocks; each ends in 10 reductions per quad
+  static const int nt = [] { const char* e = getenv("HNB_SUB_BWD_THREADS"); return e && atoi(e) == 384 ? 384 : 256; }();   // 384-thread blocks measured slower (658 vs 626 us)
+  static const int minb = [] { const char* e = getenv("HNB_SUB_BWD_MINB"); return e && atoi(e) == 2 ? 2 : 3; }();   // 80 registers (12 bytes spilled), four resident 192-thread blocks: 556 us; 114 registers, no spill: 621 us
+  const int CG = C / 4, PX = nt / CG > 0 ? nt / CG : 1;
+  static const int bpsm = [] { const char* e = getenv("HNB_SUB_BWD_BLOCKS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 12; }();   // measured 3 / 4 / 6 / 8 / 12 / 16 per SM: 705 / 617 / 626 / 596 / 585 / 597 us
+  int blocks = sms * bpsm;                               // whole waves of the resident blocks; each block ends in 10 reductions per quad
   if (blocks > rows) blocks = (int)rows;
   const int rpb = cdiv(rows, blocks);
   blocks = cdiv(rows, rpb);
   size_t smem = 3 * (size_t)F * sizeof(float);
   const size_t red = (size_t)(PX > 1 ? PX - 1 : 0) * CG * 40 * sizeof(float);
   if (red > smem) smem = red;
-  HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4>, (int)smem));
-  hnb::launch_pdl(sub_conv1_bwd_kernel<4>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
-      (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
+  if (nt == 384 && CG * PX <= 384) {                     // two resident blocks of up to 384 threads: a third more bytes in flight per SM
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 384, 2>, (int)smem));
+    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 384, 2>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
+        (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
+  } else if (minb != 2) {
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 256, 3>, (int)smem));
+    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 256, 3>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
+        (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
+  } else {
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 256, 2>, (int)smem));
+    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 256, 2>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
+        (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
+  }
   HNB_LAUNCH_CHECK("subsample_conv1_bwd");
   return HNB_OK;
 }
