@@ -125,7 +125,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
                      long long rows, int d, TDX* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta) {
   pdl_enter();
-  extern __shared__ float sm[];                                     // [2][d]
+  extern __shared__ float sm[];                                     // [NORM_WARPS][2][d]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float ag[NV][VN], ab[NV][VN], gm[NV][VN];
 #pragma unroll
@@ -195,21 +195,40 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
       }
     }
   }
-  // block reduction of the parameter gradients
-  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
-  __syncthreads();
+  // block reduction of the parameter gradients: every warp leaves its partial sums in its own [2][d] slice of shared memory, a
+  // column is summed over the warps by one thread and leaves as a vector reduction (the first version: 6 k shared-memory float
+  // atomics -- CAS loops -- and 2 d scalar global atomics per block, ~5 us of a 26 us kernel)
+  {
+    float* part = sm + (size_t)w * 2 * d;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = (k * 32 + lane) * VN;
-    if (c < d) {
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+      if (c < d) {
 #pragma unroll
-      for (int i = 0; i < VN; ++i) { atomicAdd(&sm[c + i], ag[k][i]); atomicAdd(&sm[d + c + i], ab[k][i]); }
+        for (int i = 0; i < VN; ++i) { part[c + i] = ag[k][i]; part[d + c + i] = ab[k][i]; }
+      }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    atomicAdd(dgamma + c, sm[c]);
-    atomicAdd(dbeta + c, sm[d + c]);
+  const bool vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0;
+  if (vec) {
+    for (int c = threadIdx.x * 4; c < 2 * d; c += blockDim.x * 4) {
+      float4 a = *reinterpret_cast<const float4*>(sm + c);
+#pragma unroll
+      for (int q = 1; q < NORM_WARPS; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(sm + (size_t)q * 2 * d + c);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      float* dst = c < d ? dgamma + c : dbeta + (c - d);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+    }
+  } else {
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < NORM_WARPS; ++q) a += sm[(size_t)q * 2 * d + c];
+      atomicAdd(c < d ? dgamma + c : dbeta + (c - d), a);
+    }
   }
 }
 
@@ -292,7 +311,7 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
                       const float* __restrict__ rstd, int ndir, int B, int L, int di, T* __restrict__ dy,
                       T* __restrict__ dzx, float* __restrict__ dw) {
   pdl_enter();
-  extern __shared__ float sm[];                                     // [di]
+  extern __shared__ float sm[];                                     // [NORM_WARPS][di]
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const long long T_ = (long long)B * L;
   const int dir = blockIdx.y;
@@ -356,18 +375,38 @@ gated_norm_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ y, const
       }
     }
   }
-  for (int c = threadIdx.x; c < di; c += blockDim.x) sm[c] = 0.f;
-  __syncthreads();
+  // dw: per-warp partial sums in shared memory, one thread per column quad sums them and issues one vector reduction
+  {
+    float* part = sm + (size_t)wi * di;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = (k * 32 + lane) * VN;
-    if (c < di) {
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * VN;
+      if (c < di) {
 #pragma unroll
-      for (int i = 0; i < VN; ++i) atomicAdd(&sm[c + i], aw[k][i]);
+        for (int i = 0; i < VN; ++i) part[c + i] = aw[k][i];
+      }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < di; c += blockDim.x) atomicAdd(dw + (long long)dir * di + c, sm[c]);
+  float* dwr = dw + (long long)dir * di;
+  if (di % 4 == 0 && (reinterpret_cast<uintptr_t>(dwr) & 15) == 0) {
+    for (int c = threadIdx.x * 4; c < di; c += blockDim.x * 4) {
+      float4 a = *reinterpret_cast<const float4*>(sm + c);
+#pragma unroll
+      for (int q = 1; q < NORM_WARPS; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(sm + (size_t)q * di + c);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwr + c), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+    }
+  } else {
+    for (int c = threadIdx.x; c < di; c += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < NORM_WARPS; ++q) a += sm[(size_t)q * di + c];
+      atomicAdd(dwr + c, a);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -523,9 +562,10 @@ extern "C" int hnb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, in
   const int vn = v4 ? 4 : 1;
   const int nv = cdiv(d, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "layernorm_bwd: d=%d too large", d);
-  const size_t smem = 2 * (size_t)d * sizeof(float);
-#define RUN2(A, Bx, C, VN, NV) hnb::launch_pdl(layernorm_bwd_kernel<A, Bx, C, VN, NV>, dim3(norm_grid(layernorm_bwd_kernel<A, Bx, C, VN, NV>, rows, smem)), dim3(\
-      NORM_WARPS * 32), smem, st, (const A*)dy, (const Bx*)x, gamma, mean, rstd, (const C*)dres, rows, d, (C*)dx, dgamma, dbeta)
+  const size_t smem = (size_t)NORM_WARPS * 2 * d * sizeof(float);
+#define RUN2(A, Bx, C, VN, NV) do { if (smem > 48 * 1024) HNB_CUDA_CALL(hnb_set_max_smem((const void*)layernorm_bwd_kernel<A, Bx, C, VN, NV>, (int)smem)); \
+  hnb::launch_pdl(layernorm_bwd_kernel<A, Bx, C, VN, NV>, dim3(norm_grid(layernorm_bwd_kernel<A, Bx, C, VN, NV>, rows, smem)), dim3(\
+      NORM_WARPS * 32), smem, st, (const A*)dy, (const Bx*)x, gamma, mean, rstd, (const C*)dres, rows, d, (C*)dx, dgamma, dbeta); } while (0)
 #define RUN(A, Bx, C, VN)                                                                  \
   do {                                                                                     \
     if (nv <= 2) RUN2(A, Bx, C, VN, 2); else if (nv <= 3) RUN2(A, Bx, C, VN, 3);           \
@@ -587,9 +627,10 @@ extern "C" int hnb_gated_norm_bwd(const void* dout, const void* y, const void* z
   const int vn = v8 ? 8 : (v4 ? 4 : 1);
   const int nv = cdiv(di, 32 * vn);
   HNB_CHECK_ARG(nv <= 16, "gated_norm_bwd: d_inner=%d too large", di);
-  const size_t smem = (size_t)di * sizeof(float);
-#define RUN2(T, VN, NV) hnb::launch_pdl(gated_norm_bwd_kernel<T, VN, NV>, dim3(dim3(std::max(1, norm_grid(gated_norm_bwd_kernel<T, VN, NV>, rows * ndir, smem) / ndir), ndir)), dim3(\
-      NORM_WARPS * 32), smem, st, (const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w)
+  const size_t smem = (size_t)NORM_WARPS * di * sizeof(float);
+#define RUN2(T, VN, NV) do { if (smem > 48 * 1024) HNB_CUDA_CALL(hnb_set_max_smem((const void*)gated_norm_bwd_kernel<T, VN, NV>, (int)smem)); \
+  hnb::launch_pdl(gated_norm_bwd_kernel<T, VN, NV>, dim3(dim3(std::max(1, norm_grid(gated_norm_bwd_kernel<T, VN, NV>, rows * ndir, smem) / ndir), ndir)), dim3(\
+      NORM_WARPS * 32), smem, st, (const T*)dout, (const T*)y, (const T*)zxbcdt, ldz, dstride, lengths, norm_w, rstd, ndir, B, L, di, (T*)dy, (T*)dzxbcdt, dnorm_w); } while (0)
 #define RUN(T, VN)                                                             \
   do {                                                                         \
     if (nv <= 1) RUN2(T, VN, 1); else if (nv <= 2) RUN2(T, VN, 2);             \
