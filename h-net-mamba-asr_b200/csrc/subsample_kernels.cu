@@ -17,12 +17,18 @@ namespace hnb {
 
 constexpr int SUB_RB = 8;            // (b, t) rows per block
 
-template <int CPT>
-__global__ void __launch_bounds__(256)
+// PK (F even): the nine taps of a pixel are consumed as PAIRS on the packed fp32 pipe of sm_100 (FFMA2): (tap 0, tap 1),
+// (3, 4), (6, 7) are aligned 8-byte shared-memory loads, (2, 5) is assembled from two 4-byte loads, tap 8 stays scalar: 4 FFMA2 +
+// 1 FFMA + 1 FADD and 6 loads per output instead of 9 FFMA and 9 loads, with the same registers (the channel-pair form tried
+// before, DESIGN.md section 9, needed duplicated inputs and lost the occupancy).  Both kernels are issue-bound at their
+// occupancy (ncu: issue slots 71-74 % busy, FMA pipe ~35 %); measured, the pairs pay in the backward (559 -> 507 us) and not
+// in the forward (354 -> 397 us), so only the backward uses them by default.
+template <int CPT, bool PK>
+__global__ void __launch_bounds__(256, PK ? 4 : 1)
 sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B, int T,
                      int F, int C, int T1, int F1, __nv_bfloat16* __restrict__ out) {
   pdl_enter();
-  extern __shared__ float s_in[];                       // [3][F]
+  extern __shared__ __align__(16) float s_in[];         // [3][F]
   const int CG = C / CPT;                               // threads per pixel
   const int cgp = threadIdx.x % CG, pl = threadIdx.x / CG, PX = blockDim.x / CG;
   const int c0 = cgp * CPT;
@@ -40,16 +46,31 @@ sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) s_in[i] = x[((long long)b * T + 2 * t + i / F) * F + i % F];
     __syncthreads();
     for (int f = pl; f < F1; f += PX) {
-      float xin[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
       float o[CPT];
+      if constexpr (PK) {
+        const float2 p0 = *reinterpret_cast<const float2*>(s_in + 2 * f), p1 = *reinterpret_cast<const float2*>(s_in + F + 2 * f),
+                     p2 = *reinterpret_cast<const float2*>(s_in + 2 * F + 2 * f);
+        const float2 q = make_float2(s_in[2 * f + 2], s_in[F + 2 * f + 2]);
+        const float x8 = s_in[2 * F + 2 * f + 2];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        float a = bs[i];
+        for (int i = 0; i < CPT; ++i) {
+          float2 a = __ffma2_rn(make_float2(wt[i][0], wt[i][1]), p0, make_float2(bs[i], 0.f));
+          a = __ffma2_rn(make_float2(wt[i][3], wt[i][4]), p1, a);
+          a = __ffma2_rn(make_float2(wt[i][6], wt[i][7]), p2, a);
+          a = __ffma2_rn(make_float2(wt[i][2], wt[i][5]), q, a);
+          o[i] = fmaxf(fmaf(wt[i][8], x8, a.x) + a.y, 0.f);
+        }
+      } else {
+        float xin[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) a = fmaf(wt[i][k], xin[k], a);
-        o[i] = fmaxf(a, 0.f);
+        for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          float a = bs[i];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a = fmaf(wt[i][k], xin[k], a);
+          o[i] = fmaxf(a, 0.f);
+        }
       }
       stv<__nv_bfloat16, CPT>(out + ((r * F1 + f) * C + c0), o);
     }
@@ -59,14 +80,14 @@ sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
 // backward: dA1 and the saved output A1 (both NHWC, bf16) -> dW1 [C, 9], db1 [C] (fp32, accumulated).  The ReLU mask
 // is A1 > 0, as in the reference's threshold_backward; the input needs no gradient.  A block reduces its rows in
 // registers, then across its pixel lanes through shared memory, then issues 10 vector reductions per channel quad.
-template <int CPT, int NT, int MINB>
+template <int CPT, int NT, int MINB, bool PK>
 __global__ void __launch_bounds__(NT, MINB)
 sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ a1, const __nv_bfloat16* __restrict__ dout,
                      int B, int T, int F, int C, int T1, int F1, int rows_per_block, float* __restrict__ dw,
                      float* __restrict__ db) {
   pdl_enter();
   static_assert(CPT == 4, "vector reductions below assume channel quads");
-  extern __shared__ float s_in[];                       // [3][F], then reused for the block reduction
+  extern __shared__ __align__(16) float s_in[];         // [3][F], then reused for the block reduction
   const int CG = C / CPT;
   const int cgp = threadIdx.x % CG, pl = threadIdx.x / CG, PX = blockDim.x / CG;
   const int c0 = cgp * CPT;
@@ -111,9 +132,7 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
       for (int u = 0; u < 4; ++u) {
         const int f = pl + (4 * g + u) * PX;
         if (f >= F1) break;
-        float xin[9], gq[CPT], a[CPT];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
+        float gq[CPT], a[CPT];
         {
           const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gr[u]);
           const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ar[u]);
@@ -122,12 +141,34 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
           gq[0] = g0.x; gq[1] = g0.y; gq[2] = g1.x; gq[3] = g1.y;
           a[0] = a0.x; a[1] = a0.y; a[2] = a1v.x; a[3] = a1v.y;
         }
+        if constexpr (PK) {                               // tap pairs on the packed fp32 pipe (see the forward)
+          const float2 p0 = *reinterpret_cast<const float2*>(s_in + 2 * f), p1 = *reinterpret_cast<const float2*>(s_in + F + 2 * f),
+                       p2 = *reinterpret_cast<const float2*>(s_in + 2 * F + 2 * f);
+          const float2 q = make_float2(s_in[2 * f + 2], s_in[F + 2 * f + 2]);
+          const float x8 = s_in[2 * F + 2 * f + 2];
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          const float gi = a[i] > 0.f ? gq[i] : 0.f;
-          gb[i] += gi;
+          for (int i = 0; i < CPT; ++i) {
+            const float gi = a[i] > 0.f ? gq[i] : 0.f;
+            const float2 g2 = make_float2(gi, gi);
+            gb[i] += gi;
+            float2 t;
+            t = __ffma2_rn(g2, p0, make_float2(gw[i][0], gw[i][1])); gw[i][0] = t.x; gw[i][1] = t.y;
+            t = __ffma2_rn(g2, p1, make_float2(gw[i][3], gw[i][4])); gw[i][3] = t.x; gw[i][4] = t.y;
+            t = __ffma2_rn(g2, p2, make_float2(gw[i][6], gw[i][7])); gw[i][6] = t.x; gw[i][7] = t.y;
+            t = __ffma2_rn(g2, q, make_float2(gw[i][2], gw[i][5])); gw[i][2] = t.x; gw[i][5] = t.y;
+            gw[i][8] = fmaf(gi, x8, gw[i][8]);
+          }
+        } else {
+          float xin[9];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) gw[i][k] = fmaf(gi, xin[k], gw[i][k]);
+          for (int k = 0; k < 9; ++k) xin[k] = s_in[(k / 3) * F + 2 * f + k % 3];
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            const float gi = a[i] > 0.f ? gq[i] : 0.f;
+            gb[i] += gi;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) gw[i][k] = fmaf(gi, xin[k], gw[i][k]);
+          }
         }
       }
     }
@@ -236,14 +277,20 @@ extern "C" int hnb_subsample_conv1_fwd(const float* feats, const float* w, const
   if (rc) return rc;
   const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
   const long long rows = (long long)B * T1;
+  // packed tap pairs: measured SLOWER in the forward (397 vs 354 us: the kernel is not FMA-issue-bound once a store follows every 20
+  // instructions), faster in the backward (507 vs 559 us); off here unless HNB_SUB_FWD_PACKED=1
+  static const bool pk_env = [] { const char* e = getenv("HNB_SUB_FWD_PACKED"); return e && atoi(e) == 1; }();
+  const bool pk = pk_env && F % 2 == 0;                  // packed tap pairs need 8-byte aligned input pairs
   static const int cpt = [] { const char* e = getenv("HNB_SUB_FWD_CPT"); return e && atoi(e) == 8 ? 8 : 4; }();
   if (cpt == 4) {                                        // half the taps per thread, 64 registers, five resident blocks: 401 -> 334 us (HNB_SUB_FWD_CPT=8: the former kernel)
     const int CG = C / 4, PX = 256 / CG > 0 ? 256 / CG : 1;
-    hnb::launch_pdl(sub_conv1_fwd_kernel<4>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
+    if (pk) hnb::launch_pdl(sub_conv1_fwd_kernel<4, true>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
+        feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
+    else hnb::launch_pdl(sub_conv1_fwd_kernel<4, false>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
         feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
   } else {
     const int CG = C / 8, PX = 256 / CG > 0 ? 256 / CG : 1;
-    hnb::launch_pdl(sub_conv1_fwd_kernel<8>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
+    hnb::launch_pdl(sub_conv1_fwd_kernel<8, false>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
         feats, w, bias, B, T, F, C, T1, F1, (__nv_bfloat16*)out);
   }
   HNB_LAUNCH_CHECK("subsample_conv1_fwd");
@@ -264,6 +311,8 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   static const int nt = [] { const char* e = getenv("HNB_SUB_BWD_THREADS"); return e && atoi(e) == 384 ? 384 : 256; }();   // 384-thread blocks measured slower (658 vs 626 us)
+  static const bool pk_env = [] { const char* e = getenv("HNB_SUB_PACKED"); return !(e && atoi(e) == 0); }();
+  const bool pk = pk_env && F % 2 == 0;
   static const int minb = [] { const char* e = getenv("HNB_SUB_BWD_MINB"); return e && atoi(e) == 2 ? 2 : 3; }();   // 80 registers (12 bytes spilled), four resident 192-thread blocks: 556 us; 114 registers, no spill: 621 us
   const int CG = C / 4, PX = nt / CG > 0 ? nt / CG : 1;
   static const int bpsm = [] { const char* e = getenv("HNB_SUB_BWD_BLOCKS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 12; }();   // measured 3 / 4 / 6 / 8 / 12 / 16 per SM: 705 / 617 / 626 / 596 / 585 / 597 us
@@ -275,16 +324,20 @@ extern "C" int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const
   const size_t red = (size_t)(PX > 1 ? PX - 1 : 0) * CG * 40 * sizeof(float);
   if (red > smem) smem = red;
   if (nt == 384 && CG * PX <= 384) {                     // two resident blocks of up to 384 threads: a third more bytes in flight per SM
-    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 384, 2>, (int)smem));
-    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 384, 2>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 384, 2, false>, (int)smem));
+    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 384, 2, false>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
+        (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
+  } else if (minb != 2 && pk) {
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 256, 3, true>, (int)smem));
+    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 256, 3, true>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
         (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
   } else if (minb != 2) {
-    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 256, 3>, (int)smem));
-    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 256, 3>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 256, 3, false>, (int)smem));
+    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 256, 3, false>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
         (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
   } else {
-    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 256, 2>, (int)smem));
-    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 256, 2>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
+    HNB_CUDA_CALL(hnb_set_max_smem((const void*)sub_conv1_bwd_kernel<4, 256, 2, false>, (int)smem));
+    hnb::launch_pdl(sub_conv1_bwd_kernel<4, 256, 2, false>, dim3(blocks), dim3(CG * PX), smem, (cudaStream_t)stream, feats, (const __nv_bfloat16*)a1,
         (const __nv_bfloat16*)dout, B, T, F, C, T1, F1, rpb, dw, db);
   }
   HNB_LAUNCH_CHECK("subsample_conv1_bwd");
