@@ -23,10 +23,10 @@ constexpr int SUB_RB = 8;            // (b, t) rows per block
 // before, DESIGN.md section 9, needed duplicated inputs and lost the occupancy).  Both kernels are issue-bound at their
 // occupancy (ncu: issue slots 71-74 % busy, FMA pipe ~35 %); measured, the pairs pay in the backward (559 -> 507 us) and not
 // in the forward (354 -> 397 us), so only the backward uses them by default.
-template <int CPT, bool PK>
+template <int CPT, bool PK, typename TO = __nv_bfloat16>
 __global__ void __launch_bounds__(256, PK ? 4 : 1)
 sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B, int T,
-                     int F, int C, int T1, int F1, __nv_bfloat16* __restrict__ out) {
+                     int F, int C, int T1, int F1, TO* __restrict__ out) {
   pdl_enter();
   extern __shared__ __align__(16) float s_in[];         // [3][F]
   const int CG = C / CPT;                               // threads per pixel
@@ -72,7 +72,7 @@ sub_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
           o[i] = fmaxf(a, 0.f);
         }
       }
-      stv<__nv_bfloat16, CPT>(out + ((r * F1 + f) * C + c0), o);
+      stv<TO, CPT>(out + ((r * F1 + f) * C + c0), o);
     }
   }
 }
@@ -210,6 +210,18 @@ sub_conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
 // ---- bias + ReLU over an NHWC tensor viewed as [rows, C] (the second convolution's output) ----------------------
 // forward: in place.  backward: dpre = dout * [out > 0] and db[c] += sum_rows dpre in the same pass (ATen ran a strided
 // broadcast add, a clamp, a threshold_backward and a 116 M-element bf16 column reduction: four passes each way).
+// fp32 twin (decode: the second convolution's fp32 NHWC output), 4 channels = 16 bytes per thread
+__global__ void __launch_bounds__(256)
+bias_relu_fwd_f32_kernel(float* __restrict__ x, const float* __restrict__ bias, long long n4, int C4) {
+  pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % C4));
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 bias_relu_fwd_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ bias, long long rows, int C) {
   pdl_enter();
@@ -267,6 +279,22 @@ static int sub_check(const char* who, int B, int T, int F, int C) {
     set_error("%s: channels must be a multiple of 8, at most 1024 (got %d)", who, C);
     return HNB_ERR_UNSUPPORTED;
   }
+  return HNB_OK;
+}
+
+extern "C" int hnb_subsample_conv1_fwd_dt(const float* feats, const float* w, const float* bias, int B, int T, int F, int C,
+                                          void* out, int out_dtype, void* stream) {
+  HNB_CHECK_ARG(out_dtype == HNB_BF16 || out_dtype == HNB_F32, "subsample_conv1_fwd: output dtype must be bf16 or fp32");
+  if (out_dtype == HNB_BF16) return hnb_subsample_conv1_fwd(feats, w, bias, B, T, F, C, out, stream);
+  HNB_CHECK_ARG(feats && w && bias && out, "subsample_conv1_fwd: null pointer");
+  int rc = sub_check("subsample_conv1_fwd", B, T, F, C);
+  if (rc) return rc;
+  const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
+  const long long rows = (long long)B * T1;
+  const int CG = C / 4, PX = 256 / CG > 0 ? 256 / CG : 1;   // fp32 output (decode): 4 channels = one 16-byte store per thread and pixel
+  hnb::launch_pdl(sub_conv1_fwd_kernel<4, false, float>, dim3(cdiv(rows, SUB_RB)), dim3(CG * PX), 3 * F * sizeof(float), (cudaStream_t)stream,
+      feats, w, bias, B, T, F, C, T1, F1, (float*)out);
+  HNB_LAUNCH_CHECK("subsample_conv1_fwd");
   return HNB_OK;
 }
 
@@ -364,6 +392,22 @@ extern "C" int hnb_bias_relu_fwd(void* x, const float* bias, long long rows, int
   if (rc) return rc;
   hnb::launch_pdl(bias_relu_fwd_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (__nv_bfloat16*)x, bias, rows, C);
   HNB_LAUNCH_CHECK("bias_relu_fwd");
+  return HNB_OK;
+}
+
+extern "C" int hnb_bias_relu_fwd_f32(float* x, const float* bias, long long rows, int C, void* stream) {
+  HNB_CHECK_ARG(x && bias && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+                "bias_relu_fwd_f32: null or misaligned pointer");
+  HNB_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0, "bias_relu_fwd_f32: C must be a multiple of 4");
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const long long n4 = rows * (C / 4);
+  const long long want = (n4 + 255) / 256;
+  const int blocks = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+  hnb::launch_pdl(bias_relu_fwd_f32_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, bias, n4, C / 4);
+  HNB_LAUNCH_CHECK("bias_relu_fwd_f32");
   return HNB_OK;
 }
 

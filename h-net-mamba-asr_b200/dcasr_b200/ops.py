@@ -321,13 +321,17 @@ def subsample_conv1_supported(C: int) -> bool:
     return C % 8 == 0 and C <= 1024
 
 
-def subsample_conv1_fwd(feats, w, b):
-    """feats [B, T, F] fp32, w [C, 1, 3, 3] fp32, b [C] -> relu(conv) as bf16 [B, C, T1, F1] in channels_last memory."""
+def subsample_conv1_fwd(feats, w, b, out_dtype=torch.bfloat16):
+    """feats [B, T, F] fp32, w [C, 1, 3, 3] fp32, b [C] -> relu(conv) as bf16 (training) or fp32 (decode) [B, C, T1, F1] in
+    channels_last memory."""
     B, T, F = feats.shape
     C = w.shape[0]
     T1, F1 = (T - 3) // 2 + 1, (F - 3) // 2 + 1
-    out = torch.empty((B, T1, F1, C), dtype=torch.bfloat16, device=feats.device)       # NHWC storage
-    lib().call("subsample_conv1_fwd", feats, w, b, B, T, F, C, out, stream())
+    out = torch.empty((B, T1, F1, C), dtype=out_dtype, device=feats.device)            # NHWC storage
+    if out_dtype == torch.bfloat16:
+        lib().call("subsample_conv1_fwd", feats, w, b, B, T, F, C, out, stream())
+    else:
+        lib().call("subsample_conv1_fwd_dt", feats, w, b, B, T, F, C, out, dtype_code(out_dtype), stream())
     return out.permute(0, 3, 1, 2)                                                      # logical NCHW, channels_last strides
 
 
@@ -342,9 +346,12 @@ def subsample_conv1_bwd(feats, a1, dout):
 
 
 def bias_relu_fwd_(x2d, bias):
-    """x2d [rows, C] bf16 contiguous (an NHWC tensor flattened), in place: relu(x + bias)."""
+    """x2d [rows, C] bf16 (or fp32) contiguous (an NHWC tensor flattened), in place: relu(x + bias)."""
     rows, C = x2d.shape
-    lib().call("bias_relu_fwd", x2d, bias, rows, C, stream())
+    if x2d.dtype == torch.float32:                      # decode: the fp32 twin
+        lib().call("bias_relu_fwd_f32", x2d, bias, rows, C, stream())
+    else:
+        lib().call("bias_relu_fwd", x2d, bias, rows, C, stream())
     return x2d
 
 

@@ -297,6 +297,10 @@ int hnb_umma_selftest(float* max_abs_err_host, void* stream);
  * the layout the tensor-core kernels of the second convolution consume.  C % 8 == 0, C <= 1024. */
 int hnb_subsample_conv1_fwd(const float* feats, const float* w, const float* bias, int B, int T, int F, int C,
                             void* out, void* stream);
+/* The same with the output dtype chosen by the caller (HNB_BF16 as above, or HNB_F32: the fp32 no_grad forward of decoding,
+ * src/dcasr/tasks/decode_task.py:123-151, where the reference runs this layer through cuDNN in fp32). */
+int hnb_subsample_conv1_fwd_dt(const float* feats, const float* w, const float* bias, int B, int T, int F, int C,
+                               void* out, int out_dtype, void* stream);
 /* Backward of the same: a1 (the forward's output) and dout (both bf16, NHWC) -> dw [C, 9] and db [C], ACCUMULATED
  * into pre-zeroed, 16-byte aligned fp32 buffers.  ReLU mask = a1 > 0; the input needs no gradient. */
 int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const void* dout, int B, int T, int F, int C,
@@ -304,6 +308,8 @@ int hnb_subsample_conv1_bwd(const float* feats, const void* a1, const void* dout
 
 /* bias + ReLU of the second convolution's output (encoder.py:61-62), bf16 NHWC viewed as [rows, C], IN PLACE */
 int hnb_bias_relu_fwd(void* x, const float* bias, long long rows, int C, void* stream);
+/* the same on an fp32 tensor (the fp32 no_grad forward of decoding); C % 4 == 0, x and bias 16-byte aligned */
+int hnb_bias_relu_fwd_f32(float* x, const float* bias, long long rows, int C, void* stream);
 /* its backward in one pass: dpre = dout * [out > 0] (bf16), db [C] ACCUMULATED (pre-zeroed fp32, 16-byte aligned) */
 int hnb_bias_relu_bwd(const void* dout, const void* out, void* dpre, float* db, long long rows, int C, void* stream);
 

@@ -517,6 +517,38 @@ def test_subsample_conv1_kernels_fp32_reference():
     assert rel_err(dw, w.grad) < 1e-4 and rel_err(db, b.grad) < 1e-4
 
 
+@pytest.mark.parametrize("B,T,C", [(3, 203, 128), (2, 1598, 384)])
+def test_subsample_front_end_fp32_decode_path_vs_reference_ops(B, T, C):
+    """ConvSubsampling4 in fp32 under no_grad (decoding): fused conv1 + ReLU (fp32 NHWC), cuDNN conv2 on that memory, Linear
+    through the fp32-accurate tensor-core GEMM, against the reference's own op sequence on the same module, TF32 off."""
+    import dcasr_b200 as dd
+    torch.manual_seed(0)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sub = dd.ConvSubsampling4(80, C).to(DEV)
+        feats = torch.randn(B, T, 80, device=DEV)
+        lens = torch.tensor([T - 7 * i for i in range(B)], device=DEV)
+        res = {}
+        with torch.no_grad():
+            for fused in (True, False):
+                sub.fused_front_end = fused
+                dd.reset_launch_count()
+                y, ol = sub(feats, lens)
+                res[fused] = (y.clone(), ol.clone(), dd.launch_count())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert res[True][2] >= 2 and res[False][2] == 0            # our conv1 kernel + GEMM ran / the reference sequence launched none of ours
+    assert res[True][0].dtype == torch.float32 and res[True][0].shape == res[False][0].shape
+    assert torch.equal(res[True][1], res[False][1])
+    assert rel_err(res[True][0], res[False][0]) < 1e-5
+    # with gradients enabled the fp32 call keeps the reference op sequence (autograd through nn.Sequential)
+    sub.fused_front_end = True
+    dd.reset_launch_count()
+    y, _ = sub(feats, lens)
+    assert y.requires_grad and dd.launch_count() == 0
+
+
 def test_host_batch_prefetcher_round_trip():
     """Side-stream H2D staging used by bench.py's e2e leg: what pop() returns is what was pushed, and a second push
     before the pop is refused."""
