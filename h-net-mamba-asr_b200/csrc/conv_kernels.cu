@@ -255,7 +255,6 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
   constexpr int RUN = TS * NTILE - 3;
   static_assert(TS > 3, "layout");
   __shared__ float s_red[CONV_SEG - 1][5 * VN][CONV_CT];      // parameter-gradient partials of segments 1..3
-  __shared__ float s_dtb[64];
   const int ct = threadIdx.x % CONV_CT, sg = threadIdx.x / CONV_CT;
   const int dir = blockIdx.z / B, bi = blockIdx.z % B;
   const int C = di + 2 * N;
@@ -269,7 +268,6 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
   const int c = (blockIdx.x * CONV_CT + ct) * VN;
   const int sb = (blockIdx.y * CONV_SEG + sg) * RUN;
   const int se = min(sb + RUN, L);
-  if (threadIdx.x < 64) s_dtb[threadIdx.x] = 0.f;
 
   float gw[VN][4], gb[VN];
 #pragma unroll
@@ -465,19 +463,34 @@ conv_bwd_kernel(const T* __restrict__ zx, const T* __restrict__ dxc, long long l
       for (int i = 0; i < VN; ++i) atomicAdd(dconv_b + (long long)dir * C + c + i, gb[i]);
     }
   }
-  // dt: d raw = ddt * sigmoid(raw + bias); one column block per (row, segment group) does it
+  // dt: d raw = ddt * sigmoid(raw + bias); one column block per (row, segment group) does it.  A thread keeps ONE head (tid % H)
+  // and walks positions with stride blockDim / H, so its d dt_bias contribution is a private sum; the sums meet through the
+  // (by now idle) parameter-gradient scratch in shared memory.  (The first version added every element into 12 shared-memory
+  // floats: 1.4 k CAS-loop atomics on 12 addresses per block, on a quarter of the blocks.)
   if (blockIdx.x == 0) {
     const int s_lo = blockIdx.y * CONV_SEG * RUN, s_hi = min(s_lo + CONV_SEG * RUN, L);
-    for (int idx = threadIdx.x; idx < (s_hi - s_lo) * H; idx += blockDim.x) {
-      const int s = s_lo + idx / H, hh = idx % H;
-      const long long nat = (long long)scan_to_nat(dir, s, len) * ldz + doff + hh;
-      const float raw = to_f(rowbase[nat]);
-      const float g = ddt[(sbase + s) * H + hh] * sigmoid_f(raw + dt_bias[dir * H + hh]);
-      drowbase[nat] = from_f<T>(g);
-      atomicAdd(&s_dtb[hh], g);
+    const int G = blockDim.x / H;                                   // position lanes (H <= 64: at least 4)
+    const int hh = threadIdx.x % H, g0 = threadIdx.x / H;
+    float part = 0.f;
+    if (g0 < G) {
+      const float bias_h = dt_bias[dir * H + hh];
+      for (int s = s_lo + g0; s < s_hi; s += G) {
+        const long long nat = (long long)scan_to_nat(dir, s, len) * ldz + doff + hh;
+        const float raw = to_f(rowbase[nat]);
+        const float g = ddt[(sbase + s) * H + hh] * sigmoid_f(raw + bias_h);
+        drowbase[nat] = from_f<T>(g);
+        part += g;
+      }
     }
+    __syncthreads();                                                // s_red is no longer read by segment 0
+    float* scratch = &s_red[0][0][0];                               // >= 256 floats
+    scratch[threadIdx.x] = g0 < G ? part : 0.f;
     __syncthreads();
-    if (threadIdx.x < H) atomicAdd(ddt_bias + dir * H + threadIdx.x, s_dtb[threadIdx.x]);
+    if (threadIdx.x < H) {
+      float a = 0.f;
+      for (int g = 0; g < G; ++g) a += scratch[g * H + threadIdx.x];
+      atomicAdd(ddt_bias + dir * H + threadIdx.x, a);
+    }
   }
 }
 
